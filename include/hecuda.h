@@ -1,0 +1,128 @@
+/*
+ * hecuda.h -- C ABI of the B200-native RNS-BFV polynomial-arithmetic engine (libhecuda.so).
+ *
+ * This is the drop-in boundary for the hot path of apple/swift-homomorphic-encryption: a SwiftPM C target placed
+ * beside Sources/CUtil (the reference's only C target, Package.swift:100-105, Sources/CUtil/zeroize.h:20-26) exposes
+ * this header; an in-package overlay of Bfv<UInt64> calls it from the HeScheme entry points listed below
+ * (INTEGRATION.md shows the Swift side).  Every entry point cites the reference interface it replaces, with paths
+ * relative to the reference checkout.
+ *
+ * Conventions
+ *   - All polynomial data is unsigned 64-bit, little-endian, laid out exactly like the reference's
+ *     Array2d<UInt64> (Sources/HomomorphicEncryption/Array2d.swift:19-29,115-123): a polynomial is `rows x N`
+ *     row-major, row i holding the residues mod the i-th modulus; a ciphertext is its polynomials back to back
+ *     (Ciphertext.polys, Ciphertext.swift:18-28); a batch is ciphertexts back to back.
+ *     Coeff format = coefficient order, Eval format = the reference's bit-reversed NTT order.
+ *   - Every value read or written is the canonical residue in [0, q_i) (PolyRq.swift:36,85-95).
+ *   - Pointers are borrowed for the duration of the call only.  Functions without a `_device` suffix take HOST
+ *     pointers and return when the outputs are complete; `_device` variants take device pointers on the current
+ *     device and enqueue on `stream` (a cudaStream_t passed as void*; NULL = the legacy default stream) without
+ *     synchronizing.
+ *   - Return value: HECUDA_OK or a negative status; hecuda_last_error() gives the message for the calling thread
+ *     (maps onto the reference's `throws HeError`, Sources/HomomorphicEncryption/Error.swift:17-54).
+ *   - All entry points are thread-safe (HeScheme statics are called from concurrent TaskGroup tasks,
+ *     Sources/HomomorphicEncryption/Util.swift:141-173); contexts and keys are immutable after creation.
+ */
+#ifndef HECUDA_H
+#define HECUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hecuda_context hecuda_context; /* Context<Bfv<UInt64>>, Context.swift:19 */
+typedef struct hecuda_evk hecuda_evk;         /* EvaluationKey<Bfv<UInt64>>, Keys.swift:66-99,222 */
+
+enum {
+    HECUDA_OK = 0,
+    HECUDA_ERR_INVALID_ARGUMENT = -1,  /* HeError.invalidCiphertext / invalidPolyContext / invalidDegree ... */
+    HECUDA_ERR_UNSUPPORTED = -2,       /* HeError.unsupportedHeOperation */
+    HECUDA_ERR_CUDA = -3,              /* device failure (no reference equivalent) */
+    HECUDA_ERR_NO_DEVICE = -4,         /* the library never falls back to a CPU path */
+    HECUDA_ERR_MISSING_KEY = -5        /* HeError.missingRelinearizationKey / missingGaloisKey */
+};
+
+/* Which RNS base the rows of a polynomial are under (selects the NTT tables per row). */
+enum {
+    HECUDA_BASE_Q = 0,         /* ciphertext context q_0..q_{rows-1}            (Context.swift:102-112) */
+    HECUDA_BASE_Q_BSK = 1,     /* [q_0..q_{L-1}, Bsk], rows = 2L+1               (RnsTool.swift:228-233) */
+    HECUDA_BASE_KEYSWITCH = 2  /* q_0..q_{rows-2}, q_ks                          (Context.swift:114-127) */
+};
+
+int32_t hecuda_version(void);
+const char *hecuda_last_error(void);
+int32_t hecuda_device_count(int32_t *count);
+int32_t hecuda_set_device(int32_t device); /* one process (or thread) per GPU; contexts belong to a device */
+
+/* Pinned host buffers for the host-pointer entry points (pageable memory works too, but cannot overlap copies). */
+int32_t hecuda_host_alloc(void **ptr, uint64_t bytes);
+int32_t hecuda_host_free(void *ptr);
+int32_t hecuda_host_register(void *ptr, uint64_t bytes); /* pin an existing allocation, e.g. a Swift array buffer */
+int32_t hecuda_host_unregister(void *ptr);
+
+/* Context<Bfv<UInt64>>.init(encryptionParameters:)  -- Context.swift:94-143.
+ * coefficient_moduli = q_0..q_{L-1}, q_ks (the last one is reserved for key switching, Context.swift:102-107);
+ * all must be NTT-friendly primes < 2^62.  Builds NTT tables (PolyRq+Ntt.swift:118-169), the BEHZ base and
+ * constants (RnsTool.swift:30-33,132-251) and key-/mod-switch constants (PolyContext.swift:108-111). */
+int32_t hecuda_context_create(int64_t poly_degree, const uint64_t *coefficient_moduli, int32_t moduli_count,
+                              uint64_t plaintext_modulus, hecuda_context **out);
+int32_t hecuda_context_destroy(hecuda_context *ctx);
+/* Introspection used by the parity tests (the reference exposes the same values as public lets). */
+int32_t hecuda_context_ciphertext_moduli_count(const hecuda_context *ctx, int32_t *count);
+int32_t hecuda_context_bsk_moduli(const hecuda_context *ctx, uint64_t *out, int32_t capacity, int32_t *count);
+/* rootOfUnityPowers / inverse powers of `modulus` in the reference's bit-reversed order (PolyRq+Ntt.swift:125-137);
+ * inverse table is indexed like the forward one (inv[i] = roots[i]^-1). */
+int32_t hecuda_context_root_tables(const hecuda_context *ctx, uint64_t modulus, uint64_t *roots, uint64_t *inverse_roots);
+
+/* PolyRq.forwardNtt() / inverseNtt() -- PolyRq+Ntt.swift:230,541 (PolyContext.forwardNtt(poly:) :209-222,
+ * inverseNtt(poly:) :524-533), batched: data = poly_count x row_count x N, in place. */
+int32_t hecuda_ntt_forward(const hecuda_context *ctx, int32_t base, uint64_t *data, int32_t row_count, int64_t poly_count);
+int32_t hecuda_ntt_inverse(const hecuda_context *ctx, int32_t base, uint64_t *data, int32_t row_count, int64_t poly_count);
+int32_t hecuda_ntt_forward_device(const hecuda_context *ctx, int32_t base, uint64_t *data, int32_t row_count,
+                                  int64_t poly_count, void *stream);
+int32_t hecuda_ntt_inverse_device(const hecuda_context *ctx, int32_t base, uint64_t *data, int32_t row_count,
+                                  int64_t poly_count, void *stream);
+/* PolyContext.forwardNtt(dataPtr:modulus:) -- PolyRq+Ntt.swift:329-347: rows of N residues, all mod `modulus`. */
+int32_t hecuda_ntt_forward_rows(const hecuda_context *ctx, uint64_t modulus, uint64_t *data, int64_t row_count);
+int32_t hecuda_ntt_inverse_rows(const hecuda_context *ctx, uint64_t modulus, uint64_t *data, int64_t row_count);
+
+/* Bfv.mulAssign(_:_:) -- Bfv/Bfv+Multiply.swift:18-21 (multiplyWithoutScaling :63-85 + dropExtendedBase :31-48).
+ * lhs, rhs: batch x 2 x L x N (Coeff, top level, correction factor 1); out: batch x 3 x L x N (Coeff).
+ * Ciphertexts below the top level are refused (HECUDA_ERR_UNSUPPORTED; DESIGN.md "levels"). */
+int32_t hecuda_bfv_multiply(const hecuda_context *ctx, const uint64_t *lhs, const uint64_t *rhs, uint64_t *out,
+                            int64_t batch);
+int32_t hecuda_bfv_multiply_device(const hecuda_context *ctx, const uint64_t *lhs, const uint64_t *rhs, uint64_t *out,
+                                   int64_t batch, void *stream);
+
+/* EvaluationKey upload.  relin_key = the _KeySwitchKey of the relinearization key (Keys.swift:66-99, generated by
+ * Bfv+Keys.swift:58-103): L ciphertexts x 2 polys x K x N in Eval format, K = L + 1 rows under [q_0..q_{L-1}, q_ks]. */
+int32_t hecuda_evk_create(const hecuda_context *ctx, const uint64_t *relin_key, hecuda_evk **out);
+int32_t hecuda_evk_destroy(hecuda_evk *evk);
+/* NCCL-free plumbing for multi-GPU setup: raw device pointer + size of the key so that torch.distributed /
+ * ncclBroadcast can replicate it from rank 0. */
+int32_t hecuda_evk_create_empty(const hecuda_context *ctx, hecuda_evk **out);
+int32_t hecuda_evk_device_buffer(hecuda_evk *evk, void **device_ptr, uint64_t *bytes);
+
+/* Bfv.relinearize(_:using:) -- Bfv/Bfv.swift:201-219 (key switch: Bfv+Keys.swift:123-208).
+ * ct3: batch x 3 x l x N (Coeff), l = moduli_count in [1, L]; out: batch x 2 x l x N (Coeff). */
+int32_t hecuda_bfv_relinearize(const hecuda_context *ctx, const hecuda_evk *evk, const uint64_t *ct3,
+                               int32_t moduli_count, uint64_t *out, int64_t batch);
+int32_t hecuda_bfv_relinearize_device(const hecuda_context *ctx, const hecuda_evk *evk, const uint64_t *ct3,
+                                      int32_t moduli_count, uint64_t *out, int64_t batch, void *stream);
+
+/* Bfv.modSwitchDown(_:) -- Bfv/Bfv.swift:163-171 (PolyRq.divideAndRoundQLast, PolyRq.swift:365-393).
+ * ct: batch x poly_count x l x N (Coeff), l = moduli_count in [2, L]; out: batch x poly_count x (l-1) x N. */
+int32_t hecuda_bfv_mod_switch_down(const hecuda_context *ctx, const uint64_t *ct, int32_t poly_count,
+                                   int32_t moduli_count, uint64_t *out, int64_t batch);
+int32_t hecuda_bfv_mod_switch_down_device(const hecuda_context *ctx, const uint64_t *ct, int32_t poly_count,
+                                          int32_t moduli_count, uint64_t *out, int64_t batch, void *stream);
+
+/* Bookkeeping for bench.py: number of kernel launches issued by this library in the calling process so far. */
+uint64_t hecuda_kernel_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HECUDA_H */

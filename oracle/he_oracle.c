@@ -8,6 +8,7 @@
  */
 #include "he_oracle.h"
 
+#include <malloc.h>
 #include <stdlib.h>
 #include <string.h>
 #ifdef _OPENMP
@@ -799,6 +800,10 @@ struct orc_context {
 
 orc_context *orc_context_create(int64_t n, const uint64_t *coeff_moduli, int32_t nmod, uint64_t t) {
     if (nmod < 2 || nmod > ORC_MAX_MODULI / 2 - 2) return NULL;
+    /* keep the per-call scratch on the heap (no mmap/munmap + page faults per multiply): a fair CPU baseline */
+    mallopt(M_MMAP_THRESHOLD, 1 << 30);
+    mallopt(M_TRIM_THRESHOLD, 1 << 30);
+    mallopt(M_ARENA_MAX, 256);
     orc_context *ctx = (orc_context *)calloc(1, sizeof(orc_context));
     ctx->n = n;
     ctx->L = nmod - 1;

@@ -1,0 +1,585 @@
+// capi.cu -- the C ABI declared in include/hecuda.h.  No torch types, no exceptions across the boundary.
+//
+// Host-pointer entry points run a chunked, double-buffered pipeline (two workspaces on two streams) so that the
+// H2D copy of chunk k+1, the kernels of chunk k and the D2H copy of chunk k-1 overlap when the caller's buffers are
+// pinned.  Device-pointer entry points enqueue on the caller's stream and do not synchronize.
+#include "../../include/hecuda.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "context.hpp"
+#include "kernels.cuh"
+
+namespace hecuda {
+std::atomic<unsigned long long> g_kernel_launches{0};
+}
+
+using namespace hecuda;
+
+namespace {
+
+thread_local std::string tl_error;
+
+int32_t fail(int32_t code, const std::string &msg) {
+    tl_error = msg;
+    return code;
+}
+int32_t cuda_fail(cudaError_t e, const char *what) {
+    return fail(HECUDA_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CK(expr)                                          \
+    do {                                                  \
+        cudaError_t e_ = (expr);                          \
+        if (e_ != cudaSuccess) return cuda_fail(e_, #expr); \
+    } while (0)
+
+// Scratch for one in-flight chunk.  Grows on demand, never shrinks.
+struct Workspace {
+    cudaStream_t stream = nullptr;
+    bool owns_stream = false;
+    u64 *buf[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t cap[6] = {0, 0, 0, 0, 0, 0};
+    cudaError_t reserve(int i, size_t words) {
+        if (cap[i] >= words) return cudaSuccess;
+        if (buf[i]) {
+            cudaError_t e = cudaFree(buf[i]);
+            if (e != cudaSuccess) return e;
+            buf[i] = nullptr;
+            cap[i] = 0;
+        }
+        cudaError_t e = cudaMalloc(&buf[i], words * sizeof(u64));
+        if (e == cudaSuccess) cap[i] = words;
+        return e;
+    }
+    void release() {
+        for (int i = 0; i < 6; ++i)
+            if (buf[i]) cudaFree(buf[i]);
+        if (owns_stream && stream) cudaStreamDestroy(stream);
+    }
+};
+
+}  // namespace
+
+struct hecuda_context {
+    Context *ctx = nullptr;
+    int64_t chunk = 32;  // ciphertexts per pipeline stage
+    std::mutex mu;
+    std::vector<Workspace *> free_ws;  // pooled workspaces (each with its own stream)
+    Workspace *acquire() {
+        std::lock_guard<std::mutex> g(mu);
+        if (!free_ws.empty()) {
+            Workspace *w = free_ws.back();
+            free_ws.pop_back();
+            return w;
+        }
+        Workspace *w = new (std::nothrow) Workspace();
+        if (!w) return nullptr;
+        if (cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking) != cudaSuccess) {
+            delete w;
+            return nullptr;
+        }
+        w->owns_stream = true;
+        return w;
+    }
+    void release(Workspace *w) {
+        std::lock_guard<std::mutex> g(mu);
+        free_ws.push_back(w);
+    }
+};
+
+struct hecuda_evk {
+    const hecuda_context *owner = nullptr;
+    u64 *d_relin = nullptr;  // L x 2 x K x N, Eval
+    size_t words = 0;
+    bool loaded = false;
+};
+
+namespace {
+
+struct WsGuard {
+    hecuda_context *h;
+    Workspace *w;
+    WsGuard(const hecuda_context *hc) : h(const_cast<hecuda_context *>(hc)), w(h->acquire()) {}
+    ~WsGuard() {
+        if (w) h->release(w);
+    }
+};
+
+int32_t check_ctx(const hecuda_context *h) {
+    if (!h || !h->ctx) return fail(HECUDA_ERR_INVALID_ARGUMENT, "invalidContext: null context");
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess) return fail(HECUDA_ERR_NO_DEVICE, "no CUDA device available");
+    if (dev != h->ctx->device) {
+        cudaError_t e = cudaSetDevice(h->ctx->device);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    }
+    return HECUDA_OK;
+}
+
+bool make_map(const Context &c, int32_t base, int32_t rows, NttRowMap &map, std::string &err) {
+    switch (base) {
+        case HECUDA_BASE_Q:
+            if (rows < 1 || rows > c.L) { err = "invalidPolyContext: row_count must be in [1, L] for BASE_Q"; return false; }
+            map = c.map_q(rows);
+            return true;
+        case HECUDA_BASE_Q_BSK:
+            if (rows != 2 * c.L + 1) { err = "invalidPolyContext: BASE_Q_BSK needs 2L+1 rows"; return false; }
+            map = c.map_qbsk();
+            return true;
+        case HECUDA_BASE_KEYSWITCH:
+            if (rows < 2 || rows > c.L + 1) { err = "invalidPolyContext: BASE_KEYSWITCH needs 2..L+1 rows"; return false; }
+            map = c.map_ks(rows - 1);
+            return true;
+        default:
+            err = "invalidPolyContext: unknown base";
+            return false;
+    }
+}
+
+// ---------------------------------------------------------------- device-side op bodies (enqueue only)
+
+// scratch words needed per ciphertext pair / ciphertext
+size_t multiply_scratch_words(const Context &c) { return (size_t)7 * (2 * c.L + 1) * c.n; }
+size_t relinearize_scratch_words(const Context &c, int l) { return (size_t)((l + 1) * l + 2 * (l + 1)) * c.n; }
+
+cudaError_t multiply_chunk(const Context &c, u64 *scratch, const u64 *lhs, const u64 *rhs, u64 *out, int64_t items,
+                           cudaStream_t s) {
+    const int R = 2 * c.L + 1;
+    const size_t poly_words = (size_t)R * c.n;
+    cudaError_t e;
+    u64 *ext = scratch, *ten = scratch + 4 * poly_words * items;
+    const NttRowMap map = c.map_qbsk();
+    // computeBehzPolys for both operands: lift + forward NTT      (Bfv+Multiply.swift:51-57)
+    if ((e = launch_lift(c, lhs, 2, ext, 4, 0, items, s)) != cudaSuccess) return e;
+    if ((e = launch_lift(c, rhs, 2, ext, 4, 2, items, s)) != cudaSuccess) return e;
+    if ((e = launch_ntt_forward(c, map, ext, ext, items * 4 * R, s)) != cudaSuccess) return e;
+    // tensor product                                               (Bfv+Multiply.swift:80-82)
+    if ((e = launch_tensor(c, ext, ten, items, s)) != cudaSuccess) return e;
+    // dropExtendedBase: (* t) folded into the inverse NTT, floor    (Bfv+Multiply.swift:31-48)
+    if ((e = launch_ntt_inverse(c, map, ten, ten, items * 3 * R, true, s)) != cudaSuccess) return e;
+    return launch_floor(c, ten, out, items * 3, s);
+}
+
+cudaError_t relinearize_chunk(const Context &c, u64 *scratch, const u64 *key, const u64 *ct3, int l, u64 *out,
+                              int64_t items, cudaStream_t s) {
+    const size_t dig_words = (size_t)(l + 1) * l * c.n;
+    cudaError_t e;
+    u64 *dig = scratch, *prod = scratch + dig_words * items;
+    const int64_t ct_stride = (int64_t)3 * l * c.n;
+    if ((e = launch_ks_digits(c, ct3 + (int64_t)2 * l * c.n, ct_stride, l, dig, items, s)) != cudaSuccess) return e;
+    if ((e = launch_ntt_forward(c, c.map_ks_digits(l), dig, dig, items * (l + 1) * l, s)) != cudaSuccess) return e;
+    if ((e = launch_ks_mac(c, dig, key, l, prod, items, s)) != cudaSuccess) return e;
+    if ((e = launch_ntt_inverse(c, c.map_ks(l), prod, prod, items * 2 * (l + 1), false, s)) != cudaSuccess) return e;
+    return launch_ks_finish(c, prod, ct3, ct_stride, l, out, items, s);
+}
+
+// Generic double-buffered host pipeline: for each chunk, copy inputs in, run `body`, copy outputs out.
+struct HostIo {
+    const u64 *src;  // host
+    size_t words_per_item;
+};
+template <class Body>
+int32_t host_pipeline(const hecuda_context *h, int64_t batch, int64_t chunk_hint, size_t scratch_words_per_item,
+                      const std::vector<HostIo> &inputs, u64 *host_out, size_t out_words_per_item, Body body) {
+    if (batch == 0) return HECUDA_OK;
+    WsGuard g0(h), g1(h);
+    if (!g0.w || !g1.w) return fail(HECUDA_ERR_CUDA, "could not create a CUDA stream / workspace");
+    Workspace *ws[2] = {g0.w, g1.w};
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(chunk_hint, batch));
+    int k = 0;
+    for (int64_t done = 0; done < batch; done += chunk, ++k) {
+        Workspace &w = *ws[k & 1];
+        const int64_t items = std::min<int64_t>(chunk, batch - done);
+        // Work on one workspace is ordered by its stream; buffers only ever grow (first two iterations).
+        // slot 0 = kernel scratch, slot 4 = staged inputs (back to back), slot 5 = staged output
+        size_t in_words = 0;
+        for (const HostIo &io : inputs) in_words += io.words_per_item * (size_t)items;
+        CK(w.reserve(0, scratch_words_per_item * (size_t)items));
+        CK(w.reserve(4, in_words));
+        CK(w.reserve(5, out_words_per_item * (size_t)items));
+        std::vector<const u64 *> d_in;
+        size_t off = 0;
+        for (const HostIo &io : inputs) {
+            const size_t words = io.words_per_item * (size_t)items;
+            CK(cudaMemcpyAsync(w.buf[4] + off, io.src + io.words_per_item * (size_t)done, words * sizeof(u64),
+                               cudaMemcpyHostToDevice, w.stream));
+            d_in.push_back(w.buf[4] + off);
+            off += words;
+        }
+        cudaError_t e = body(w, d_in, w.buf[5], items);
+        if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
+        CK(cudaMemcpyAsync(host_out + out_words_per_item * (size_t)done, w.buf[5],
+                           out_words_per_item * (size_t)items * sizeof(u64), cudaMemcpyDeviceToHost, w.stream));
+    }
+    CK(cudaStreamSynchronize(ws[0]->stream));
+    CK(cudaStreamSynchronize(ws[1]->stream));
+    return HECUDA_OK;
+}
+
+}  // namespace
+
+// ====================================================================================================== C ABI
+
+extern "C" {
+
+int32_t hecuda_version(void) { return 100; }
+const char *hecuda_last_error(void) { return tl_error.c_str(); }
+
+int32_t hecuda_device_count(int32_t *count) {
+    if (!count) return fail(HECUDA_ERR_INVALID_ARGUMENT, "null count");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        *count = 0;
+        return fail(HECUDA_ERR_NO_DEVICE, std::string("no CUDA device: ") + cudaGetErrorString(e));
+    }
+    *count = n;
+    return HECUDA_OK;
+}
+int32_t hecuda_set_device(int32_t device) {
+    CK(cudaSetDevice(device));
+    return HECUDA_OK;
+}
+
+int32_t hecuda_host_alloc(void **ptr, uint64_t bytes) {
+    if (!ptr) return fail(HECUDA_ERR_INVALID_ARGUMENT, "null ptr");
+    CK(cudaHostAlloc(ptr, bytes, cudaHostAllocDefault));
+    return HECUDA_OK;
+}
+int32_t hecuda_host_free(void *ptr) {
+    CK(cudaFreeHost(ptr));
+    return HECUDA_OK;
+}
+int32_t hecuda_host_register(void *ptr, uint64_t bytes) {
+    CK(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+    return HECUDA_OK;
+}
+int32_t hecuda_host_unregister(void *ptr) {
+    CK(cudaHostUnregister(ptr));
+    return HECUDA_OK;
+}
+
+int32_t hecuda_context_create(int64_t poly_degree, const uint64_t *coefficient_moduli, int32_t moduli_count,
+                              uint64_t plaintext_modulus, hecuda_context **out) {
+    if (!out || !coefficient_moduli) return fail(HECUDA_ERR_INVALID_ARGUMENT, "null argument");
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(HECUDA_ERR_NO_DEVICE, "no CUDA device: libhecuda has no CPU fallback");
+    std::string err;
+    Context *c = Context::create(poly_degree, (const u64 *)coefficient_moduli, moduli_count, plaintext_modulus, err);
+    if (!c) {
+        const bool unsupported = err.rfind("unsupported", 0) == 0;
+        return fail(unsupported ? HECUDA_ERR_UNSUPPORTED : HECUDA_ERR_INVALID_ARGUMENT, err);
+    }
+    hecuda_context *h = new (std::nothrow) hecuda_context();
+    if (!h) {
+        delete c;
+        return fail(HECUDA_ERR_CUDA, "out of host memory");
+    }
+    h->ctx = c;
+    {   // keep stream-ordered scratch cached in the default pool instead of returning it to the OS at every sync
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, c->device) == cudaSuccess) {
+            unsigned long long threshold = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+        }
+    }
+    // pipeline stage size: keep one stage's intermediates (7 R N words per ciphertext pair) near the L2 size
+    const size_t per_item = (size_t)7 * (2 * c->L + 1) * c->n * sizeof(u64);
+    int64_t chunk = (int64_t)((size_t)96 * 1024 * 1024 / per_item);
+    if (const char *env = std::getenv("HECUDA_CHUNK")) chunk = std::atoll(env);
+    h->chunk = std::max<int64_t>(1, std::min<int64_t>(chunk, 4096));
+    *out = h;
+    return HECUDA_OK;
+}
+
+int32_t hecuda_context_destroy(hecuda_context *h) {
+    if (!h) return HECUDA_OK;
+    if (h->ctx) cudaSetDevice(h->ctx->device);
+    cudaDeviceSynchronize();
+    for (Workspace *w : h->free_ws) {
+        w->release();
+        delete w;
+    }
+    delete h->ctx;
+    delete h;
+    return HECUDA_OK;
+}
+
+int32_t hecuda_context_ciphertext_moduli_count(const hecuda_context *h, int32_t *count) {
+    if (!h || !count) return fail(HECUDA_ERR_INVALID_ARGUMENT, "null argument");
+    *count = h->ctx->L;
+    return HECUDA_OK;
+}
+int32_t hecuda_context_bsk_moduli(const hecuda_context *h, uint64_t *out, int32_t capacity, int32_t *count) {
+    if (!h || !count) return fail(HECUDA_ERR_INVALID_ARGUMENT, "null argument");
+    *count = (int32_t)h->ctx->bsk.size();
+    if (out) {
+        if (capacity < *count) return fail(HECUDA_ERR_INVALID_ARGUMENT, "capacity too small");
+        std::memcpy(out, h->ctx->bsk.data(), sizeof(u64) * h->ctx->bsk.size());
+    }
+    return HECUDA_OK;
+}
+int32_t hecuda_context_root_tables(const hecuda_context *h, uint64_t modulus, uint64_t *roots, uint64_t *inverse_roots) {
+    if (!h) return fail(HECUDA_ERR_INVALID_ARGUMENT, "null context");
+    const int s = h->ctx->find_slot(modulus);
+    if (s < 0) return fail(HECUDA_ERR_INVALID_ARGUMENT, "invalidNttModulus: modulus is not part of this context");
+    if (roots) std::memcpy(roots, h->ctx->slots[s].roots.data(), sizeof(u64) * h->ctx->n);
+    if (inverse_roots) std::memcpy(inverse_roots, h->ctx->slots[s].inv_roots.data(), sizeof(u64) * h->ctx->n);
+    return HECUDA_OK;
+}
+
+// ---------------------------------------------------------------- NTT
+
+static int32_t ntt_device(const hecuda_context *h, int32_t base, uint64_t *data, int32_t rows, int64_t polys,
+                          void *stream, bool inverse) {
+    int32_t rc = check_ctx(h);
+    if (rc) return rc;
+    if (polys < 0 || (!data && polys)) return fail(HECUDA_ERR_INVALID_ARGUMENT, "invalid data / poly_count");
+    NttRowMap map;
+    std::string err;
+    if (!make_map(*h->ctx, base, rows, map, err)) return fail(HECUDA_ERR_INVALID_ARGUMENT, err);
+    cudaError_t e = inverse ? launch_ntt_inverse(*h->ctx, map, (u64 *)data, (u64 *)data, polys * rows, false,
+                                                 (cudaStream_t)stream)
+                            : launch_ntt_forward(*h->ctx, map, (u64 *)data, (u64 *)data, polys * rows,
+                                                 (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "ntt launch");
+    return HECUDA_OK;
+}
+int32_t hecuda_ntt_forward_device(const hecuda_context *h, int32_t base, uint64_t *data, int32_t rows, int64_t polys,
+                                  void *stream) {
+    return ntt_device(h, base, data, rows, polys, stream, false);
+}
+int32_t hecuda_ntt_inverse_device(const hecuda_context *h, int32_t base, uint64_t *data, int32_t rows, int64_t polys,
+                                  void *stream) {
+    return ntt_device(h, base, data, rows, polys, stream, true);
+}
+
+static int32_t ntt_host(const hecuda_context *h, const NttRowMap &map, uint64_t *data, size_t words_per_item,
+                        int64_t items, int64_t rows_per_item, bool inverse) {
+    const Context &c = *h->ctx;
+    std::vector<HostIo> in = {{(const u64 *)data, words_per_item}};
+    // NTT items are single polynomials: stage ~32 MB per pipeline step
+    const int64_t chunk = std::max<int64_t>(1, (int64_t)((size_t)4 * 1024 * 1024 / std::max<size_t>(1, words_per_item)));
+    return host_pipeline(h, items, chunk, 0, in, (u64 *)data, words_per_item,
+                         [&](Workspace &w, const std::vector<const u64 *> &d_in, u64 *d_out, int64_t n_items) {
+                             return inverse ? launch_ntt_inverse(c, map, d_in[0], d_out, n_items * rows_per_item, false,
+                                                                 w.stream)
+                                            : launch_ntt_forward(c, map, d_in[0], d_out, n_items * rows_per_item,
+                                                                 w.stream);
+                         });
+}
+int32_t hecuda_ntt_forward(const hecuda_context *h, int32_t base, uint64_t *data, int32_t rows, int64_t polys) {
+    int32_t rc = check_ctx(h);
+    if (rc) return rc;
+    if (polys < 0 || (!data && polys)) return fail(HECUDA_ERR_INVALID_ARGUMENT, "invalid data / poly_count");
+    NttRowMap map;
+    std::string err;
+    if (!make_map(*h->ctx, base, rows, map, err)) return fail(HECUDA_ERR_INVALID_ARGUMENT, err);
+    return ntt_host(h, map, data, (size_t)rows * h->ctx->n, polys, rows, false);
+}
+int32_t hecuda_ntt_inverse(const hecuda_context *h, int32_t base, uint64_t *data, int32_t rows, int64_t polys) {
+    int32_t rc = check_ctx(h);
+    if (rc) return rc;
+    if (polys < 0 || (!data && polys)) return fail(HECUDA_ERR_INVALID_ARGUMENT, "invalid data / poly_count");
+    NttRowMap map;
+    std::string err;
+    if (!make_map(*h->ctx, base, rows, map, err)) return fail(HECUDA_ERR_INVALID_ARGUMENT, err);
+    return ntt_host(h, map, data, (size_t)rows * h->ctx->n, polys, rows, true);
+}
+static int32_t ntt_rows_host(const hecuda_context *h, uint64_t modulus, uint64_t *data, int64_t rows, bool inverse) {
+    int32_t rc = check_ctx(h);
+    if (rc) return rc;
+    if (rows < 0 || (!data && rows)) return fail(HECUDA_ERR_INVALID_ARGUMENT, "invalid data / row_count");
+    const int s = h->ctx->find_slot(modulus);
+    if (s < 0) return fail(HECUDA_ERR_INVALID_ARGUMENT, "invalidPolyContext: modulus is not part of this context");
+    return ntt_host(h, h->ctx->map_single(s), data, (size_t)h->ctx->n, rows, 1, inverse);
+}
+int32_t hecuda_ntt_forward_rows(const hecuda_context *h, uint64_t modulus, uint64_t *data, int64_t rows) {
+    return ntt_rows_host(h, modulus, data, rows, false);
+}
+int32_t hecuda_ntt_inverse_rows(const hecuda_context *h, uint64_t modulus, uint64_t *data, int64_t rows) {
+    return ntt_rows_host(h, modulus, data, rows, true);
+}
+
+// ---------------------------------------------------------------- multiply
+
+int32_t hecuda_bfv_multiply_device(const hecuda_context *h, const uint64_t *lhs, const uint64_t *rhs, uint64_t *out,
+                                   int64_t batch, void *stream) {
+    int32_t rc = check_ctx(h);
+    if (rc) return rc;
+    if (batch < 0 || (batch && (!lhs || !rhs || !out))) return fail(HECUDA_ERR_INVALID_ARGUMENT, "invalidCiphertext: null buffer");
+    if (batch == 0) return HECUDA_OK;
+    const Context &c = *h->ctx;
+    const size_t in_words = (size_t)2 * c.L * c.n, out_words = (size_t)3 * c.L * c.n;
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(h->chunk, batch));
+    cudaStream_t s = (cudaStream_t)stream;
+    u64 *scratch = nullptr;  // stream-ordered scratch: no host synchronization, graph-capturable
+    CK(cudaMallocAsync(&scratch, multiply_scratch_words(c) * (size_t)chunk * sizeof(u64), s));
+    for (int64_t done = 0; done < batch; done += chunk) {
+        const int64_t items = std::min<int64_t>(chunk, batch - done);
+        cudaError_t e = multiply_chunk(c, scratch, (const u64 *)lhs + in_words * done, (const u64 *)rhs + in_words * done,
+                                       (u64 *)out + out_words * done, items, s);
+        if (e != cudaSuccess) {
+            cudaFreeAsync(scratch, s);
+            return cuda_fail(e, "multiply");
+        }
+    }
+    CK(cudaFreeAsync(scratch, s));
+    return HECUDA_OK;
+}
+
+int32_t hecuda_bfv_multiply(const hecuda_context *h, const uint64_t *lhs, const uint64_t *rhs, uint64_t *out,
+                            int64_t batch) {
+    int32_t rc = check_ctx(h);
+    if (rc) return rc;
+    if (batch < 0 || (batch && (!lhs || !rhs || !out))) return fail(HECUDA_ERR_INVALID_ARGUMENT, "invalidCiphertext: null buffer");
+    const Context &c = *h->ctx;
+    const size_t in_words = (size_t)2 * c.L * c.n, out_words = (size_t)3 * c.L * c.n;
+    std::vector<HostIo> in = {{(const u64 *)lhs, in_words}, {(const u64 *)rhs, in_words}};
+    return host_pipeline(h, batch, h->chunk, multiply_scratch_words(c), in, (u64 *)out, out_words,
+                         [&](Workspace &w, const std::vector<const u64 *> &d_in, u64 *d_out, int64_t items) {
+                             return multiply_chunk(c, w.buf[0], d_in[0], d_in[1], d_out, items, w.stream);
+                         });
+}
+
+// ---------------------------------------------------------------- evaluation key
+
+int32_t hecuda_evk_create_empty(const hecuda_context *h, hecuda_evk **out) {
+    int32_t rc = check_ctx(h);
+    if (rc) return rc;
+    if (!out) return fail(HECUDA_ERR_INVALID_ARGUMENT, "null argument");
+    const Context &c = *h->ctx;
+    hecuda_evk *k = new (std::nothrow) hecuda_evk();
+    if (!k) return fail(HECUDA_ERR_CUDA, "out of host memory");
+    k->owner = h;
+    k->words = (size_t)c.L * 2 * (c.L + 1) * c.n;
+    cudaError_t e = cudaMalloc(&k->d_relin, k->words * sizeof(u64));
+    if (e != cudaSuccess) {
+        delete k;
+        return cuda_fail(e, "cudaMalloc(evk)");
+    }
+    *out = k;
+    return HECUDA_OK;
+}
+int32_t hecuda_evk_create(const hecuda_context *h, const uint64_t *relin_key, hecuda_evk **out) {
+    if (!relin_key) return fail(HECUDA_ERR_MISSING_KEY, "missingRelinearizationKey");
+    int32_t rc = hecuda_evk_create_empty(h, out);
+    if (rc) return rc;
+    cudaError_t e = cudaMemcpy((*out)->d_relin, relin_key, (*out)->words * sizeof(u64), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        hecuda_evk_destroy(*out);
+        *out = nullptr;
+        return cuda_fail(e, "cudaMemcpy(evk)");
+    }
+    (*out)->loaded = true;
+    return HECUDA_OK;
+}
+int32_t hecuda_evk_destroy(hecuda_evk *k) {
+    if (!k) return HECUDA_OK;
+    if (k->d_relin) cudaFree(k->d_relin);
+    delete k;
+    return HECUDA_OK;
+}
+int32_t hecuda_evk_device_buffer(hecuda_evk *k, void **device_ptr, uint64_t *bytes) {
+    if (!k || !device_ptr || !bytes) return fail(HECUDA_ERR_INVALID_ARGUMENT, "null argument");
+    *device_ptr = k->d_relin;
+    *bytes = k->words * sizeof(u64);
+    k->loaded = true;  // the caller fills it (e.g. ncclBroadcast from rank 0)
+    return HECUDA_OK;
+}
+
+// ---------------------------------------------------------------- relinearize / mod switch
+
+static int32_t check_relin(const hecuda_context *h, const hecuda_evk *k, const uint64_t *ct3, int32_t l, uint64_t *out,
+                           int64_t batch) {
+    int32_t rc = check_ctx(h);
+    if (rc) return rc;
+    if (!k || !k->loaded) return fail(HECUDA_ERR_MISSING_KEY, "missingRelinearizationKey");
+    if (k->owner != h) return fail(HECUDA_ERR_INVALID_ARGUMENT, "invalidContext: evaluation key belongs to another context");
+    if (l < 1 || l > h->ctx->L) return fail(HECUDA_ERR_INVALID_ARGUMENT, "invalidCiphertext: moduli_count out of range");
+    if (batch < 0 || (batch && (!ct3 || !out))) return fail(HECUDA_ERR_INVALID_ARGUMENT, "invalidCiphertext: null buffer");
+    return HECUDA_OK;
+}
+
+int32_t hecuda_bfv_relinearize_device(const hecuda_context *h, const hecuda_evk *k, const uint64_t *ct3, int32_t l,
+                                      uint64_t *out, int64_t batch, void *stream) {
+    int32_t rc = check_relin(h, k, ct3, l, out, batch);
+    if (rc) return rc;
+    if (batch == 0) return HECUDA_OK;
+    const Context &c = *h->ctx;
+    const size_t in_words = (size_t)3 * l * c.n, out_words = (size_t)2 * l * c.n;
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(h->chunk, batch));
+    cudaStream_t s = (cudaStream_t)stream;
+    u64 *scratch = nullptr;
+    CK(cudaMallocAsync(&scratch, relinearize_scratch_words(c, l) * (size_t)chunk * sizeof(u64), s));
+    for (int64_t done = 0; done < batch; done += chunk) {
+        const int64_t items = std::min<int64_t>(chunk, batch - done);
+        cudaError_t e = relinearize_chunk(c, scratch, k->d_relin, (const u64 *)ct3 + in_words * done, l,
+                                          (u64 *)out + out_words * done, items, s);
+        if (e != cudaSuccess) {
+            cudaFreeAsync(scratch, s);
+            return cuda_fail(e, "relinearize");
+        }
+    }
+    CK(cudaFreeAsync(scratch, s));
+    return HECUDA_OK;
+}
+
+int32_t hecuda_bfv_relinearize(const hecuda_context *h, const hecuda_evk *k, const uint64_t *ct3, int32_t l,
+                               uint64_t *out, int64_t batch) {
+    int32_t rc = check_relin(h, k, ct3, l, out, batch);
+    if (rc) return rc;
+    const Context &c = *h->ctx;
+    std::vector<HostIo> in = {{(const u64 *)ct3, (size_t)3 * l * c.n}};
+    return host_pipeline(h, batch, h->chunk, relinearize_scratch_words(c, l), in, (u64 *)out, (size_t)2 * l * c.n,
+                         [&](Workspace &w, const std::vector<const u64 *> &d_in, u64 *d_out, int64_t items) {
+                             return relinearize_chunk(c, w.buf[0], k->d_relin, d_in[0], l, d_out, items, w.stream);
+                         });
+}
+
+static int32_t check_ms(const hecuda_context *h, const uint64_t *ct, int32_t polys, int32_t l, uint64_t *out,
+                        int64_t batch) {
+    int32_t rc = check_ctx(h);
+    if (rc) return rc;
+    if (polys < 1) return fail(HECUDA_ERR_INVALID_ARGUMENT, "invalidCiphertext: poly_count");
+    if (l < 2 || l > h->ctx->L)
+        return fail(HECUDA_ERR_INVALID_ARGUMENT, "invalidPolyContext: modSwitchDown needs a next context (2 <= moduli_count <= L)");
+    if (batch < 0 || (batch && (!ct || !out))) return fail(HECUDA_ERR_INVALID_ARGUMENT, "invalidCiphertext: null buffer");
+    return HECUDA_OK;
+}
+
+int32_t hecuda_bfv_mod_switch_down_device(const hecuda_context *h, const uint64_t *ct, int32_t polys, int32_t l,
+                                          uint64_t *out, int64_t batch, void *stream) {
+    int32_t rc = check_ms(h, ct, polys, l, out, batch);
+    if (rc) return rc;
+    cudaError_t e = launch_mod_switch(*h->ctx, (const u64 *)ct, l, (u64 *)out, batch * polys, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "mod_switch");
+    return HECUDA_OK;
+}
+
+int32_t hecuda_bfv_mod_switch_down(const hecuda_context *h, const uint64_t *ct, int32_t polys, int32_t l, uint64_t *out,
+                                   int64_t batch) {
+    int32_t rc = check_ms(h, ct, polys, l, out, batch);
+    if (rc) return rc;
+    const Context &c = *h->ctx;
+    std::vector<HostIo> in = {{(const u64 *)ct, (size_t)polys * l * c.n}};
+    const int64_t chunk = std::max<int64_t>(1, (int64_t)((size_t)4 * 1024 * 1024 / ((size_t)polys * l * c.n)));
+    return host_pipeline(h, batch, chunk, 0, in, (u64 *)out, (size_t)polys * (l - 1) * c.n,
+                         [&](Workspace &w, const std::vector<const u64 *> &d_in, u64 *d_out, int64_t items) {
+                             return launch_mod_switch(c, d_in[0], l, d_out, items * polys, w.stream);
+                         });
+}
+
+uint64_t hecuda_kernel_launch_count(void) { return g_kernel_launches.load(); }
+
+}  // extern "C"

@@ -1,0 +1,267 @@
+// context.cu -- builds the immutable device context (see context.hpp for the reference mapping).
+#include "context.hpp"
+
+#include <cuda_runtime.h>
+
+#include <cstring>
+
+#include "hostmath.hpp"
+
+namespace hecuda {
+using namespace host;
+
+static constexpr u64 kMTilde = 1ull << 32;  // Sources/ModularArithmetic/Scalar.swift:522-524
+
+static void fill_barrett(u64 p, u64 &mu1, u64 &mu_hi, u64 &mu_lo) {
+    mu1 = (u64)(((u128)1 << 64) / p);
+    u128 mu = (p & (p - 1)) == 0 ? ((u128)1 << (128 - (bit_length(p) - 1))) : (~(u128)0) / p;
+    mu_hi = (u64)(mu >> 64);
+    mu_lo = (u64)mu;
+}
+
+static bool build_slot(HostSlot &hs, u64 p, int64_t n, int logn, u64 t, std::vector<ulonglong2> &tw,
+                       std::vector<ulonglong2> &itw, std::string &err) {
+    if (!is_prime(p) || (p - 1) % (2 * (u64)n) != 0) {
+        err = "invalidNttModulus: " + std::to_string(p) + " is not a prime = 1 mod 2N";
+        return false;
+    }
+    if (p >= (1ull << 62)) {  // Modulus<UInt64>.max, Sources/ModularArithmetic/Modulus.swift:177-180
+        err = "invalidModulus: " + std::to_string(p) + " exceeds 2^62 - 1";
+        return false;
+    }
+    ModSlot &d = hs.dev;
+    std::memset(&d, 0, sizeof(d));
+    d.p = p;
+    fill_barrett(p, d.mu1, d.mu_hi, d.mu_lo);
+    d.bits = bit_length(p);
+    d.s_prod = d.bits - 2;
+    d.mu_prod = (u64)(((u128)1 << (d.bits + 62)) / p);
+    const u64 psi = min_primitive_root(2 * (u64)n, p);
+    const u64 psi_inv = invmod(psi, p);
+    hs.roots.assign(n, 1);
+    hs.inv_roots.assign(n, 1);
+    // roots[bitrev(i)] = psi^i   (PolyRq+Ntt.swift:125-137); inverse table uses the same indexing here.
+    u64 pw = 1, ipw = 1;
+    for (int64_t i = 0; i < n; ++i) {
+        unsigned r = bitrev((unsigned)i, logn);
+        hs.roots[r] = pw;
+        hs.inv_roots[r] = ipw;
+        pw = mulmod(pw, psi, p);
+        ipw = mulmod(ipw, psi_inv, p);
+    }
+    tw.resize(n);
+    itw.resize(n);
+    for (int64_t i = 0; i < n; ++i) {
+        tw[i] = make_ulonglong2(hs.roots[i], shoup_factor(hs.roots[i], p));
+        itw[i] = make_ulonglong2(hs.inv_roots[i], shoup_factor(hs.inv_roots[i], p));
+    }
+    const u64 n_inv = invmod((u64)n % p, p);
+    const u64 w1_inv = n > 1 ? hs.inv_roots[1] : 1;  // psi^-(N/2)
+    d.n_inv = n_inv;
+    d.n_inv_p = shoup_factor(d.n_inv, p);
+    d.n_inv_w = mulmod(n_inv, w1_inv, p);
+    d.n_inv_w_p = shoup_factor(d.n_inv_w, p);
+    d.tn_inv = mulmod(n_inv, t % p, p);
+    d.tn_inv_p = shoup_factor(d.tn_inv, p);
+    d.tn_inv_w = mulmod(d.tn_inv, w1_inv, p);
+    d.tn_inv_w_p = shoup_factor(d.tn_inv_w, p);
+    return true;
+}
+
+static DivRoundConsts build_divround(const std::vector<u64> &base) {
+    DivRoundConsts c;
+    std::memset(&c, 0, sizeof(c));
+    c.l = (int)base.size();
+    c.last = base.back();
+    c.half = c.last >> 1;
+    for (int i = 0; i + 1 < c.l; ++i) {
+        const u64 m = base[i];
+        c.m[i] = m;
+        c.mu1[i] = (u64)(((u128)1 << 64) / m);
+        c.half_mod[i] = c.half % m;
+        c.inv_w[i] = invmod(c.last % m, m);
+        c.inv_wp[i] = shoup_factor(c.inv_w[i], m);
+    }
+    return c;
+}
+
+Context *Context::create(int64_t n, const u64 *coeff_moduli, int nmod, u64 t, std::string &err) {
+    if (n < 2 || (n & (n - 1)) || n > (1 << 17)) { err = "invalidDegree: N must be a power of two in [2, 2^17]"; return nullptr; }
+    if (nmod < 2) { err = "invalidEncryptionParameters: need >= 1 ciphertext modulus plus the key-switching modulus"; return nullptr; }
+    if (nmod - 1 > kMaxL) { err = "unsupportedHeOperation: more than " + std::to_string(kMaxL) + " ciphertext moduli"; return nullptr; }
+    if (t < 2) { err = "invalidEncryptionParameters: plaintext modulus"; return nullptr; }
+    for (int i = 0; i < nmod; ++i)
+        for (int j = 0; j < i; ++j)
+            if (coeff_moduli[i] == coeff_moduli[j]) { err = "coprimeModuli: repeated coefficient modulus"; return nullptr; }
+
+    Context *c = new Context();
+    c->n = n;
+    c->logn = bit_length((u64)n) - 1;
+    c->L = nmod - 1;
+    c->t = t;
+    cudaGetDevice(&c->device);
+    const int L = c->L;
+    c->q.assign(coeff_moduli, coeff_moduli + L);
+    c->q_ks = coeff_moduli[L];
+    for (u64 qi : c->q)
+        if (t >= qi) { err = "invalidEncryptionParameters: plaintext modulus must be below every coefficient modulus"; delete c; return nullptr; }
+    // BEHZ auxiliary base: the L+1 smallest 61-bit NTT primes (RnsTool.swift:30-33)
+    c->bsk = smallest_ntt_primes(61, L + 1, (u64)n);
+    if ((int)c->bsk.size() != L + 1) { err = "notEnoughPrimes for Bsk"; delete c; return nullptr; }
+    for (u64 b : c->bsk)
+        for (int i = 0; i < nmod; ++i)
+            if (b == coeff_moduli[i]) { err = "coprimeModuli: coefficient modulus collides with the BEHZ base"; delete c; return nullptr; }
+
+    // ---- NTT slots
+    const int nslots = 2 * L + 2;
+    c->slots.resize(nslots);
+    std::vector<u64> slot_mod(nslots);
+    for (int i = 0; i < L; ++i) slot_mod[c->slot_q(i)] = c->q[i];
+    for (int j = 0; j <= L; ++j) slot_mod[c->slot_bsk(j)] = c->bsk[j];
+    slot_mod[c->slot_ks()] = c->q_ks;
+    const size_t table_bytes = sizeof(ulonglong2) * (size_t)n;
+    if (cudaMalloc(&c->d_pool, table_bytes * 2 * nslots) != cudaSuccess) { err = "cudaMalloc failed for twiddle tables"; delete c; return nullptr; }
+    std::vector<ulonglong2> tw, itw;
+    std::vector<ModSlot> dev_slots(nslots);
+    for (int s = 0; s < nslots; ++s) {
+        if (!build_slot(c->slots[s], slot_mod[s], n, c->logn, t, tw, itw, err)) { delete c; return nullptr; }
+        char *base = (char *)c->d_pool + table_bytes * 2 * s;
+        cudaMemcpy(base, tw.data(), table_bytes, cudaMemcpyHostToDevice);
+        cudaMemcpy(base + table_bytes, itw.data(), table_bytes, cudaMemcpyHostToDevice);
+        c->slots[s].dev.tw = (const ulonglong2 *)base;
+        c->slots[s].dev.itw = (const ulonglong2 *)(base + table_bytes);
+        dev_slots[s] = c->slots[s].dev;
+    }
+    if (cudaMalloc(&c->d_slots, sizeof(ModSlot) * nslots) != cudaSuccess) { err = "cudaMalloc failed"; delete c; return nullptr; }
+    cudaMemcpy(c->d_slots, dev_slots.data(), sizeof(ModSlot) * nslots, cudaMemcpyHostToDevice);
+
+    // ---- BEHZ constants (top level)
+    const u64 *Q = c->q.data();
+    const u64 *BSK = c->bsk.data();
+    const u64 msk = c->bsk[L];
+    LiftConsts &lf = c->lift;
+    std::memset(&lf, 0, sizeof(lf));
+    lf.L = L;
+    {
+        const u64 q_mod_mt = prod_mod(Q, L, kMTilde);
+        lf.neg_inv_q_mt = (u32)((kMTilde - invmod(q_mod_mt, kMTilde)) % kMTilde);
+    }
+    for (int i = 0; i < L; ++i) {
+        const u64 qi = Q[i];
+        lf.q[i] = qi;
+        const u64 inv_punct = invmod(punctured_mod(Q, L, i, qi), qi);
+        lf.in_w[i] = mulmod(kMTilde % qi, inv_punct, qi);
+        lf.in_wp[i] = shoup_factor(lf.in_w[i], qi);
+        lf.punct_mt[i] = (u32)punctured_mod(Q, L, i, kMTilde);
+    }
+    for (int j = 0; j <= L; ++j) {
+        const u64 bj = BSK[j];
+        u64 mu1;
+        lf.b[j] = bj;
+        fill_barrett(bj, mu1, lf.b_mu_hi[j], lf.b_mu_lo[j]);
+        const u64 mt_inv = invmod(kMTilde % bj, bj);
+        for (int i = 0; i < L; ++i) lf.mat[j][i] = mulmod(punctured_mod(Q, L, i, bj), mt_inv, bj);
+        lf.qr[j] = mulmod(prod_mod(Q, L, bj), mt_inv, bj);
+    }
+    FloorConsts &fl = c->floor;
+    std::memset(&fl, 0, sizeof(fl));
+    fl.L = L;
+    const u64 b_mod_msk = prod_mod(BSK, L, msk);
+    const u64 b_inv_msk = invmod(b_mod_msk, msk);
+    fl.a_msk = (msk - b_inv_msk) % msk;
+    for (int i = 0; i < L; ++i) {
+        const u64 qi = Q[i];
+        u64 mu1;
+        fl.q[i] = qi;
+        fill_barrett(qi, mu1, fl.q_mu_hi[i], fl.q_mu_lo[i]);
+        fl.inq_w[i] = invmod(punctured_mod(Q, L, i, qi), qi);
+        fl.inq_wp[i] = shoup_factor(fl.inq_w[i], qi);
+        for (int k = 0; k < L; ++k) fl.omat[i][k] = punctured_mod(BSK, L, k, qi);
+        fl.b_mod_q[i] = prod_mod(BSK, L, qi);
+        fl.neg_b_mod_q[i] = (qi - fl.b_mod_q[i]) % qi;
+    }
+    for (int j = 0; j <= L; ++j) {
+        const u64 bj = BSK[j];
+        u64 mu1;
+        fl.b[j] = bj;
+        fill_barrett(bj, mu1, fl.b_mu_hi[j], fl.b_mu_lo[j]);
+        const u64 q_inv = invmod(prod_mod(Q, L, bj), bj);
+        fl.fq[j] = q_inv;
+        for (int i = 0; i < L; ++i) {
+            const u64 v = mulmod(punctured_mod(Q, L, i, bj), q_inv, bj);
+            fl.fmat[j][i] = (bj - v) % bj;
+        }
+    }
+    for (int k = 0; k < L; ++k) {
+        const u64 bk = BSK[k];
+        fl.inb_w[k] = invmod(punctured_mod(BSK, L, k, bk), bk);
+        fl.inb_wp[k] = shoup_factor(fl.inb_w[k], bk);
+        fl.amat[k] = mulmod(punctured_mod(BSK, L, k, msk), b_inv_msk, msk);
+    }
+
+    // ---- divide-and-round constants
+    c->ks_divround.resize(L + 1);
+    c->ms_divround.resize(L + 1);
+    for (int l = 1; l <= L; ++l) {
+        std::vector<u64> base(c->q.begin(), c->q.begin() + l);
+        if (l >= 2) c->ms_divround[l] = build_divround(base);
+        base.push_back(c->q_ks);
+        c->ks_divround[l] = build_divround(base);
+    }
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { err = std::string("CUDA error during context setup: ") + cudaGetErrorString(e); delete c; return nullptr; }
+    return c;
+}
+
+Context::~Context() {
+    if (d_pool) cudaFree(d_pool);
+    if (d_slots) cudaFree(d_slots);
+}
+
+NttRowMap Context::map_q(int rows) const {
+    NttRowMap m;
+    std::memset(&m, 0, sizeof(m));
+    m.rows_per_poly = rows;
+    m.group = 1;
+    for (int r = 0; r < rows; ++r) m.slot[r] = (unsigned char)slot_q(r);
+    return m;
+}
+NttRowMap Context::map_qbsk() const {
+    NttRowMap m;
+    std::memset(&m, 0, sizeof(m));
+    m.rows_per_poly = 2 * L + 1;
+    m.group = 1;
+    for (int r = 0; r < L; ++r) m.slot[r] = (unsigned char)slot_q(r);
+    for (int j = 0; j <= L; ++j) m.slot[L + j] = (unsigned char)slot_bsk(j);
+    return m;
+}
+NttRowMap Context::map_ks(int l) const {
+    NttRowMap m;
+    std::memset(&m, 0, sizeof(m));
+    m.rows_per_poly = l + 1;
+    m.group = 1;
+    for (int r = 0; r < l; ++r) m.slot[r] = (unsigned char)slot_q(r);
+    m.slot[l] = (unsigned char)slot_ks();
+    return m;
+}
+NttRowMap Context::map_single(int slot) const {
+    NttRowMap m;
+    std::memset(&m, 0, sizeof(m));
+    m.rows_per_poly = 1;
+    m.group = 1;
+    m.slot[0] = (unsigned char)slot;
+    return m;
+}
+NttRowMap Context::map_ks_digits(int l) const {
+    NttRowMap m = map_ks(l);
+    m.rows_per_poly = (l + 1) * l;
+    m.group = l;
+    return m;
+}
+int Context::find_slot(u64 modulus) const {
+    for (size_t s = 0; s < slots.size(); ++s)
+        if (slots[s].dev.p == modulus) return (int)s;
+    return -1;
+}
+
+}  // namespace hecuda

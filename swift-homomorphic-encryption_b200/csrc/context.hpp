@@ -1,0 +1,121 @@
+// context.hpp -- immutable device context: moduli, NTT root tables and BEHZ / key-switch constants.
+//
+// Host-side construction mirrors what the reference precomputes in Context<Bfv<UInt64>>.init
+// (Sources/HomomorphicEncryption/Context.swift:94-143), PolyContext.init (PolyRq/PolyContext.swift:45-123),
+// _NttContext.init (PolyRq/PolyRq+Ntt.swift:118-169) and _RnsTool.init (RnsTool.swift:132-251).
+// Where the reference applies two exact modular steps in a row, the constants here are pre-multiplied so the
+// kernels do one multiply-accumulate pass (see DESIGN.md "fused constants"); results are the same canonical residues.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "modarith.cuh"
+
+namespace hecuda {
+
+constexpr int kMaxL = 16;               // ciphertext moduli supported by the kernels
+constexpr int kMaxSlots = 2 * kMaxL + 2;  // q_0..q_{L-1} | bsk_0..bsk_L | q_ks
+constexpr int kMaxRows = 2 * kMaxL + 1;
+
+// One NTT-capable modulus.  Twiddle tables are interleaved (w, floor(w 2^64 / p)) pairs, indexed like the
+// reference's rootOfUnityPowers: entry m + i serves group i of the stage with m groups (PolyRq+Ntt.swift:128-137).
+struct ModSlot {
+    u64 p;
+    u64 mu1;          // floor(2^64 / p)
+    u64 mu_hi, mu_lo; // floor(2^128 / p)
+    u64 mu_prod;      // floor(2^(bits+62) / p)
+    int s_prod;       // bits - 2
+    int bits;
+    u64 n_inv, n_inv_p;       // N^-1                       (PolyRq+Ntt.swift:159-160)
+    u64 n_inv_w, n_inv_w_p;   // N^-1 * psi^-(N/2)          (PolyRq+Ntt.swift:162-168)
+    u64 tn_inv, tn_inv_p;     // t * N^-1        (poly * tVec folded into the inverse NTT, Bfv+Multiply.swift:40)
+    u64 tn_inv_w, tn_inv_w_p; // t * N^-1 * psi^-(N/2)
+    const ulonglong2 *tw;     // forward twiddles  [N]
+    const ulonglong2 *itw;    // inverse twiddles  [N]  (itw[m+i] = tw[m+i]^-1)
+};
+
+struct NttRowMap {       // which modulus slot each row of a polynomial uses:
+    int rows_per_poly;   //   slot[((row % rows_per_poly) / group)]
+    int group;
+    unsigned char slot[kMaxRows + 1];
+};
+
+// liftQToQBsk (RnsTool.swift:324-368) fused to: z_i = [x_i * in_w_i]_{q_i};
+//   r = [ -Q^-1 * sum_i z_i (Q/q_i) ]_{2^32}, centered;  out_j = [ sum_i z_i mat[j][i] + r_c * qr[j] ]_{b_j}
+struct LiftConsts {
+    int L;
+    u64 q[kMaxL];
+    u64 in_w[kMaxL], in_wp[kMaxL];   // m~ (Q/q_i)^-1 mod q_i
+    u32 punct_mt[kMaxL];             // (Q/q_i) mod 2^32
+    u32 neg_inv_q_mt;                // -Q^-1 mod 2^32
+    u64 b[kMaxL + 1], b_mu_hi[kMaxL + 1], b_mu_lo[kMaxL + 1];
+    u64 mat[kMaxL + 1][kMaxL];       // (Q/q_i) m~^-1 mod b_j
+    u64 qr[kMaxL + 1];               // Q m~^-1 mod b_j
+};
+
+// floorQBskToQ (RnsTool.swift:378-456) fused to:
+//   y_i = [x_i inq_w_i]_{q_i};  f_j = [x_bj fq[j] + sum_i y_i fmat[j][i]]_{b_j}           (approximateFloor)
+//   w_k = [f_k inb_w_k]_{b_k};  alpha = [sum_k w_k amat[k] + f_msk a_msk]_{m_sk}          (Shenoy-Kumaresan)
+//   out_i = [sum_k w_k omat[i][k] + alpha' D_i]_{q_i},  (alpha', D) = alpha > m_sk/2 ? (m_sk-alpha, B) : (alpha, -B)
+struct FloorConsts {
+    int L;
+    u64 q[kMaxL], q_mu_hi[kMaxL], q_mu_lo[kMaxL];
+    u64 inq_w[kMaxL], inq_wp[kMaxL];   // (Q/q_i)^-1 mod q_i
+    u64 b[kMaxL + 1], b_mu_hi[kMaxL + 1], b_mu_lo[kMaxL + 1];
+    u64 fq[kMaxL + 1];                 // Q^-1 mod b_j
+    u64 fmat[kMaxL + 1][kMaxL];        // -(Q/q_i) Q^-1 mod b_j
+    u64 inb_w[kMaxL], inb_wp[kMaxL];   // (B/b_k)^-1 mod b_k
+    u64 amat[kMaxL];                   // (B/b_k) B^-1 mod m_sk
+    u64 a_msk;                         // -B^-1 mod m_sk
+    u64 omat[kMaxL][kMaxL];            // (B/b_k) mod q_i
+    u64 b_mod_q[kMaxL], neg_b_mod_q[kMaxL];
+};
+
+// divideAndRoundQLast (PolyRq.swift:365-393) for a base [m_0..m_{l-2}, m_last]
+struct DivRoundConsts {
+    int l;                              // rows in (including the last)
+    u64 m[kMaxL + 1], mu1[kMaxL + 1];   // moduli of the kept rows + Barrett factor
+    u64 last, half;                     // m_last, m_last >> 1
+    u64 half_mod[kMaxL + 1];            // half mod m_i
+    u64 inv_w[kMaxL + 1], inv_wp[kMaxL + 1];  // m_last^-1 mod m_i
+};
+
+struct HostSlot {
+    ModSlot dev;                      // with device pointers filled in
+    std::vector<u64> roots, inv_roots;  // host copies (w only) for parity checks
+};
+
+class Context {
+   public:
+    static Context *create(int64_t n, const u64 *coeff_moduli, int nmod, u64 t, std::string &err);
+    ~Context();
+
+    int64_t n;
+    int logn;
+    int L;           // ciphertext moduli
+    u64 t;
+    int device;
+    std::vector<u64> q;    // q_0..q_{L-1}
+    u64 q_ks;
+    std::vector<u64> bsk;  // L+1 primes
+    std::vector<HostSlot> slots;  // L q's, L+1 bsk, 1 q_ks
+    ModSlot *d_slots = nullptr;   // device array [2L+2]
+    LiftConsts lift;
+    FloorConsts floor;
+    std::vector<DivRoundConsts> ks_divround;   // index l (1..L): base [q_0..q_{l-1}, q_ks]
+    std::vector<DivRoundConsts> ms_divround;   // index l (2..L): base [q_0..q_{l-1}]
+    void *d_pool = nullptr;  // twiddle storage
+
+    int slot_q(int i) const { return i; }
+    int slot_bsk(int j) const { return L + j; }
+    int slot_ks() const { return 2 * L + 1; }
+    NttRowMap map_q(int rows) const;      // rows of the ciphertext context
+    NttRowMap map_qbsk() const;           // [Q, Bsk]
+    NttRowMap map_ks(int l) const;        // [q_0..q_{l-1}, q_ks]
+    NttRowMap map_single(int slot) const;
+    NttRowMap map_ks_digits(int l) const; // (l+1) x l digit rows, row (r, j) under m_r
+    int find_slot(u64 modulus) const;
+};
+
+}  // namespace hecuda

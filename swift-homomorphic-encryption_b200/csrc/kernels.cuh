@@ -1,0 +1,49 @@
+// kernels.cuh -- launchers of the sm_100a kernels (all take device pointers and a stream).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+
+#include "context.hpp"
+
+namespace hecuda {
+
+extern std::atomic<unsigned long long> g_kernel_launches;  // every <<<>>> issued by this library
+
+// ---- negacyclic NTT over rows (ntt.cu).  data: rows x N, row r uses slot map.slot[r % map.rows_per_poly].
+// Forward: natural order in -> bit-reversed out (PolyRq+Ntt.swift:237-319); inverse is its inverse (:379-483).
+// scale_t: fold the BFV `poly * t` step (Bfv+Multiply.swift:40) into the inverse transform's N^-1 scaling.
+cudaError_t launch_ntt_forward(const Context &ctx, const NttRowMap &map, const u64 *in, u64 *out, int64_t rows,
+                               cudaStream_t stream);
+cudaError_t launch_ntt_inverse(const Context &ctx, const NttRowMap &map, const u64 *in, u64 *out, int64_t rows,
+                               bool scale_t, cudaStream_t stream);
+
+// implementations behind the dispatcher (ntt_simple.cu)
+cudaError_t launch_ntt_forward_simple(const Context &ctx, const NttRowMap &map, const u64 *in, u64 *out, int64_t rows,
+                                      cudaStream_t stream);
+cudaError_t launch_ntt_inverse_simple(const Context &ctx, const NttRowMap &map, const u64 *in, u64 *out, int64_t rows,
+                                      bool scale_t, cudaStream_t stream);
+
+// ---- BEHZ steps of ct x ct multiply (behz.cu)
+// lift: `items` x polys_in x L x N  ->  ext[item][out_poly_offset + p][R][N]  with ext item stride ext_polys*R*N
+cudaError_t launch_lift(const Context &ctx, const u64 *in, int polys_in, u64 *ext, int ext_polys, int out_poly_offset,
+                        int64_t items, cudaStream_t stream);
+// tensor: ext[item][4][R][N] (Eval) -> ten[item][3][R][N]
+cudaError_t launch_tensor(const Context &ctx, const u64 *ext, u64 *ten, int64_t items, cudaStream_t stream);
+// floor: polys x R x N (Coeff, already scaled by t) -> polys x L x N
+cudaError_t launch_floor(const Context &ctx, const u64 *in, u64 *out, int64_t polys, cudaStream_t stream);
+
+// ---- key switching and modulus switching (keyswitch.cu)
+// digits: target rows [item][l][N] inside ct3 (poly index 2 of 3) -> dig[item][l+1][l][N], dig[.][r][j] = [c_j]_{m_r}
+cudaError_t launch_ks_digits(const Context &ctx, const u64 *target, int64_t target_item_stride, int l, u64 *dig,
+                             int64_t items, cudaStream_t stream);
+// mac: dig (Eval) x key -> prod[item][2][l+1][N] (Eval)
+cudaError_t launch_ks_mac(const Context &ctx, const u64 *dig, const u64 *key, int l, u64 *prod, int64_t items,
+                          cudaStream_t stream);
+// finish: out[item][c][i] = base[item][c][i] + divround(prod[item][c])[i]   (base may be null -> no add)
+cudaError_t launch_ks_finish(const Context &ctx, const u64 *prod, const u64 *base, int64_t base_item_stride, int l,
+                             u64 *out, int64_t items, cudaStream_t stream);
+// divideAndRoundQLast over polys x l x N -> polys x (l-1) x N
+cudaError_t launch_mod_switch(const Context &ctx, const u64 *in, int l, u64 *out, int64_t polys, cudaStream_t stream);
+
+}  // namespace hecuda

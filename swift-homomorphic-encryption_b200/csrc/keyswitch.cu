@@ -1,0 +1,151 @@
+// keyswitch.cu -- hybrid key switching (alpha = 1) and modulus switching.
+//
+//   Bfv._computeKeySwitchingUpdate   Bfv/Bfv+Keys.swift:123-208
+//   Bfv.relinearize                  Bfv/Bfv.swift:201-219
+//   PolyRq.divideAndRoundQLast       PolyRq/PolyRq.swift:365-393
+//   Bfv.modSwitchDown                Bfv/Bfv.swift:163-171
+//
+// Stage kernels (v1): digits -> forward NTT (ntt.cu) -> mac -> inverse NTT -> finish.
+#include "kernels.cuh"
+
+namespace hecuda {
+
+// dig[item][r][j][.] = target[item][j][.] reduced into [0, m_r)   (Bfv+Keys.swift:165-172)
+__global__ void __launch_bounds__(256) ks_digits_kernel(const u64 *__restrict__ target, int64_t target_item_stride, int l,
+                                                       u64 *__restrict__ dig, const ModSlot *__restrict__ slots,
+                                                       NttRowMap ks_map, int64_t n) {
+    const int j = blockIdx.y;
+    const int64_t item = blockIdx.z;
+    const int64_t coeff = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (coeff >= n) return;
+    const u64 x = target[item * target_item_stride + (int64_t)j * n + coeff];
+    const u64 qj = slots[ks_map.slot[j]].p;
+    for (int r = 0; r <= l; ++r) {
+        const ModSlot &S = slots[ks_map.slot[r]];
+        const u64 v = qj > S.p ? barrett64(x, S.p, S.mu1) : x;
+        dig[((item * (l + 1) + r) * l + j) * n + coeff] = v;
+    }
+}
+
+// prod[item][comp][r][.] = [ sum_j dig[item][r][j][.] * key[j][comp][keyrow(r)][.] ]_{m_r}   (Bfv+Keys.swift:180-202)
+__global__ void __launch_bounds__(256) ks_mac_kernel(const u64 *__restrict__ dig, const u64 *__restrict__ key, int l, int K,
+                                                    u64 *__restrict__ prod, const ModSlot *__restrict__ slots,
+                                                    NttRowMap ks_map, int64_t n) {
+    const int r = blockIdx.y;
+    const int64_t item = blockIdx.z;
+    const int64_t coeff = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (coeff >= n) return;
+    const ModSlot &S = slots[ks_map.slot[r]];
+    const int key_row = (r == l) ? K - 1 : r;  // Bfv+Keys.swift:153
+    u128w acc0 = {0, 0}, acc1 = {0, 0};
+    for (int j = 0; j < l; ++j) {
+        const u64 d = dig[((item * (l + 1) + r) * l + j) * n + coeff];
+        const u64 *kj = key + ((int64_t)j * 2 * K + key_row) * n + coeff;
+        mac_wide(acc0, d, kj[0]);
+        mac_wide(acc1, d, kj[(int64_t)K * n]);
+    }
+    u64 *o = prod + ((item * 2) * (l + 1) + r) * n + coeff;
+    o[0] = barrett128(acc0, S.p, S.mu_hi, S.mu_lo);
+    o[(int64_t)(l + 1) * n] = barrett128(acc1, S.p, S.mu_hi, S.mu_lo);
+}
+
+// divide-and-round by the last modulus of `in` (rows c.l), optionally adding `base`, write c.l - 1 rows
+__device__ __forceinline__ void divround_column(const u64 *__restrict__ in, const u64 *__restrict__ base,
+                                                u64 *__restrict__ out, const DivRoundConsts &c, int64_t n) {
+    const int kept = c.l - 1;
+    const u64 last = add_mod(in[(int64_t)kept * n], c.half, c.last);  // PolyRq.swift:376-379
+    for (int i = 0; i < kept; ++i) {
+        const u64 m = c.m[i];
+        const u64 tmp = barrett64(last, m, c.mu1[i]);
+        u64 v = sub_mod(add_mod(in[(int64_t)i * n], c.half_mod[i], m), tmp, m);
+        v = shoup_mul(v, c.inv_w[i], c.inv_wp[i], m);
+        if (base) v = add_mod(v, base[(int64_t)i * n], m);
+        out[(int64_t)i * n] = v;
+    }
+}
+
+__global__ void __launch_bounds__(256) ks_finish_kernel(const u64 *__restrict__ prod, const u64 *__restrict__ base,
+                                                       int64_t base_item_stride, u64 *__restrict__ out,
+                                                       const __grid_constant__ DivRoundConsts c, int64_t n) {
+    const int comp = blockIdx.y;
+    const int64_t item = blockIdx.z;
+    const int64_t coeff = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (coeff >= n) return;
+    const int l = c.l - 1;
+    const u64 *in = prod + ((item * 2 + comp) * c.l) * n + coeff;
+    const u64 *b = base ? base + item * base_item_stride + (int64_t)comp * l * n + coeff : nullptr;
+    u64 *o = out + ((item * 2 + comp) * l) * n + coeff;
+    divround_column(in, b, o, c, n);
+}
+
+__global__ void __launch_bounds__(256) mod_switch_kernel(const u64 *__restrict__ in, u64 *__restrict__ out,
+                                                        const __grid_constant__ DivRoundConsts c, int64_t n,
+                                                        int64_t total) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int64_t poly = idx / n, coeff = idx - poly * n;
+    divround_column(in + poly * c.l * n + coeff, nullptr, out + poly * (c.l - 1) * n + coeff, c, n);
+}
+
+static inline int pick_threads(int64_t n) { return n >= 256 ? 256 : (n < 32 ? 32 : (int)n); }
+
+cudaError_t launch_ks_digits(const Context &ctx, const u64 *target, int64_t target_item_stride, int l, u64 *dig,
+                             int64_t items, cudaStream_t stream) {
+    if (items == 0) return cudaSuccess;
+    const NttRowMap map = ctx.map_ks(l);
+    const int threads = pick_threads(ctx.n);
+    for (int64_t done = 0; done < items;) {
+        const int64_t chunk = (items - done) > 65535 ? 65535 : (items - done);
+        dim3 grid((unsigned)((ctx.n + threads - 1) / threads), (unsigned)l, (unsigned)chunk);
+        ++g_kernel_launches;
+        ks_digits_kernel<<<grid, threads, 0, stream>>>(target + done * target_item_stride, target_item_stride, l,
+                                                       dig + done * (l + 1) * l * ctx.n, ctx.d_slots, map, ctx.n);
+        done += chunk;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_ks_mac(const Context &ctx, const u64 *dig, const u64 *key, int l, u64 *prod, int64_t items,
+                          cudaStream_t stream) {
+    if (items == 0) return cudaSuccess;
+    const NttRowMap map = ctx.map_ks(l);
+    const int threads = pick_threads(ctx.n);
+    for (int64_t done = 0; done < items;) {
+        const int64_t chunk = (items - done) > 65535 ? 65535 : (items - done);
+        dim3 grid((unsigned)((ctx.n + threads - 1) / threads), (unsigned)(l + 1), (unsigned)chunk);
+        ++g_kernel_launches;
+        ks_mac_kernel<<<grid, threads, 0, stream>>>(dig + done * (l + 1) * l * ctx.n, key, l, ctx.L + 1,
+                                                    prod + done * 2 * (l + 1) * ctx.n, ctx.d_slots, map, ctx.n);
+        done += chunk;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_ks_finish(const Context &ctx, const u64 *prod, const u64 *base, int64_t base_item_stride, int l,
+                             u64 *out, int64_t items, cudaStream_t stream) {
+    if (items == 0) return cudaSuccess;
+    const int threads = pick_threads(ctx.n);
+    const DivRoundConsts &c = ctx.ks_divround[l];
+    for (int64_t done = 0; done < items;) {
+        const int64_t chunk = (items - done) > 65535 ? 65535 : (items - done);
+        dim3 grid((unsigned)((ctx.n + threads - 1) / threads), 2, (unsigned)chunk);
+        ++g_kernel_launches;
+        ks_finish_kernel<<<grid, threads, 0, stream>>>(prod + done * 2 * (l + 1) * ctx.n,
+                                                       base ? base + done * base_item_stride : nullptr, base_item_stride,
+                                                       out + done * 2 * l * ctx.n, c, ctx.n);
+        done += chunk;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_mod_switch(const Context &ctx, const u64 *in, int l, u64 *out, int64_t polys, cudaStream_t stream) {
+    const int64_t total = polys * ctx.n;
+    if (total == 0) return cudaSuccess;
+    if (l < 2 || l > ctx.L) return cudaErrorInvalidValue;
+    const unsigned blocks = (unsigned)((total + 255) / 256);
+    ++g_kernel_launches;
+    mod_switch_kernel<<<blocks, 256, 0, stream>>>(in, out, ctx.ms_divround[l], ctx.n, total);
+    return cudaGetLastError();
+}
+
+}  // namespace hecuda

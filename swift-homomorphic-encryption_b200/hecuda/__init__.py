@@ -1,0 +1,289 @@
+"""hecuda -- host-side mirror of the reference's HeScheme surface for the RNS-BFV hot path, over libhecuda.so.
+
+Names follow the reference (Sources/HomomorphicEncryption/HeScheme.swift): `Context`, `EvaluationKey`,
+`Bfv.mulAssign / relinearize / modSwitchDown / forwardNtt / inverseNtt`.  Data crosses the boundary as numpy uint64
+arrays shaped like the reference's Array2d-backed values:
+
+    polynomial  : (rows, N)                  -- PolyRq.data            (PolyRq.swift:21-28)
+    ciphertext  : (polys, rows, N)           -- Ciphertext.polys       (Ciphertext.swift:18-28)
+    batch       : (batch, polys, rows, N)
+
+Everything runs on the GPU through the C ABI in include/hecuda.h; there is no CPU fallback -- if the CUDA extension
+is missing or no device is present, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "libhecuda.so")
+
+HECUDA_OK = 0
+BASE_Q, BASE_Q_BSK, BASE_KEYSWITCH = 0, 1, 2
+u64p = C.POINTER(C.c_uint64)
+
+# every symbol include/hecuda.h declares: (restype, argtypes)
+_VP = C.c_void_p
+SYMBOLS = {
+    "hecuda_version": (C.c_int32, []),
+    "hecuda_last_error": (C.c_char_p, []),
+    "hecuda_device_count": (C.c_int32, [C.POINTER(C.c_int32)]),
+    "hecuda_set_device": (C.c_int32, [C.c_int32]),
+    "hecuda_host_alloc": (C.c_int32, [C.POINTER(_VP), C.c_uint64]),
+    "hecuda_host_free": (C.c_int32, [_VP]),
+    "hecuda_host_register": (C.c_int32, [_VP, C.c_uint64]),
+    "hecuda_host_unregister": (C.c_int32, [_VP]),
+    "hecuda_context_create": (C.c_int32, [C.c_int64, u64p, C.c_int32, C.c_uint64, C.POINTER(_VP)]),
+    "hecuda_context_destroy": (C.c_int32, [_VP]),
+    "hecuda_context_ciphertext_moduli_count": (C.c_int32, [_VP, C.POINTER(C.c_int32)]),
+    "hecuda_context_bsk_moduli": (C.c_int32, [_VP, u64p, C.c_int32, C.POINTER(C.c_int32)]),
+    "hecuda_context_root_tables": (C.c_int32, [_VP, C.c_uint64, u64p, u64p]),
+    "hecuda_ntt_forward": (C.c_int32, [_VP, C.c_int32, _VP, C.c_int32, C.c_int64]),
+    "hecuda_ntt_inverse": (C.c_int32, [_VP, C.c_int32, _VP, C.c_int32, C.c_int64]),
+    "hecuda_ntt_forward_device": (C.c_int32, [_VP, C.c_int32, _VP, C.c_int32, C.c_int64, _VP]),
+    "hecuda_ntt_inverse_device": (C.c_int32, [_VP, C.c_int32, _VP, C.c_int32, C.c_int64, _VP]),
+    "hecuda_ntt_forward_rows": (C.c_int32, [_VP, C.c_uint64, _VP, C.c_int64]),
+    "hecuda_ntt_inverse_rows": (C.c_int32, [_VP, C.c_uint64, _VP, C.c_int64]),
+    "hecuda_bfv_multiply": (C.c_int32, [_VP, _VP, _VP, _VP, C.c_int64]),
+    "hecuda_bfv_multiply_device": (C.c_int32, [_VP, _VP, _VP, _VP, C.c_int64, _VP]),
+    "hecuda_evk_create": (C.c_int32, [_VP, _VP, C.POINTER(_VP)]),
+    "hecuda_evk_destroy": (C.c_int32, [_VP]),
+    "hecuda_evk_create_empty": (C.c_int32, [_VP, C.POINTER(_VP)]),
+    "hecuda_evk_device_buffer": (C.c_int32, [_VP, C.POINTER(_VP), C.POINTER(C.c_uint64)]),
+    "hecuda_bfv_relinearize": (C.c_int32, [_VP, _VP, _VP, C.c_int32, _VP, C.c_int64]),
+    "hecuda_bfv_relinearize_device": (C.c_int32, [_VP, _VP, _VP, C.c_int32, _VP, C.c_int64, _VP]),
+    "hecuda_bfv_mod_switch_down": (C.c_int32, [_VP, _VP, C.c_int32, C.c_int32, _VP, C.c_int64]),
+    "hecuda_bfv_mod_switch_down_device": (C.c_int32, [_VP, _VP, C.c_int32, C.c_int32, _VP, C.c_int64, _VP]),
+    "hecuda_kernel_launch_count": (C.c_uint64, []),
+}
+
+_lib = None
+
+
+class HeError(RuntimeError):
+    """Mirrors `throws HeError` (Sources/HomomorphicEncryption/Error.swift:17-54)."""
+
+    def __init__(self, code: int, message: str):
+        super().__init__(f"[{code}] {message}")
+        self.code = code
+        self.message = message
+
+
+def load_library(path: str = LIB_PATH):
+    """dlopen libhecuda.so and bind every declared symbol.  Raises if the library or a symbol is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(path):
+            raise HeError(-4, f"libhecuda.so not found at {path}: build it with __graft_entry__.build() "
+                              "(the product has no CPU fallback)")
+        lib = C.CDLL(path)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(lib, name)  # AttributeError if the .so does not export it
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def _check(rc: int):
+    if rc != HECUDA_OK:
+        raise HeError(rc, (load_library().hecuda_last_error() or b"").decode())
+
+
+def _host(a) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(a, dtype=np.uint64))
+
+
+def _ptr(a: np.ndarray):
+    return C.c_void_p(a.ctypes.data)
+
+
+def device_count() -> int:
+    n = C.c_int32(0)
+    rc = load_library().hecuda_device_count(C.byref(n))
+    return n.value if rc == HECUDA_OK else 0
+
+
+def set_device(i: int):
+    _check(load_library().hecuda_set_device(i))
+
+
+def kernel_launch_count() -> int:
+    return int(load_library().hecuda_kernel_launch_count())
+
+
+class PinnedBuffer:
+    """Page-locked host array (hecuda_host_alloc) so the host-pointer entry points can overlap their copies."""
+
+    def __init__(self, shape, dtype=np.uint64):
+        self.nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        _check(load_library().hecuda_host_alloc(C.byref(p), max(self.nbytes, 8)))
+        self._p = p
+        buf = (C.c_char * max(self.nbytes, 8)).from_address(p.value)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def free(self):
+        if self._p is not None:
+            self.array = None
+            load_library().hecuda_host_free(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Context:
+    """Context<Bfv<UInt64>> (Context.swift:19,94-143).  coefficient_moduli = [q_0 .. q_{L-1}, q_ks]."""
+
+    def __init__(self, poly_degree: int, coefficient_moduli, plaintext_modulus: int):
+        lib = load_library()
+        self.degree = int(poly_degree)
+        self.coefficientModuli = [int(m) for m in coefficient_moduli]
+        self.plaintextModulus = int(plaintext_modulus)
+        mods = _host(self.coefficientModuli)
+        h = C.c_void_p()
+        _check(lib.hecuda_context_create(self.degree, mods.ctypes.data_as(u64p), len(mods), self.plaintextModulus,
+                                         C.byref(h)))
+        self._h = h
+        n = C.c_int32(0)
+        _check(lib.hecuda_context_ciphertext_moduli_count(h, C.byref(n)))
+        self.L = n.value
+        out = np.zeros(self.L + 1, dtype=np.uint64)
+        _check(lib.hecuda_context_bsk_moduli(h, out.ctypes.data_as(u64p), len(out), C.byref(n)))
+        self.bskModuli = [int(v) for v in out]
+
+    @property
+    def ciphertextModuli(self):
+        return self.coefficientModuli[: self.L]
+
+    def close(self):
+        if getattr(self, "_h", None) is not None:
+            load_library().hecuda_context_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def rootTables(self, modulus: int):
+        roots = np.zeros(self.degree, dtype=np.uint64)
+        inv = np.zeros(self.degree, dtype=np.uint64)
+        _check(load_library().hecuda_context_root_tables(self._h, modulus, roots.ctypes.data_as(u64p),
+                                                         inv.ctypes.data_as(u64p)))
+        return roots, inv
+
+
+class EvaluationKey:
+    """EvaluationKey<Bfv<UInt64>> holding the relinearization key (Keys.swift:66-99,222)."""
+
+    def __init__(self, context: Context, relinearizationKey=None):
+        self.context = context
+        h = C.c_void_p()
+        if relinearizationKey is None:
+            _check(load_library().hecuda_evk_create_empty(context._h, C.byref(h)))
+        else:
+            key = _host(relinearizationKey)
+            K = context.L + 1
+            if key.size != context.L * 2 * K * context.degree:
+                raise HeError(-1, "invalidContext: relinearization key must be L x 2 x (L+1) x N")
+            _check(load_library().hecuda_evk_create(context._h, _ptr(key), C.byref(h)))
+        self._h = h
+
+    def deviceBuffer(self):
+        p, n = C.c_void_p(), C.c_uint64(0)
+        _check(load_library().hecuda_evk_device_buffer(self._h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def close(self):
+        if getattr(self, "_h", None) is not None:
+            load_library().hecuda_evk_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Bfv:
+    """enum Bfv<UInt64>: HeScheme -- the hot-path statics (Bfv/Bfv.swift:20), batched over a leading axis."""
+
+    @staticmethod
+    def mulAssign(context: Context, lhs, rhs, out=None):
+        """Bfv.mulAssign (Bfv+Multiply.swift:18-21): (batch, 2, L, N) x (batch, 2, L, N) -> (batch, 3, L, N)."""
+        a, b = _host(lhs), _host(rhs)
+        shape = (2, context.L, context.degree)
+        if a.shape[-3:] != shape or b.shape != a.shape:
+            raise HeError(-1, f"invalidCiphertext: expected (..., 2, {context.L}, {context.degree}), got {a.shape} and {b.shape}")
+        batch = int(np.prod(a.shape[:-3], dtype=np.int64))
+        if out is None:
+            out = np.empty(a.shape[:-3] + (3, context.L, context.degree), dtype=np.uint64)
+        _check(load_library().hecuda_bfv_multiply(context._h, _ptr(a), _ptr(b), _ptr(out), batch))
+        return out
+
+    @staticmethod
+    def relinearize(context: Context, ciphertext, key: EvaluationKey, out=None):
+        """Bfv.relinearize (Bfv.swift:201-219): (batch, 3, l, N) -> (batch, 2, l, N)."""
+        c = _host(ciphertext)
+        if c.ndim < 3 or c.shape[-3] != 3 or c.shape[-1] != context.degree:
+            raise HeError(-1, "invalidCiphertext: ciphertext must have three polys when relinearizing")
+        if key is None:
+            raise HeError(-5, "missingRelinearizationKey")
+        l = c.shape[-2]
+        batch = int(np.prod(c.shape[:-3], dtype=np.int64))
+        if out is None:
+            out = np.empty(c.shape[:-3] + (2, l, context.degree), dtype=np.uint64)
+        _check(load_library().hecuda_bfv_relinearize(context._h, key._h, _ptr(c), l, _ptr(out), batch))
+        return out
+
+    @staticmethod
+    def modSwitchDown(context: Context, ciphertext, out=None):
+        """Bfv.modSwitchDown (Bfv.swift:163-171): (batch, polys, l, N) -> (batch, polys, l-1, N)."""
+        c = _host(ciphertext)
+        if c.ndim < 3 or c.shape[-1] != context.degree:
+            raise HeError(-1, "invalidCiphertext")
+        polys, l = c.shape[-3], c.shape[-2]
+        batch = int(np.prod(c.shape[:-3], dtype=np.int64))
+        if out is None:
+            out = np.empty(c.shape[:-3] + (polys, l - 1, context.degree), dtype=np.uint64)
+        _check(load_library().hecuda_bfv_mod_switch_down(context._h, _ptr(c), polys, l, _ptr(out), batch))
+        return out
+
+    @staticmethod
+    def forwardNtt(context: Context, polys, base: int = BASE_Q):
+        """PolyRq.forwardNtt (PolyRq+Ntt.swift:230): (..., rows, N) Coeff -> Eval."""
+        d = _host(polys).copy()
+        rows = d.shape[-2]
+        _check(load_library().hecuda_ntt_forward(context._h, base, _ptr(d), rows, d.size // (rows * context.degree)))
+        return d
+
+    @staticmethod
+    def inverseNtt(context: Context, polys, base: int = BASE_Q):
+        """PolyRq.inverseNtt (PolyRq+Ntt.swift:541): (..., rows, N) Eval -> Coeff."""
+        d = _host(polys).copy()
+        rows = d.shape[-2]
+        _check(load_library().hecuda_ntt_inverse(context._h, base, _ptr(d), rows, d.size // (rows * context.degree)))
+        return d
+
+    @staticmethod
+    def forwardNttRows(context: Context, modulus: int, rows):
+        """PolyContext.forwardNtt(dataPtr:modulus:) (PolyRq+Ntt.swift:329-347)."""
+        d = _host(rows).copy()
+        _check(load_library().hecuda_ntt_forward_rows(context._h, modulus, _ptr(d), d.size // context.degree))
+        return d
+
+    @staticmethod
+    def inverseNttRows(context: Context, modulus: int, rows):
+        d = _host(rows).copy()
+        _check(load_library().hecuda_ntt_inverse_rows(context._h, modulus, _ptr(d), d.size // context.degree))
+        return d
