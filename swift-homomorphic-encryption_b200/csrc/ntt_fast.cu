@@ -1,0 +1,243 @@
+// ntt_fast.cu -- sm_100a kernels of the register-tiled NTT (see ntt_fast.cuh for the pass structure).
+// One CTA per row, N/16 threads, row staged in padded shared memory between passes, 16-byte coalesced global
+// accesses on the contiguous side.  Rows are dispatched per modulus class (NARROW / WIDE) so each launch runs
+// one specialised instruction stream.
+#include "kernels.cuh"
+#include "ntt_fast.cuh"
+
+namespace hecuda {
+using namespace fast;
+
+struct RowList {          // rows (within a polynomial) that one launch handles
+    int rows_per_poly;
+    int count;
+    unsigned char row[kMaxRows + 1];
+    unsigned char slot[kMaxRows + 1];
+};
+
+template <int LOGN, int LB, int C>
+__device__ __forceinline__ void load_smem(u64 (&x)[16], const u64 *sm, int tau) {
+#pragma unroll
+    for (int g = 0; g < (16 >> C); ++g)
+#pragma unroll
+        for (int a = 0; a < (1 << C); ++a) x[g * (1 << C) + a] = sm[smem_phys(elem_index<LOGN, LB, C>(tau, g, a))];
+}
+template <int LOGN, int LB, int C>
+__device__ __forceinline__ void store_smem(const u64 (&x)[16], u64 *sm, int tau) {
+#pragma unroll
+    for (int g = 0; g < (16 >> C); ++g)
+#pragma unroll
+        for (int a = 0; a < (1 << C); ++a) sm[smem_phys(elem_index<LOGN, LB, C>(tau, g, a))] = x[g * (1 << C) + a];
+}
+// global side: when LB == 0 a thread's 2^C elements of one sub-block are contiguous -> 16-byte vectors
+template <int LOGN, int LB, int C>
+__device__ __forceinline__ void load_global(u64 (&x)[16], const u64 *__restrict__ src, int tau) {
+    if (LB == 0 && C >= 1) {
+#pragma unroll
+        for (int g = 0; g < (16 >> C); ++g)
+#pragma unroll
+            for (int a = 0; a < (1 << C); a += 2) {
+                const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(src + elem_index<LOGN, LB, C>(tau, g, a));
+                x[g * (1 << C) + a] = v.x;
+                x[g * (1 << C) + a + 1] = v.y;
+            }
+    } else {
+#pragma unroll
+        for (int g = 0; g < (16 >> C); ++g)
+#pragma unroll
+            for (int a = 0; a < (1 << C); ++a) x[g * (1 << C) + a] = src[elem_index<LOGN, LB, C>(tau, g, a)];
+    }
+}
+template <int LOGN, int LB, int C>
+__device__ __forceinline__ void store_global(const u64 (&x)[16], u64 *__restrict__ dst, int tau) {
+    if (LB == 0 && C >= 1) {
+#pragma unroll
+        for (int g = 0; g < (16 >> C); ++g)
+#pragma unroll
+            for (int a = 0; a < (1 << C); a += 2)
+                *reinterpret_cast<ulonglong2 *>(dst + elem_index<LOGN, LB, C>(tau, g, a)) =
+                    make_ulonglong2(x[g * (1 << C) + a], x[g * (1 << C) + a + 1]);
+    } else {
+#pragma unroll
+        for (int g = 0; g < (16 >> C); ++g)
+#pragma unroll
+            for (int a = 0; a < (1 << C); ++a) dst[elem_index<LOGN, LB, C>(tau, g, a)] = x[g * (1 << C) + a];
+    }
+}
+
+template <int LOGN, bool NARROW>
+__global__ void __launch_bounds__((1 << LOGN) / 16, (1024 / ((1 << LOGN) / 16))) ntt_fwd_fast_kernel(const u64 *__restrict__ in, u64 *__restrict__ out,
+                                                                       const ModSlot *__restrict__ slots,
+                                                                       const __grid_constant__ RowList rl) {
+    extern __shared__ u64 sm[];
+    constexpr int P = plan_passes(LOGN);
+    const int tau = threadIdx.x;
+    const int64_t poly = blockIdx.x / rl.count;
+    const int which = blockIdx.x - poly * rl.count;
+    const int64_t row = poly * rl.rows_per_poly + rl.row[which];
+    const ModSlot &S = slots[rl.slot[which]];
+    RowMod m;
+    m.p = S.p;
+    m.two_p = 2 * S.p;
+    m.mu1 = S.mu1;
+    m.tw = S.tw;
+    const u64 *src = in + (row << LOGN);
+    u64 *dst = out + (row << LOGN);
+    u64 x[16];
+    {
+        constexpr int C = fwd_c(LOGN, 0), LB = fwd_lb(LOGN, 0);
+        load_global<LOGN, LB, C>(x, src, tau);
+        fwd_pass<LOGN, LB, C, NARROW>(x, tau, m);
+        store_smem<LOGN, LB, C>(x, sm, tau);
+    }
+    __syncthreads();
+    {
+        constexpr int C = fwd_c(LOGN, 1), LB = fwd_lb(LOGN, 1);
+        load_smem<LOGN, LB, C>(x, sm, tau);
+        fwd_pass<LOGN, LB, C, NARROW>(x, tau, m);
+        store_smem<LOGN, LB, C>(x, sm, tau);
+    }
+    __syncthreads();
+    if (P == 4) {
+        constexpr int C = fwd_c(LOGN, 2), LB = fwd_lb(LOGN, 2);
+        load_smem<LOGN, LB, C>(x, sm, tau);
+        fwd_pass<LOGN, LB, C, NARROW>(x, tau, m);
+        store_smem<LOGN, LB, C>(x, sm, tau);
+        __syncthreads();
+    }
+    {
+        constexpr int C = fwd_c(LOGN, P - 1), LB = fwd_lb(LOGN, P - 1);
+        load_smem<LOGN, LB, C>(x, sm, tau);
+        fwd_pass<LOGN, LB, C, NARROW>(x, tau, m);
+        fwd_finish<LOGN, NARROW>(x, m);
+        store_global<LOGN, LB, C>(x, dst, tau);
+    }
+}
+
+template <int LOGN, bool NARROW>
+__global__ void __launch_bounds__((1 << LOGN) / 16, (1024 / ((1 << LOGN) / 16))) ntt_inv_fast_kernel(const u64 *__restrict__ in, u64 *__restrict__ out,
+                                                                       const ModSlot *__restrict__ slots,
+                                                                       const __grid_constant__ RowList rl, int scale_t) {
+    extern __shared__ u64 sm[];
+    constexpr int P = plan_passes(LOGN);
+    const int tau = threadIdx.x;
+    const int64_t poly = blockIdx.x / rl.count;
+    const int which = blockIdx.x - poly * rl.count;
+    const int64_t row = poly * rl.rows_per_poly + rl.row[which];
+    const ModSlot &S = slots[rl.slot[which]];
+    RowMod m;
+    m.p = S.p;
+    m.two_p = 2 * S.p;
+    m.mu1 = S.mu1;
+    m.tw = S.itw;
+    m.c0 = scale_t ? S.tn_inv : S.n_inv;
+    m.c0p = scale_t ? S.tn_inv_p : S.n_inv_p;
+    m.c1 = scale_t ? S.tn_inv_w : S.n_inv_w;
+    m.c1p = scale_t ? S.tn_inv_w_p : S.n_inv_w_p;
+    const u64 *src = in + (row << LOGN);
+    u64 *dst = out + (row << LOGN);
+    u64 x[16];
+    {
+        constexpr int C = inv_c(LOGN, 0), LB = inv_lb(LOGN, 0);
+        load_global<LOGN, LB, C>(x, src, tau);
+        inv_pass<LOGN, LB, C, NARROW, inv_bound_in(LOGN, 0)>(x, tau, m);
+        store_smem<LOGN, LB, C>(x, sm, tau);
+    }
+    __syncthreads();
+    {
+        constexpr int C = inv_c(LOGN, 1), LB = inv_lb(LOGN, 1);
+        load_smem<LOGN, LB, C>(x, sm, tau);
+        if (NARROW && inv_reduce_at(LOGN, 1)) inv_reduce<0>(x, m);
+        inv_pass<LOGN, LB, C, NARROW, inv_bound_in(LOGN, 1)>(x, tau, m);
+        store_smem<LOGN, LB, C>(x, sm, tau);
+    }
+    __syncthreads();
+    if (P == 4) {
+        constexpr int C = inv_c(LOGN, 2), LB = inv_lb(LOGN, 2);
+        load_smem<LOGN, LB, C>(x, sm, tau);
+        if (NARROW && inv_reduce_at(LOGN, 2)) inv_reduce<0>(x, m);
+        inv_pass<LOGN, LB, C, NARROW, inv_bound_in(LOGN, 2)>(x, tau, m);
+        store_smem<LOGN, LB, C>(x, sm, tau);
+        __syncthreads();
+    }
+    {
+        constexpr int C = inv_c(LOGN, P - 1), LB = inv_lb(LOGN, P - 1);
+        load_smem<LOGN, LB, C>(x, sm, tau);
+        if (NARROW && inv_reduce_at(LOGN, P - 1)) inv_reduce<0>(x, m);
+        inv_pass<LOGN, LB, C, NARROW, inv_bound_in(LOGN, P - 1)>(x, tau, m);
+        store_global<LOGN, LB, C>(x, dst, tau);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- launch
+static void build_row_lists(const Context &ctx, const NttRowMap &map, RowList &narrow, RowList &wide) {
+    narrow.rows_per_poly = wide.rows_per_poly = map.rows_per_poly;
+    narrow.count = wide.count = 0;
+    for (int r = 0; r < map.rows_per_poly; ++r) {
+        const int slot = map.slot[r / map.group];
+        RowList &l = ctx.slots[slot].dev.bits <= kNarrowBits ? narrow : wide;
+        l.row[l.count] = (unsigned char)r;
+        l.slot[l.count] = (unsigned char)slot;
+        ++l.count;
+    }
+}
+
+template <int LOGN, bool NARROW, bool INVERSE>
+static cudaError_t launch_class(const Context &ctx, const RowList &rl, const u64 *in, u64 *out, int64_t polys,
+                                bool scale_t, cudaStream_t stream) {
+    if (rl.count == 0 || polys == 0) return cudaSuccess;
+    constexpr int threads = (1 << LOGN) / 16;
+    constexpr size_t smem = sizeof(u64) * smem_words(LOGN);
+    const int64_t blocks = polys * rl.count;
+    if (blocks > 0x7fffffffLL) return cudaErrorInvalidValue;
+    cudaError_t e;
+    ++g_kernel_launches;
+    if (INVERSE) {
+        auto k = ntt_inv_fast_kernel<LOGN, NARROW>;
+        if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        k<<<(unsigned)blocks, threads, smem, stream>>>(in, out, ctx.d_slots, rl, scale_t ? 1 : 0);
+    } else {
+        auto k = ntt_fwd_fast_kernel<LOGN, NARROW>;
+        if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        k<<<(unsigned)blocks, threads, smem, stream>>>(in, out, ctx.d_slots, rl);
+    }
+    return cudaGetLastError();
+}
+
+template <int LOGN, bool INVERSE>
+static cudaError_t launch_logn(const Context &ctx, const NttRowMap &map, const u64 *in, u64 *out, int64_t rows,
+                               bool scale_t, cudaStream_t stream) {
+    if (rows % map.rows_per_poly) return cudaErrorInvalidValue;
+    RowList narrow, wide;
+    build_row_lists(ctx, map, narrow, wide);
+    const int64_t polys = rows / map.rows_per_poly;
+    cudaError_t e = launch_class<LOGN, true, INVERSE>(ctx, narrow, in, out, polys, scale_t, stream);
+    if (e != cudaSuccess) return e;
+    return launch_class<LOGN, false, INVERSE>(ctx, wide, in, out, polys, scale_t, stream);
+}
+
+bool ntt_fast_supported(const Context &ctx) { return ctx.logn >= kMinLogN && ctx.logn <= kMaxLogN; }
+
+template <bool INVERSE>
+static cudaError_t launch_fast(const Context &ctx, const NttRowMap &map, const u64 *in, u64 *out, int64_t rows,
+                               bool scale_t, cudaStream_t stream) {
+    switch (ctx.logn) {
+        case 10: return launch_logn<10, INVERSE>(ctx, map, in, out, rows, scale_t, stream);
+        case 11: return launch_logn<11, INVERSE>(ctx, map, in, out, rows, scale_t, stream);
+        case 12: return launch_logn<12, INVERSE>(ctx, map, in, out, rows, scale_t, stream);
+        case 13: return launch_logn<13, INVERSE>(ctx, map, in, out, rows, scale_t, stream);
+        case 14: return launch_logn<14, INVERSE>(ctx, map, in, out, rows, scale_t, stream);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+cudaError_t launch_ntt_forward_fast(const Context &ctx, const NttRowMap &map, const u64 *in, u64 *out, int64_t rows,
+                                    cudaStream_t stream) {
+    return launch_fast<false>(ctx, map, in, out, rows, false, stream);
+}
+cudaError_t launch_ntt_inverse_fast(const Context &ctx, const NttRowMap &map, const u64 *in, u64 *out, int64_t rows,
+                                    bool scale_t, cudaStream_t stream) {
+    return launch_fast<true>(ctx, map, in, out, rows, scale_t, stream);
+}
+
+}  // namespace hecuda
