@@ -12,6 +12,8 @@
 
 namespace hecuda {
 
+// Bounds (checked for the actual moduli by Context::create): every 128-bit accumulator below stays < 2^127 and the
+// Montgomery-reduced sums are < 2p (lift, f_j, out_i) or < 4p (alpha), so the conditional subtractions shown suffice.
 template <int L>
 __global__ void __launch_bounds__(256) lift_kernel(const u64 *__restrict__ in, int polys_in, u64 *__restrict__ ext,
                                                   int ext_polys, int out_poly_offset, const __grid_constant__ LiftConsts c,
@@ -29,22 +31,23 @@ __global__ void __launch_bounds__(256) lift_kernel(const u64 *__restrict__ in, i
     for (int i = 0; i < L; ++i) {
         const u64 x = src[(int64_t)i * n];
         dst[(int64_t)i * n] = x;
-        z[i] = shoup_mul(x, c.in_w[i], c.in_wp[i], c.q[i]);
+        z[i] = shoup_mul(x, c.in_w[i], c.in_wp[i], c.q[i]);  // canonical: reinterpreted mod b_j and mod m~ below
         acc_mt += (u32)z[i] * c.punct_mt[i];
     }
     const u32 r = acc_mt * c.neg_inv_q_mt;        // [-x' Q^-1]_{m~}, RnsTool.swift:343-348
     const bool neg = r >= 0x80000000u;            // centered representative r - m~ (:357-360)
 #pragma unroll
     for (int j = 0; j <= L; ++j) {
-        u128w acc = {0, 0};
-#pragma unroll
-        for (int i = 0; i < L; ++i) mac_wide(acc, z[i], c.mat[j][i]);
         const u64 rc = neg ? (u64)r + c.b[j] - 0x100000000ull : (u64)r;
-        mac_wide(acc, rc, c.qr[j]);
-        dst[(int64_t)(L + j) * n] = barrett128(acc, c.b[j], c.b_mu_hi[j], c.b_mu_lo[j]);
+        u128 acc = (u128)rc * c.qr[j];
+#pragma unroll
+        for (int i = 0; i < L; ++i) mac128(acc, z[i], c.mat[j][i]);
+        dst[(int64_t)(L + j) * n] = csub(mont_reduce(acc, c.b[j], c.b_ninv[j]), c.b[j]);
     }
 }
 
+// Tensor product in Montgomery form: out = a b 2^-64 mod p (canonical).  The missing 2^64 is restored by the
+// kScaleTMont scaling of the inverse NTT that always follows (Bfv+Multiply.swift:80-82 then :40-41).
 __global__ void __launch_bounds__(256) tensor_kernel(const u64 *__restrict__ ext, u64 *__restrict__ ten,
                                                     const ModSlot *__restrict__ slots, NttRowMap map, int64_t n) {
     const int R = map.rows_per_poly;
@@ -53,17 +56,16 @@ __global__ void __launch_bounds__(256) tensor_kernel(const u64 *__restrict__ ext
     const int64_t coeff = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (coeff >= n) return;
     const ModSlot &S = slots[map.slot[row]];
-    const u64 p = S.p, mu = S.mu_prod;
-    const int s = S.s_prod;
+    const u64 p = S.p, ninv = S.ninv;
     const u64 *e = ext + (item * 4 * R + row) * n + coeff;
     const int64_t ps = (int64_t)R * n;
     const u64 a0 = e[0], a1 = e[ps], b0 = e[2 * ps], b1 = e[3 * ps];
     u64 *o = ten + (item * 3 * R + row) * n + coeff;
-    o[0] = barrett_prod(mul_wide(a0, b0), p, mu, s);
-    const u64 x = barrett_prod(mul_wide(a0, b1), p, mu, s);
-    const u64 y = barrett_prod(mul_wide(a1, b0), p, mu, s);
-    o[ps] = add_mod(x, y, p);
-    o[2 * ps] = barrett_prod(mul_wide(a1, b1), p, mu, s);
+    o[0] = csub(mont_reduce((u128)a0 * b0, p, ninv), p);
+    u128 mid = (u128)a0 * b1;
+    mac128(mid, a1, b0);
+    o[ps] = csub(mont_reduce(mid, p, ninv), p);
+    o[2 * ps] = csub(mont_reduce((u128)a1 * b1, p, ninv), p);
 }
 
 template <int L>
@@ -78,33 +80,34 @@ __global__ void __launch_bounds__(256) floor_kernel(const u64 *__restrict__ in, 
     u64 y[L];
 #pragma unroll
     for (int i = 0; i < L; ++i) y[i] = shoup_mul(src[(int64_t)i * n], c.inq_w[i], c.inq_wp[i], c.q[i]);
-    // approximateFloor, RnsTool.swift:378-398: f_j = (x_bj - FBC(x_Q)_j) Q^-1 mod b_j
+    // approximateFloor, RnsTool.swift:378-398: f_j = (x_bj - FBC(x_Q)_j) Q^-1 mod b_j   (kept lazy, < 2 b_j)
     u64 f[L + 1];
 #pragma unroll
     for (int j = 0; j <= L; ++j) {
-        u128w acc = mul_wide(src[(int64_t)(L + j) * n], c.fq[j]);
+        u128 acc = (u128)src[(int64_t)(L + j) * n] * c.fq[j];
 #pragma unroll
-        for (int i = 0; i < L; ++i) mac_wide(acc, y[i], c.fmat[j][i]);
-        f[j] = barrett128(acc, c.b[j], c.b_mu_hi[j], c.b_mu_lo[j]);
+        for (int i = 0; i < L; ++i) mac128(acc, y[i], c.fmat[j][i]);
+        f[j] = mont_reduce(acc, c.b[j], c.b_ninv[j]);
     }
     // convertApproximateBskToQ, RnsTool.swift:402-450
     const u64 msk = c.b[L];
     u64 w[L];
-    u128w acc = mul_wide(f[L], c.a_msk);
+    u128 acc = (u128)f[L] * c.a_msk;
 #pragma unroll
     for (int k = 0; k < L; ++k) {
-        w[k] = shoup_mul(f[k], c.inb_w[k], c.inb_wp[k], c.b[k]);
-        mac_wide(acc, w[k], c.amat[k]);
+        w[k] = shoup_mul(f[k], c.inb_w[k], c.inb_wp[k], c.b[k]);  // canonical: reinterpreted mod m_sk and mod q_i
+        mac128(acc, w[k], c.amat[k]);
     }
-    const u64 alpha = barrett128(acc, msk, c.b_mu_hi[L], c.b_mu_lo[L]);
+    u64 alpha = mont_reduce(acc, msk, c.b_ninv[L]);
+    alpha = csub(csub(csub(alpha, 4 * msk), 2 * msk), msk);
     const bool exceeds = alpha > (msk >> 1);
     const u64 alpha_c = exceeds ? msk - alpha : alpha;
 #pragma unroll
     for (int i = 0; i < L; ++i) {
-        u128w o = mul_wide(alpha_c, exceeds ? c.b_mod_q[i] : c.neg_b_mod_q[i]);
+        u128 o = (u128)alpha_c * (exceeds ? c.b_mod_q[i] : c.neg_b_mod_q[i]);
 #pragma unroll
-        for (int k = 0; k < L; ++k) mac_wide(o, w[k], c.omat[i][k]);
-        dst[(int64_t)i * n] = barrett128(o, c.q[i], c.q_mu_hi[i], c.q_mu_lo[i]);
+        for (int k = 0; k < L; ++k) mac128(o, w[k], c.omat[i][k]);
+        dst[(int64_t)i * n] = csub(csub(mont_reduce(o, c.q[i], c.q_ninv[i]), 2 * c.q[i]), c.q[i]);
     }
 }
 

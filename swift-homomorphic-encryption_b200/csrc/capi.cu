@@ -164,7 +164,7 @@ cudaError_t multiply_chunk(const Context &c, u64 *scratch, const u64 *lhs, const
     // tensor product                                               (Bfv+Multiply.swift:80-82)
     if ((e = launch_tensor(c, ext, ten, items, s)) != cudaSuccess) return e;
     // dropExtendedBase: (* t) folded into the inverse NTT, floor    (Bfv+Multiply.swift:31-48)
-    if ((e = launch_ntt_inverse(c, map, ten, ten, items * 3 * R, true, s)) != cudaSuccess) return e;
+    if ((e = launch_ntt_inverse(c, map, ten, ten, items * 3 * R, kScaleTMont, s)) != cudaSuccess) return e;
     return launch_floor(c, ten, out, items * 3, s);
 }
 
@@ -177,7 +177,7 @@ cudaError_t relinearize_chunk(const Context &c, u64 *scratch, const u64 *key, co
     if ((e = launch_ks_digits(c, ct3 + (int64_t)2 * l * c.n, ct_stride, l, dig, items, s)) != cudaSuccess) return e;
     if ((e = launch_ntt_forward(c, c.map_ks_digits(l), dig, dig, items * (l + 1) * l, s)) != cudaSuccess) return e;
     if ((e = launch_ks_mac(c, dig, key, l, prod, items, s)) != cudaSuccess) return e;
-    if ((e = launch_ntt_inverse(c, c.map_ks(l), prod, prod, items * 2 * (l + 1), false, s)) != cudaSuccess) return e;
+    if ((e = launch_ntt_inverse(c, c.map_ks(l), prod, prod, items * 2 * (l + 1), kScaleMont, s)) != cudaSuccess) return e;
     return launch_ks_finish(c, prod, ct3, ct_stride, l, out, items, s);
 }
 
@@ -294,8 +294,10 @@ int32_t hecuda_context_create(int64_t poly_degree, const uint64_t *coefficient_m
         }
     }
     // pipeline stage size: keep one stage's intermediates (7 R N words per ciphertext pair) near the L2 size
+    // Every kernel on this path is instruction-issue bound, not HBM bound, so large launches that
+    // amortise wave tails beat L2-resident small ones: size a stage to ~2 GB of scratch.
     const size_t per_item = (size_t)7 * (2 * c->L + 1) * c->n * sizeof(u64);
-    int64_t chunk = (int64_t)((size_t)96 * 1024 * 1024 / per_item);
+    int64_t chunk = (int64_t)((size_t)2048 * 1024 * 1024 / per_item);
     if (const char *env = std::getenv("HECUDA_CHUNK")) chunk = std::atoll(env);
     h->chunk = std::max<int64_t>(1, std::min<int64_t>(chunk, 4096));
     *out = h;
@@ -348,7 +350,7 @@ static int32_t ntt_device(const hecuda_context *h, int32_t base, uint64_t *data,
     NttRowMap map;
     std::string err;
     if (!make_map(*h->ctx, base, rows, map, err)) return fail(HECUDA_ERR_INVALID_ARGUMENT, err);
-    cudaError_t e = inverse ? launch_ntt_inverse(*h->ctx, map, (u64 *)data, (u64 *)data, polys * rows, false,
+    cudaError_t e = inverse ? launch_ntt_inverse(*h->ctx, map, (u64 *)data, (u64 *)data, polys * rows, kScalePlain,
                                                  (cudaStream_t)stream)
                             : launch_ntt_forward(*h->ctx, map, (u64 *)data, (u64 *)data, polys * rows,
                                                  (cudaStream_t)stream);
@@ -372,7 +374,7 @@ static int32_t ntt_host(const hecuda_context *h, const NttRowMap &map, uint64_t 
     const int64_t chunk = std::max<int64_t>(1, (int64_t)((size_t)4 * 1024 * 1024 / std::max<size_t>(1, words_per_item)));
     return host_pipeline(h, items, chunk, 0, in, (u64 *)data, words_per_item,
                          [&](Workspace &w, const std::vector<const u64 *> &d_in, u64 *d_out, int64_t n_items) {
-                             return inverse ? launch_ntt_inverse(c, map, d_in[0], d_out, n_items * rows_per_item, false,
+                             return inverse ? launch_ntt_inverse(c, map, d_in[0], d_out, n_items * rows_per_item, kScalePlain,
                                                                  w.stream)
                                             : launch_ntt_forward(c, map, d_in[0], d_out, n_items * rows_per_item,
                                                                  w.stream);

@@ -57,14 +57,20 @@ static bool build_slot(HostSlot &hs, u64 p, int64_t n, int logn, u64 t, std::vec
     }
     const u64 n_inv = invmod((u64)n % p, p);
     const u64 w1_inv = n > 1 ? hs.inv_roots[1] : 1;  // psi^-(N/2)
-    d.n_inv = n_inv;
-    d.n_inv_p = shoup_factor(d.n_inv, p);
-    d.n_inv_w = mulmod(n_inv, w1_inv, p);
-    d.n_inv_w_p = shoup_factor(d.n_inv_w, p);
-    d.tn_inv = mulmod(n_inv, t % p, p);
-    d.tn_inv_p = shoup_factor(d.tn_inv, p);
-    d.tn_inv_w = mulmod(d.tn_inv, w1_inv, p);
-    d.tn_inv_w_p = shoup_factor(d.tn_inv_w, p);
+    d.r64 = (u64)(((u128)1 << 64) % p);
+    {   // -p^-1 mod 2^64 by Newton iteration
+        u64 inv = p;  // correct to 3 bits for odd p
+        for (int i = 0; i < 6; ++i) inv *= 2 - p * inv;
+        d.ninv = 0 - inv;
+    }
+    const u64 scalings[3] = {1 % p, mulmod(t % p, d.r64, p), d.r64};
+    for (int k = 0; k < 3; ++k) {
+        ModSlot::InvScale &sc = d.inv_scale[k];
+        sc.c0 = mulmod(n_inv, scalings[k], p);
+        sc.c0p = shoup_factor(sc.c0, p);
+        sc.c1 = mulmod(sc.c0, w1_inv, p);
+        sc.c1p = shoup_factor(sc.c1, p);
+    }
     return true;
 }
 
@@ -156,10 +162,10 @@ Context *Context::create(int64_t n, const u64 *coeff_moduli, int nmod, u64 t, st
     }
     for (int j = 0; j <= L; ++j) {
         const u64 bj = BSK[j];
-        u64 mu1;
         lf.b[j] = bj;
-        fill_barrett(bj, mu1, lf.b_mu_hi[j], lf.b_mu_lo[j]);
-        const u64 mt_inv = invmod(kMTilde % bj, bj);
+        lf.b_ninv[j] = c->slots[c->slot_bsk(j)].dev.ninv;
+        const u64 r64 = c->slots[c->slot_bsk(j)].dev.r64;
+        const u64 mt_inv = mulmod(invmod(kMTilde % bj, bj), r64, bj);  // m~^-1 2^64
         for (int i = 0; i < L; ++i) lf.mat[j][i] = mulmod(punctured_mod(Q, L, i, bj), mt_inv, bj);
         lf.qr[j] = mulmod(prod_mod(Q, L, bj), mt_inv, bj);
     }
@@ -167,25 +173,25 @@ Context *Context::create(int64_t n, const u64 *coeff_moduli, int nmod, u64 t, st
     std::memset(&fl, 0, sizeof(fl));
     fl.L = L;
     const u64 b_mod_msk = prod_mod(BSK, L, msk);
-    const u64 b_inv_msk = invmod(b_mod_msk, msk);
+    const u64 r64_msk = c->slots[c->slot_bsk(L)].dev.r64;
+    const u64 b_inv_msk = mulmod(invmod(b_mod_msk, msk), r64_msk, msk);  // B^-1 2^64
     fl.a_msk = (msk - b_inv_msk) % msk;
     for (int i = 0; i < L; ++i) {
         const u64 qi = Q[i];
-        u64 mu1;
         fl.q[i] = qi;
-        fill_barrett(qi, mu1, fl.q_mu_hi[i], fl.q_mu_lo[i]);
+        fl.q_ninv[i] = c->slots[c->slot_q(i)].dev.ninv;
+        const u64 r64 = c->slots[c->slot_q(i)].dev.r64;
         fl.inq_w[i] = invmod(punctured_mod(Q, L, i, qi), qi);
         fl.inq_wp[i] = shoup_factor(fl.inq_w[i], qi);
-        for (int k = 0; k < L; ++k) fl.omat[i][k] = punctured_mod(BSK, L, k, qi);
-        fl.b_mod_q[i] = prod_mod(BSK, L, qi);
+        for (int k = 0; k < L; ++k) fl.omat[i][k] = mulmod(punctured_mod(BSK, L, k, qi), r64, qi);
+        fl.b_mod_q[i] = mulmod(prod_mod(BSK, L, qi), r64, qi);
         fl.neg_b_mod_q[i] = (qi - fl.b_mod_q[i]) % qi;
     }
     for (int j = 0; j <= L; ++j) {
         const u64 bj = BSK[j];
-        u64 mu1;
         fl.b[j] = bj;
-        fill_barrett(bj, mu1, fl.b_mu_hi[j], fl.b_mu_lo[j]);
-        const u64 q_inv = invmod(prod_mod(Q, L, bj), bj);
+        fl.b_ninv[j] = c->slots[c->slot_bsk(j)].dev.ninv;
+        const u64 q_inv = mulmod(invmod(prod_mod(Q, L, bj), bj), c->slots[c->slot_bsk(j)].dev.r64, bj);  // Q^-1 2^64
         fl.fq[j] = q_inv;
         for (int i = 0; i < L; ++i) {
             const u64 v = mulmod(punctured_mod(Q, L, i, bj), q_inv, bj);
@@ -197,6 +203,19 @@ Context *Context::create(int64_t n, const u64 *coeff_moduli, int nmod, u64 t, st
         fl.inb_w[k] = invmod(punctured_mod(BSK, L, k, bk), bk);
         fl.inb_wp[k] = shoup_factor(fl.inb_w[k], bk);
         fl.amat[k] = mulmod(punctured_mod(BSK, L, k, msk), b_inv_msk, msk);
+    }
+
+    // ---- range check behind the single conditional subtraction after the lift / approximate-floor sums:
+    // (b_j^2 + L q_max b_j) / 2^64 < b_j  <=>  b_j + L q_max < 2^64   (see behz.cu)
+    {
+        u64 qmax = 0, bmax = 0;
+        for (u64 v : c->q) qmax = v > qmax ? v : qmax;
+        for (u64 v : c->bsk) bmax = v > bmax ? v : bmax;
+        if ((u128)bmax + (u128)L * qmax >= ((u128)1 << 64)) {
+            err = "unsupportedHeOperation: " + std::to_string(L) + " ciphertext moduli of this size exceed the lazy-sum bound";
+            delete c;
+            return nullptr;
+        }
     }
 
     // ---- divide-and-round constants

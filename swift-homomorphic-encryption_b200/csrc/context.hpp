@@ -27,13 +27,19 @@ struct ModSlot {
     u64 mu_prod;      // floor(2^(bits+62) / p)
     int s_prod;       // bits - 2
     int bits;
-    u64 n_inv, n_inv_p;       // N^-1                       (PolyRq+Ntt.swift:159-160)
-    u64 n_inv_w, n_inv_w_p;   // N^-1 * psi^-(N/2)          (PolyRq+Ntt.swift:162-168)
-    u64 tn_inv, tn_inv_p;     // t * N^-1        (poly * tVec folded into the inverse NTT, Bfv+Multiply.swift:40)
-    u64 tn_inv_w, tn_inv_w_p; // t * N^-1 * psi^-(N/2)
+    u64 ninv;         // -p^-1 mod 2^64 (Montgomery)
+    u64 r64;          // 2^64 mod p
+    // Last inverse-NTT stage: x' = (x + y) c0, y' = (x - y) c1 with c0 = s N^-1, c1 = s N^-1 psi^-(N/2)
+    // (PolyRq+Ntt.swift:159-168,416-419) for three scalings s:
+    //   kScalePlain  s = 1                 the reference's inverseNtt
+    //   kScaleTMont  s = t 2^64            after the Montgomery-form tensor product; folds `poly * tVec` (Bfv+Multiply.swift:40)
+    //   kScaleMont   s = 2^64              after the Montgomery-reduced key-switch accumulation
+    struct InvScale { u64 c0, c0p, c1, c1p; } inv_scale[3];
     const ulonglong2 *tw;     // forward twiddles  [N]
     const ulonglong2 *itw;    // inverse twiddles  [N]  (itw[m+i] = tw[m+i]^-1)
 };
+
+enum { kScalePlain = 0, kScaleTMont = 1, kScaleMont = 2 };
 
 struct NttRowMap {       // which modulus slot each row of a polynomial uses:
     int rows_per_poly;   //   slot[((row % rows_per_poly) / group)]
@@ -41,35 +47,36 @@ struct NttRowMap {       // which modulus slot each row of a polynomial uses:
     unsigned char slot[kMaxRows + 1];
 };
 
-// liftQToQBsk (RnsTool.swift:324-368) fused to: z_i = [x_i * in_w_i]_{q_i};
-//   r = [ -Q^-1 * sum_i z_i (Q/q_i) ]_{2^32}, centered;  out_j = [ sum_i z_i mat[j][i] + r_c * qr[j] ]_{b_j}
+// liftQToQBsk (RnsTool.swift:324-368) fused to: z_i = [x_i * in_w_i]_{q_i} (canonical);
+//   r = [ -Q^-1 * sum_i z_i (Q/q_i) ]_{2^32}, centered;
+//   out_j = [ (sum_i z_i mat[j][i] + r_c qr[j]) 2^-64 ]_{b_j}   with mat, qr pre-multiplied by 2^64 (Montgomery)
 struct LiftConsts {
     int L;
     u64 q[kMaxL];
     u64 in_w[kMaxL], in_wp[kMaxL];   // m~ (Q/q_i)^-1 mod q_i
     u32 punct_mt[kMaxL];             // (Q/q_i) mod 2^32
     u32 neg_inv_q_mt;                // -Q^-1 mod 2^32
-    u64 b[kMaxL + 1], b_mu_hi[kMaxL + 1], b_mu_lo[kMaxL + 1];
-    u64 mat[kMaxL + 1][kMaxL];       // (Q/q_i) m~^-1 mod b_j
-    u64 qr[kMaxL + 1];               // Q m~^-1 mod b_j
+    u64 b[kMaxL + 1], b_ninv[kMaxL + 1];
+    u64 mat[kMaxL + 1][kMaxL];       // (Q/q_i) m~^-1 2^64 mod b_j
+    u64 qr[kMaxL + 1];               // Q m~^-1 2^64 mod b_j
 };
 
-// floorQBskToQ (RnsTool.swift:378-456) fused to:
-//   y_i = [x_i inq_w_i]_{q_i};  f_j = [x_bj fq[j] + sum_i y_i fmat[j][i]]_{b_j}           (approximateFloor)
-//   w_k = [f_k inb_w_k]_{b_k};  alpha = [sum_k w_k amat[k] + f_msk a_msk]_{m_sk}          (Shenoy-Kumaresan)
+// floorQBskToQ (RnsTool.swift:378-456) fused to (all matrix constants pre-multiplied by 2^64, sums Montgomery-reduced):
+//   y_i = [x_i inq_w_i]_{q_i} (canonical);  f_j = [x_bj fq[j] + sum_i y_i fmat[j][i]]_{b_j}  (approximateFloor, lazy < 2 b_j)
+//   w_k = [f_k inb_w_k]_{b_k} (canonical);  alpha = [sum_k w_k amat[k] + f_msk a_msk]_{m_sk}  (Shenoy-Kumaresan)
 //   out_i = [sum_k w_k omat[i][k] + alpha' D_i]_{q_i},  (alpha', D) = alpha > m_sk/2 ? (m_sk-alpha, B) : (alpha, -B)
 struct FloorConsts {
     int L;
-    u64 q[kMaxL], q_mu_hi[kMaxL], q_mu_lo[kMaxL];
+    u64 q[kMaxL], q_ninv[kMaxL];
     u64 inq_w[kMaxL], inq_wp[kMaxL];   // (Q/q_i)^-1 mod q_i
-    u64 b[kMaxL + 1], b_mu_hi[kMaxL + 1], b_mu_lo[kMaxL + 1];
-    u64 fq[kMaxL + 1];                 // Q^-1 mod b_j
-    u64 fmat[kMaxL + 1][kMaxL];        // -(Q/q_i) Q^-1 mod b_j
+    u64 b[kMaxL + 1], b_ninv[kMaxL + 1];
+    u64 fq[kMaxL + 1];                 // Q^-1 2^64 mod b_j
+    u64 fmat[kMaxL + 1][kMaxL];        // -(Q/q_i) Q^-1 2^64 mod b_j
     u64 inb_w[kMaxL], inb_wp[kMaxL];   // (B/b_k)^-1 mod b_k
-    u64 amat[kMaxL];                   // (B/b_k) B^-1 mod m_sk
-    u64 a_msk;                         // -B^-1 mod m_sk
-    u64 omat[kMaxL][kMaxL];            // (B/b_k) mod q_i
-    u64 b_mod_q[kMaxL], neg_b_mod_q[kMaxL];
+    u64 amat[kMaxL];                   // (B/b_k) B^-1 2^64 mod m_sk
+    u64 a_msk;                         // -B^-1 2^64 mod m_sk
+    u64 omat[kMaxL][kMaxL];            // (B/b_k) 2^64 mod q_i
+    u64 b_mod_q[kMaxL], neg_b_mod_q[kMaxL];  // +-B 2^64 mod q_i
 };
 
 // divideAndRoundQLast (PolyRq.swift:365-393) for a base [m_0..m_{l-2}, m_last]

@@ -16,20 +16,20 @@ extern std::atomic<unsigned long long> g_kernel_launches;  // every <<<>>> issue
 cudaError_t launch_ntt_forward(const Context &ctx, const NttRowMap &map, const u64 *in, u64 *out, int64_t rows,
                                cudaStream_t stream);
 cudaError_t launch_ntt_inverse(const Context &ctx, const NttRowMap &map, const u64 *in, u64 *out, int64_t rows,
-                               bool scale_t, cudaStream_t stream);
+                               int scale_mode, cudaStream_t stream);
 
 // implementations behind the dispatcher (ntt_simple.cu)
 cudaError_t launch_ntt_forward_simple(const Context &ctx, const NttRowMap &map, const u64 *in, u64 *out, int64_t rows,
                                       cudaStream_t stream);
 cudaError_t launch_ntt_inverse_simple(const Context &ctx, const NttRowMap &map, const u64 *in, u64 *out, int64_t rows,
-                                      bool scale_t, cudaStream_t stream);
+                                      int scale_mode, cudaStream_t stream);
 
 // register-tiled kernels (ntt_fast.cu), N = 2^10 .. 2^14
 bool ntt_fast_supported(const Context &ctx);
 cudaError_t launch_ntt_forward_fast(const Context &ctx, const NttRowMap &map, const u64 *in, u64 *out, int64_t rows,
                                     cudaStream_t stream);
 cudaError_t launch_ntt_inverse_fast(const Context &ctx, const NttRowMap &map, const u64 *in, u64 *out, int64_t rows,
-                                    bool scale_t, cudaStream_t stream);
+                                    int scale_mode, cudaStream_t stream);
 
 // ---- BEHZ steps of ct x ct multiply (behz.cu)
 // lift: `items` x polys_in x L x N  ->  ext[item][out_poly_offset + p][R][N]  with ext item stride ext_polys*R*N

@@ -37,16 +37,19 @@ __global__ void __launch_bounds__(256) ks_mac_kernel(const u64 *__restrict__ dig
     if (coeff >= n) return;
     const ModSlot &S = slots[ks_map.slot[r]];
     const int key_row = (r == l) ? K - 1 : r;  // Bfv+Keys.swift:153
-    u128w acc0 = {0, 0}, acc1 = {0, 0};
+    // 128-bit lazy accumulation like the reference (:187-190), Montgomery-reduced: prod = sum * 2^-64, restored by the
+    // kScaleMont scaling of the inverse NTT that follows.  sum < l p^2 < 2^127, reduced value < 2^-64 sum + p < (1 + l/4) p <= 5p.
+    u128 acc0 = 0, acc1 = 0;
     for (int j = 0; j < l; ++j) {
         const u64 d = dig[((item * (l + 1) + r) * l + j) * n + coeff];
         const u64 *kj = key + ((int64_t)j * 2 * K + key_row) * n + coeff;
-        mac_wide(acc0, d, kj[0]);
-        mac_wide(acc1, d, kj[(int64_t)K * n]);
+        mac128(acc0, d, kj[0]);
+        mac128(acc1, d, kj[(int64_t)K * n]);
     }
     u64 *o = prod + ((item * 2) * (l + 1) + r) * n + coeff;
-    o[0] = barrett128(acc0, S.p, S.mu_hi, S.mu_lo);
-    o[(int64_t)(l + 1) * n] = barrett128(acc1, S.p, S.mu_hi, S.mu_lo);
+    const u64 p = S.p;
+    o[0] = csub(csub(csub(mont_reduce(acc0, p, S.ninv), 4 * p), 2 * p), p);
+    o[(int64_t)(l + 1) * n] = csub(csub(csub(mont_reduce(acc1, p, S.ninv), 4 * p), 2 * p), p);
 }
 
 // divide-and-round by the last modulus of `in` (rows c.l), optionally adding `base`, write c.l - 1 rows

@@ -81,6 +81,19 @@ HE_HD u64 barrett128(u128w x, u64 p, u64 mu_hi, u64 mu_lo) {
     return csub(x.lo - q * p, p);
 }
 
+// ---- 128-bit accumulation + Montgomery reduction (the workhorse of the base-conversion kernels).
+// acc = sum of 64x64 products; mont_reduce returns acc * 2^-64 mod p in [0, (acc >> 64) + p), with
+// ninv = -p^-1 mod 2^64.  The 2^64 factor is folded into precomputed constants (or into the scaling of the
+// following inverse NTT), so results are the same canonical residues as the reference's Barrett path
+// (RnsBaseConverter.swift:117-143 accumulates in DoubleWidth and reduces once, like this).
+typedef unsigned __int128 u128;
+HE_HD void mac128(u128 &acc, u64 a, u64 b) { acc += (u128)a * b; }
+HE_HD u64 mont_reduce(u128 acc, u64 p, u64 ninv) {
+    const u64 lo = (u64)acc, hi = (u64)(acc >> 64);
+    const u64 m = lo * ninv;
+    return hi + mulhi64(m, p) + (lo != 0 ? 1ull : 0ull);
+}
+
 // Product Barrett: (hi:lo) mod p for values < 4 p^2, p < 2^61 (tensor products and sums of two of them).
 // s = bits(p) - 2, mu = floor(2^(s+64) / p).  Result canonical.
 // (reference: ReduceModulus.reduceProduct, Modulus.swift:349-360, which covers x < p^2 with one csub;

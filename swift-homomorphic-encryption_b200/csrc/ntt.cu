@@ -23,9 +23,9 @@ cudaError_t launch_ntt_forward(const Context &ctx, const NttRowMap &map, const u
 }
 
 cudaError_t launch_ntt_inverse(const Context &ctx, const NttRowMap &map, const u64 *in, u64 *out, int64_t rows,
-                               bool scale_t, cudaStream_t stream) {
-    if (use_fast(ctx)) return launch_ntt_inverse_fast(ctx, map, in, out, rows, scale_t, stream);
-    return launch_ntt_inverse_simple(ctx, map, in, out, rows, scale_t, stream);
+                               int scale_mode, cudaStream_t stream) {
+    if (use_fast(ctx)) return launch_ntt_inverse_fast(ctx, map, in, out, rows, scale_mode, stream);
+    return launch_ntt_inverse_simple(ctx, map, in, out, rows, scale_mode, stream);
 }
 
 }  // namespace hecuda

@@ -8,62 +8,13 @@
 namespace hecuda {
 using namespace fast;
 
+constexpr int kMaxRowList = (kMaxL + 1) * kMaxL;  // key-switch digit rows: (l + 1) * l
 struct RowList {          // rows (within a polynomial) that one launch handles
     int rows_per_poly;
     int count;
-    unsigned char row[kMaxRows + 1];
-    unsigned char slot[kMaxRows + 1];
+    unsigned short row[kMaxRowList];
+    unsigned char slot[kMaxRowList];
 };
-
-template <int LOGN, int LB, int C>
-__device__ __forceinline__ void load_smem(u64 (&x)[16], const u64 *sm, int tau) {
-#pragma unroll
-    for (int g = 0; g < (16 >> C); ++g)
-#pragma unroll
-        for (int a = 0; a < (1 << C); ++a) x[g * (1 << C) + a] = sm[smem_phys(elem_index<LOGN, LB, C>(tau, g, a))];
-}
-template <int LOGN, int LB, int C>
-__device__ __forceinline__ void store_smem(const u64 (&x)[16], u64 *sm, int tau) {
-#pragma unroll
-    for (int g = 0; g < (16 >> C); ++g)
-#pragma unroll
-        for (int a = 0; a < (1 << C); ++a) sm[smem_phys(elem_index<LOGN, LB, C>(tau, g, a))] = x[g * (1 << C) + a];
-}
-// global side: when LB == 0 a thread's 2^C elements of one sub-block are contiguous -> 16-byte vectors
-template <int LOGN, int LB, int C>
-__device__ __forceinline__ void load_global(u64 (&x)[16], const u64 *__restrict__ src, int tau) {
-    if (LB == 0 && C >= 1) {
-#pragma unroll
-        for (int g = 0; g < (16 >> C); ++g)
-#pragma unroll
-            for (int a = 0; a < (1 << C); a += 2) {
-                const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(src + elem_index<LOGN, LB, C>(tau, g, a));
-                x[g * (1 << C) + a] = v.x;
-                x[g * (1 << C) + a + 1] = v.y;
-            }
-    } else {
-#pragma unroll
-        for (int g = 0; g < (16 >> C); ++g)
-#pragma unroll
-            for (int a = 0; a < (1 << C); ++a) x[g * (1 << C) + a] = src[elem_index<LOGN, LB, C>(tau, g, a)];
-    }
-}
-template <int LOGN, int LB, int C>
-__device__ __forceinline__ void store_global(const u64 (&x)[16], u64 *__restrict__ dst, int tau) {
-    if (LB == 0 && C >= 1) {
-#pragma unroll
-        for (int g = 0; g < (16 >> C); ++g)
-#pragma unroll
-            for (int a = 0; a < (1 << C); a += 2)
-                *reinterpret_cast<ulonglong2 *>(dst + elem_index<LOGN, LB, C>(tau, g, a)) =
-                    make_ulonglong2(x[g * (1 << C) + a], x[g * (1 << C) + a + 1]);
-    } else {
-#pragma unroll
-        for (int g = 0; g < (16 >> C); ++g)
-#pragma unroll
-            for (int a = 0; a < (1 << C); ++a) dst[elem_index<LOGN, LB, C>(tau, g, a)] = x[g * (1 << C) + a];
-    }
-}
 
 template <int LOGN, bool NARROW>
 __global__ void __launch_bounds__((1 << LOGN) / 16, (1024 / ((1 << LOGN) / 16))) ntt_fwd_fast_kernel(const u64 *__restrict__ in, u64 *__restrict__ out,
@@ -80,6 +31,7 @@ __global__ void __launch_bounds__((1 << LOGN) / 16, (1024 / ((1 << LOGN) / 16)))
     m.p = S.p;
     m.two_p = 2 * S.p;
     m.mu1 = S.mu1;
+    m.np = 0 - S.p;
     m.tw = S.tw;
     const u64 *src = in + (row << LOGN);
     u64 *dst = out + (row << LOGN);
@@ -117,7 +69,7 @@ __global__ void __launch_bounds__((1 << LOGN) / 16, (1024 / ((1 << LOGN) / 16)))
 template <int LOGN, bool NARROW>
 __global__ void __launch_bounds__((1 << LOGN) / 16, (1024 / ((1 << LOGN) / 16))) ntt_inv_fast_kernel(const u64 *__restrict__ in, u64 *__restrict__ out,
                                                                        const ModSlot *__restrict__ slots,
-                                                                       const __grid_constant__ RowList rl, int scale_t) {
+                                                                       const __grid_constant__ RowList rl, int scale_mode) {
     extern __shared__ u64 sm[];
     constexpr int P = plan_passes(LOGN);
     const int tau = threadIdx.x;
@@ -129,11 +81,12 @@ __global__ void __launch_bounds__((1 << LOGN) / 16, (1024 / ((1 << LOGN) / 16)))
     m.p = S.p;
     m.two_p = 2 * S.p;
     m.mu1 = S.mu1;
+    m.np = 0 - S.p;
     m.tw = S.itw;
-    m.c0 = scale_t ? S.tn_inv : S.n_inv;
-    m.c0p = scale_t ? S.tn_inv_p : S.n_inv_p;
-    m.c1 = scale_t ? S.tn_inv_w : S.n_inv_w;
-    m.c1p = scale_t ? S.tn_inv_w_p : S.n_inv_w_p;
+    m.c0 = S.inv_scale[scale_mode].c0;
+    m.c0p = S.inv_scale[scale_mode].c0p;
+    m.c1 = S.inv_scale[scale_mode].c1;
+    m.c1p = S.inv_scale[scale_mode].c1p;
     const u64 *src = in + (row << LOGN);
     u64 *dst = out + (row << LOGN);
     u64 x[16];
@@ -176,7 +129,7 @@ static void build_row_lists(const Context &ctx, const NttRowMap &map, RowList &n
     for (int r = 0; r < map.rows_per_poly; ++r) {
         const int slot = map.slot[r / map.group];
         RowList &l = ctx.slots[slot].dev.bits <= kNarrowBits ? narrow : wide;
-        l.row[l.count] = (unsigned char)r;
+        l.row[l.count] = (unsigned short)r;
         l.slot[l.count] = (unsigned char)slot;
         ++l.count;
     }
@@ -184,7 +137,7 @@ static void build_row_lists(const Context &ctx, const NttRowMap &map, RowList &n
 
 template <int LOGN, bool NARROW, bool INVERSE>
 static cudaError_t launch_class(const Context &ctx, const RowList &rl, const u64 *in, u64 *out, int64_t polys,
-                                bool scale_t, cudaStream_t stream) {
+                                int scale_mode, cudaStream_t stream) {
     if (rl.count == 0 || polys == 0) return cudaSuccess;
     constexpr int threads = (1 << LOGN) / 16;
     constexpr size_t smem = sizeof(u64) * smem_words(LOGN);
@@ -195,7 +148,7 @@ static cudaError_t launch_class(const Context &ctx, const RowList &rl, const u64
     if (INVERSE) {
         auto k = ntt_inv_fast_kernel<LOGN, NARROW>;
         if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-        k<<<(unsigned)blocks, threads, smem, stream>>>(in, out, ctx.d_slots, rl, scale_t ? 1 : 0);
+        k<<<(unsigned)blocks, threads, smem, stream>>>(in, out, ctx.d_slots, rl, scale_mode);
     } else {
         auto k = ntt_fwd_fast_kernel<LOGN, NARROW>;
         if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
@@ -206,38 +159,38 @@ static cudaError_t launch_class(const Context &ctx, const RowList &rl, const u64
 
 template <int LOGN, bool INVERSE>
 static cudaError_t launch_logn(const Context &ctx, const NttRowMap &map, const u64 *in, u64 *out, int64_t rows,
-                               bool scale_t, cudaStream_t stream) {
+                               int scale_mode, cudaStream_t stream) {
     if (rows % map.rows_per_poly) return cudaErrorInvalidValue;
     RowList narrow, wide;
     build_row_lists(ctx, map, narrow, wide);
     const int64_t polys = rows / map.rows_per_poly;
-    cudaError_t e = launch_class<LOGN, true, INVERSE>(ctx, narrow, in, out, polys, scale_t, stream);
+    cudaError_t e = launch_class<LOGN, true, INVERSE>(ctx, narrow, in, out, polys, scale_mode, stream);
     if (e != cudaSuccess) return e;
-    return launch_class<LOGN, false, INVERSE>(ctx, wide, in, out, polys, scale_t, stream);
+    return launch_class<LOGN, false, INVERSE>(ctx, wide, in, out, polys, scale_mode, stream);
 }
 
 bool ntt_fast_supported(const Context &ctx) { return ctx.logn >= kMinLogN && ctx.logn <= kMaxLogN; }
 
 template <bool INVERSE>
 static cudaError_t launch_fast(const Context &ctx, const NttRowMap &map, const u64 *in, u64 *out, int64_t rows,
-                               bool scale_t, cudaStream_t stream) {
+                               int scale_mode, cudaStream_t stream) {
     switch (ctx.logn) {
-        case 10: return launch_logn<10, INVERSE>(ctx, map, in, out, rows, scale_t, stream);
-        case 11: return launch_logn<11, INVERSE>(ctx, map, in, out, rows, scale_t, stream);
-        case 12: return launch_logn<12, INVERSE>(ctx, map, in, out, rows, scale_t, stream);
-        case 13: return launch_logn<13, INVERSE>(ctx, map, in, out, rows, scale_t, stream);
-        case 14: return launch_logn<14, INVERSE>(ctx, map, in, out, rows, scale_t, stream);
+        case 10: return launch_logn<10, INVERSE>(ctx, map, in, out, rows, scale_mode, stream);
+        case 11: return launch_logn<11, INVERSE>(ctx, map, in, out, rows, scale_mode, stream);
+        case 12: return launch_logn<12, INVERSE>(ctx, map, in, out, rows, scale_mode, stream);
+        case 13: return launch_logn<13, INVERSE>(ctx, map, in, out, rows, scale_mode, stream);
+        case 14: return launch_logn<14, INVERSE>(ctx, map, in, out, rows, scale_mode, stream);
         default: return cudaErrorInvalidValue;
     }
 }
 
 cudaError_t launch_ntt_forward_fast(const Context &ctx, const NttRowMap &map, const u64 *in, u64 *out, int64_t rows,
                                     cudaStream_t stream) {
-    return launch_fast<false>(ctx, map, in, out, rows, false, stream);
+    return launch_fast<false>(ctx, map, in, out, rows, 0, stream);
 }
 cudaError_t launch_ntt_inverse_fast(const Context &ctx, const NttRowMap &map, const u64 *in, u64 *out, int64_t rows,
-                                    bool scale_t, cudaStream_t stream) {
-    return launch_fast<true>(ctx, map, in, out, rows, scale_t, stream);
+                                    int scale_mode, cudaStream_t stream) {
+    return launch_fast<true>(ctx, map, in, out, rows, scale_mode, stream);
 }
 
 }  // namespace hecuda

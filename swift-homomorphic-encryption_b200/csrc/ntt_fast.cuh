@@ -94,23 +94,86 @@ HE_HD int elem_index(int tau, int g, int a) {
     return (hi << (LB + C)) | (a << LB) | lo;
 }
 
+// ---- register <-> memory moves.  Within a sub-block the bit fields of e are disjoint, so both the element index
+// and its padded shared-memory position are (per-thread base) + (compile-time offset of a):
+//     e = base_e + (a << LB),   phys(e) = phys(base_e) + (a << LB) + ((a << LB) >> 4)
+template <int LB>
+HE_HD constexpr int smem_off(int a) { return (a << LB) + ((a << LB) >> 4); }
+
+template <int LOGN, int LB, int C>
+HE_HD void load_smem(u64 (&x)[16], const u64 *sm, int tau) {
+#pragma unroll
+    for (int g = 0; g < (16 >> C); ++g) {
+        const u64 *b = sm + smem_phys(elem_index<LOGN, LB, C>(tau, g, 0));
+#pragma unroll
+        for (int a = 0; a < (1 << C); ++a) x[g * (1 << C) + a] = b[smem_off<LB>(a)];
+    }
+}
+template <int LOGN, int LB, int C>
+HE_HD void store_smem(const u64 (&x)[16], u64 *sm, int tau) {
+#pragma unroll
+    for (int g = 0; g < (16 >> C); ++g) {
+        u64 *b = sm + smem_phys(elem_index<LOGN, LB, C>(tau, g, 0));
+#pragma unroll
+        for (int a = 0; a < (1 << C); ++a) b[smem_off<LB>(a)] = x[g * (1 << C) + a];
+    }
+}
+// global side: when LB == 0 a thread's 2^C elements of one sub-block are contiguous -> 16-byte vectors
+template <int LOGN, int LB, int C>
+HE_HD void load_global(u64 (&x)[16], const u64 *src, int tau) {
+#pragma unroll
+    for (int g = 0; g < (16 >> C); ++g) {
+        const u64 *b = src + elem_index<LOGN, LB, C>(tau, g, 0);
+        if (LB == 0) {
+#pragma unroll
+            for (int a = 0; a < (1 << C); a += 2) {
+                const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(b + a);
+                x[g * (1 << C) + a] = v.x;
+                x[g * (1 << C) + a + 1] = v.y;
+            }
+        } else {
+#pragma unroll
+            for (int a = 0; a < (1 << C); ++a) x[g * (1 << C) + a] = b[a << LB];
+        }
+    }
+}
+template <int LOGN, int LB, int C>
+HE_HD void store_global(const u64 (&x)[16], u64 *dst, int tau) {
+#pragma unroll
+    for (int g = 0; g < (16 >> C); ++g) {
+        u64 *b = dst + elem_index<LOGN, LB, C>(tau, g, 0);
+        if (LB == 0) {
+#pragma unroll
+            for (int a = 0; a < (1 << C); a += 2)
+                *reinterpret_cast<ulonglong2 *>(b + a) = make_ulonglong2(x[g * (1 << C) + a], x[g * (1 << C) + a + 1]);
+        } else {
+#pragma unroll
+            for (int a = 0; a < (1 << C); ++a) b[a << LB] = x[g * (1 << C) + a];
+        }
+    }
+}
+
 struct RowMod {
     u64 p, two_p, mu1;
+    u64 np;  // 2^64 - p: lets the Shoup product be all multiply-adds (x*w + q*np)
     const ulonglong2 *tw;
     u64 c0, c0p, c1, c1p;  // inverse: final-stage scalings
 };
 
 // ------------------------------------------------------------------------------------------------ forward
+// x*w mod p in [0, 2p) for any x (Shoup), written as multiply-adds only
+HE_HD u64 shoup_lazy_np(u64 x, u64 w, u64 wp, u64 np) { return x * w + mulhi64(x, wp) * np; }
+
 template <bool NARROW>
 HE_HD void ct_butterfly(u64 &x, u64 &y, const ulonglong2 w, const RowMod &m) {
     if (NARROW) {
-        const u64 v = shoup_lazy(y, w.x, w.y, m.p);
+        const u64 v = shoup_lazy_np(y, w.x, w.y, m.np);
         const u64 xo = x + v;
         y = x - v + m.two_p;
         x = xo;
     } else {
         const u64 xr = csub(x, m.two_p);
-        const u64 v = shoup_lazy(y, w.x, w.y, m.p);
+        const u64 v = shoup_lazy_np(y, w.x, w.y, m.np);
         x = xr + v;
         y = xr - v + m.two_p;
     }
@@ -153,11 +216,11 @@ template <bool NARROW>
 HE_HD void gs_butterfly(u64 &x, u64 &y, const ulonglong2 w, const RowMod &m, u64 kp) {
     if (NARROW) {  // inputs < kp (a multiple of p), outputs x < 2 kp, y < 2p
         const u64 s = x + y;
-        y = shoup_lazy(x - y + kp, w.x, w.y, m.p);
+        y = shoup_lazy_np(x - y + kp, w.x, w.y, m.np);
         x = s;
     } else {  // inputs < 2p, outputs < 2p
         const u64 s = csub(x + y, m.two_p);
-        y = shoup_lazy(x - y + m.two_p, w.x, w.y, m.p);
+        y = shoup_lazy_np(x - y + m.two_p, w.x, w.y, m.np);
         x = s;
     }
 }

@@ -14,7 +14,7 @@ namespace hecuda {
 
 template <bool INVERSE>
 __global__ void ntt_simple_kernel(const u64 *__restrict__ in, u64 *__restrict__ out, const ModSlot *__restrict__ slots,
-                                  NttRowMap map, int logn, int scale_t) {
+                                  NttRowMap map, int logn, int scale_mode) {
     extern __shared__ u64 sm[];
     const int64_t row = blockIdx.x;
     const int n = 1 << logn;
@@ -60,8 +60,8 @@ __global__ void ntt_simple_kernel(const u64 *__restrict__ in, u64 *__restrict__ 
             }
             __syncthreads();
         }
-        const u64 c0 = scale_t ? S.tn_inv : S.n_inv, c0p = scale_t ? S.tn_inv_p : S.n_inv_p;
-        const u64 c1 = scale_t ? S.tn_inv_w : S.n_inv_w, c1p = scale_t ? S.tn_inv_w_p : S.n_inv_w_p;
+        const u64 c0 = S.inv_scale[scale_mode].c0, c0p = S.inv_scale[scale_mode].c0p;
+        const u64 c1 = S.inv_scale[scale_mode].c1, c1p = S.inv_scale[scale_mode].c1p;
         for (int b = threadIdx.x; b < half; b += blockDim.x) {
             const u64 x = sm[b], y = sm[b + half];
             sm[b] = shoup_mul(x + y, c0, c0p, p);
@@ -74,7 +74,7 @@ __global__ void ntt_simple_kernel(const u64 *__restrict__ in, u64 *__restrict__ 
 
 template <bool INVERSE>
 static cudaError_t launch_simple(const Context &ctx, const NttRowMap &map, const u64 *in, u64 *out, int64_t rows,
-                                 bool scale_t, cudaStream_t stream) {
+                                 int scale_mode, cudaStream_t stream) {
     if (rows == 0) return cudaSuccess;
     const size_t smem = sizeof(u64) * (size_t)ctx.n;
     if (smem > 200 * 1024) return cudaErrorInvalidValue;
@@ -88,17 +88,17 @@ static cudaError_t launch_simple(const Context &ctx, const NttRowMap &map, const
     if (threads < 32) threads = 32;
     ++g_kernel_launches;
     ntt_simple_kernel<INVERSE><<<(unsigned)rows, threads, smem, stream>>>(in, out, ctx.d_slots, map, ctx.logn,
-                                                                       scale_t ? 1 : 0);
+                                                                       scale_mode);
     return cudaGetLastError();
 }
 
 cudaError_t launch_ntt_forward_simple(const Context &ctx, const NttRowMap &map, const u64 *in, u64 *out, int64_t rows,
                                       cudaStream_t stream) {
-    return launch_simple<false>(ctx, map, in, out, rows, false, stream);
+    return launch_simple<false>(ctx, map, in, out, rows, 0, stream);
 }
 cudaError_t launch_ntt_inverse_simple(const Context &ctx, const NttRowMap &map, const u64 *in, u64 *out, int64_t rows,
-                                      bool scale_t, cudaStream_t stream) {
-    return launch_simple<true>(ctx, map, in, out, rows, scale_t, stream);
+                                      int scale_mode, cudaStream_t stream) {
+    return launch_simple<true>(ctx, map, in, out, rows, scale_mode, stream);
 }
 
 }  // namespace hecuda

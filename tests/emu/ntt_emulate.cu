@@ -14,21 +14,18 @@
 using namespace hecuda;
 using namespace hecuda::fast;
 
+// the emulated "registers" of thread tau are x[tau*16 .. tau*16+15]; memory moves use the kernels' own helpers
 template <int LOGN, int LB, int C>
 static void emu_load(std::vector<u64> &x, const u64 *src, int tau, bool smem) {
-    for (int g = 0; g < (16 >> C); ++g)
-        for (int a = 0; a < (1 << C); ++a) {
-            const int e = elem_index<LOGN, LB, C>(tau, g, a);
-            x[tau * 16 + g * (1 << C) + a] = src[smem ? smem_phys(e) : e];
-        }
+    u64(&xr)[16] = *reinterpret_cast<u64(*)[16]>(&x[tau * 16]);
+    if (smem) load_smem<LOGN, LB, C>(xr, src, tau);
+    else load_global<LOGN, LB, C>(xr, src, tau);
 }
 template <int LOGN, int LB, int C>
-static void emu_store(const std::vector<u64> &x, u64 *dst, int tau, bool smem) {
-    for (int g = 0; g < (16 >> C); ++g)
-        for (int a = 0; a < (1 << C); ++a) {
-            const int e = elem_index<LOGN, LB, C>(tau, g, a);
-            dst[smem ? smem_phys(e) : e] = x[tau * 16 + g * (1 << C) + a];
-        }
+static void emu_store(std::vector<u64> &x, u64 *dst, int tau, bool smem) {
+    u64(&xr)[16] = *reinterpret_cast<u64(*)[16]>(&x[tau * 16]);
+    if (smem) store_smem<LOGN, LB, C>(xr, dst, tau);
+    else store_global<LOGN, LB, C>(xr, dst, tau);
 }
 
 template <int LOGN, bool NARROW, int K>
@@ -110,6 +107,7 @@ int main(int argc, char **argv) {
     m.p = p;
     m.two_p = 2 * p;
     m.mu1 = (u64)(((unsigned __int128)1 << 64) / p);
+    m.np = 0 - p;
     m.tw = inverse ? itw.data() : tw.data();
     u64 n_inv = host::invmod((u64)n % p, p);
     if (t) n_inv = host::mulmod(n_inv, t % p, p);
