@@ -193,7 +193,9 @@ int32_t host_pipeline(const hecuda_context *h, int64_t batch, int64_t chunk_hint
     WsGuard g0(h), g1(h);
     if (!g0.w || !g1.w) return fail(HECUDA_ERR_CUDA, "could not create a CUDA stream / workspace");
     Workspace *ws[2] = {g0.w, g1.w};
-    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(chunk_hint, batch));
+    // at least ~8 stages so that H2D of stage k+1, the kernels of stage k and D2H of stage k-1 overlap
+    int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(chunk_hint, batch));
+    if (batch >= 64) chunk = std::min<int64_t>(chunk, std::max<int64_t>(16, (batch + 7) / 8));
     int k = 0;
     for (int64_t done = 0; done < batch; done += chunk, ++k) {
         Workspace &w = *ws[k & 1];
