@@ -1,0 +1,188 @@
+// HeScheme.hpp -- C++ host-side mirror of the reference's scheme surface for the RNS-BFV hot path, over the C ABI in
+// include/hecuda.h.  The reference's host language (Swift) is not available in this build image; this header keeps
+// the reference's names, argument meaning and error behaviour so that callers and tests read like the reference's:
+//
+//   he::Context                 Context<Bfv<UInt64>>            Sources/HomomorphicEncryption/Context.swift:19,94-143
+//   he::PolyRq                  PolyRq<UInt64, F>               PolyRq/PolyRq.swift:21-52   (Array2d data, rows x N)
+//   he::Ciphertext              Ciphertext<Bfv<UInt64>, Coeff>  Ciphertext.swift:18-28
+//   he::EvaluationKey           EvaluationKey<Bfv<UInt64>>      Keys.swift:222
+//   he::Bfv::mulAssign          Bfv.mulAssign                   Bfv/Bfv+Multiply.swift:18-21
+//   he::Bfv::relinearize        Bfv.relinearize                 Bfv/Bfv.swift:201-219
+//   he::Bfv::modSwitchDown      Bfv.modSwitchDown               Bfv/Bfv.swift:163-171
+//   he::Bfv::forwardNtt/inverseNtt  PolyRq.forwardNtt/inverseNtt  PolyRq/PolyRq+Ntt.swift:230,541
+//   he::HeError                 HeError                         Error.swift:17-54
+//
+// Batched overloads take a span of ciphertexts so one call saturates the GPU ("Threading").
+#pragma once
+#include <cstdint>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/hecuda.h"
+
+namespace he {
+
+class HeError : public std::runtime_error {
+   public:
+    enum Kind { invalidCiphertext, incompatibleCiphertexts, invalidPolyContext, invalidContext, unsupportedHeOperation,
+                missingRelinearizationKey, invalidEncryptionParameters, deviceError };
+    HeError(Kind k, const std::string &m) : std::runtime_error(m), kind(k) {}
+    Kind kind;
+    static HeError fromStatus(int32_t rc) {
+        const std::string msg = hecuda_last_error() ? hecuda_last_error() : "";
+        switch (rc) {
+            case HECUDA_ERR_UNSUPPORTED: return HeError(unsupportedHeOperation, msg);
+            case HECUDA_ERR_MISSING_KEY: return HeError(missingRelinearizationKey, msg);
+            case HECUDA_ERR_INVALID_ARGUMENT: return HeError(invalidCiphertext, msg);
+            default: return HeError(deviceError, msg);
+        }
+    }
+};
+inline void check(int32_t rc) {
+    if (rc != HECUDA_OK) throw HeError::fromStatus(rc);
+}
+
+// Context<Bfv<UInt64>>: coefficientModuli = q_0..q_{L-1}, q_ks (Context.swift:102-107)
+class Context {
+   public:
+    Context(int64_t polyDegree, std::vector<uint64_t> coefficientModuli, uint64_t plaintextModulus)
+        : degree(polyDegree), coefficientModuli(std::move(coefficientModuli)), plaintextModulus(plaintextModulus) {
+        int32_t rc = hecuda_context_create(degree, this->coefficientModuli.data(), (int32_t)this->coefficientModuli.size(),
+                                           plaintextModulus, &handle_);
+        if (rc != HECUDA_OK) {
+            HeError e = HeError::fromStatus(rc);
+            throw HeError(rc == HECUDA_ERR_UNSUPPORTED ? HeError::unsupportedHeOperation : HeError::invalidEncryptionParameters,
+                          e.what());
+        }
+    }
+    ~Context() { hecuda_context_destroy(handle_); }
+    Context(const Context &) = delete;
+    Context &operator=(const Context &) = delete;
+    int ciphertextModuliCount() const { return (int)coefficientModuli.size() - 1; }
+    hecuda_context *handle() const { return handle_; }
+    bool operator==(const Context &o) const {  // Context.== (Context.swift:150-152)
+        return this == &o || (degree == o.degree && coefficientModuli == o.coefficientModuli && plaintextModulus == o.plaintextModulus);
+    }
+    const int64_t degree;
+    const std::vector<uint64_t> coefficientModuli;
+    const uint64_t plaintextModulus;
+
+   private:
+    hecuda_context *handle_ = nullptr;
+};
+
+// PolyRq: rows x N residues, row-major (Array2d.swift:115-123).  `moduliCount` rows of the ciphertext context.
+struct PolyRq {
+    std::shared_ptr<const Context> context;
+    int moduliCount = 0;
+    std::vector<uint64_t> data;
+    PolyRq() = default;
+    PolyRq(std::shared_ptr<const Context> c, int rows) : context(std::move(c)), moduliCount(rows), data((size_t)rows * context->degree) {}
+};
+
+// Ciphertext: polys back to back (Ciphertext.swift:18-28); Bfv's canonical format is Coeff.
+struct Ciphertext {
+    std::shared_ptr<const Context> context;
+    int polyCount = 0, moduliCount = 0;
+    uint64_t correctionFactor = 1;
+    std::vector<uint64_t> data;  // polyCount x moduliCount x N
+    Ciphertext() = default;
+    Ciphertext(std::shared_ptr<const Context> c, int polys, int rows)
+        : context(std::move(c)), polyCount(polys), moduliCount(rows), data((size_t)polys * rows * context->degree) {}
+    size_t polyWords() const { return (size_t)moduliCount * context->degree; }
+};
+
+class EvaluationKey {
+   public:
+    // relinearizationKey: the _KeySwitchKey's L ciphertexts x 2 polys x (L+1) x N in Eval format (Keys.swift:66-99)
+    EvaluationKey(std::shared_ptr<const Context> c, const std::vector<uint64_t> &relinearizationKey) : context(std::move(c)) {
+        const size_t L = context->ciphertextModuliCount();
+        if (relinearizationKey.size() != L * 2 * (L + 1) * (size_t)context->degree)
+            throw HeError(HeError::invalidContext, "relinearization key must be L x 2 x (L+1) x N");
+        check(hecuda_evk_create(context->handle(), relinearizationKey.data(), &handle_));
+    }
+    ~EvaluationKey() { hecuda_evk_destroy(handle_); }
+    EvaluationKey(const EvaluationKey &) = delete;
+    EvaluationKey &operator=(const EvaluationKey &) = delete;
+    std::shared_ptr<const Context> context;
+    hecuda_evk *handle() const { return handle_; }
+
+   private:
+    hecuda_evk *handle_ = nullptr;
+};
+
+// enum Bfv<UInt64>: HeScheme -- the hot-path statics
+struct Bfv {
+    static constexpr int freshCiphertextPolyCount = 2;  // HeScheme.freshCiphertextPolyCount
+
+    // validateEquality + the guards of multiplyWithoutScaling (Bfv+Multiply.swift:66-76)
+    static void validateMultiply(const Ciphertext &lhs, const Ciphertext &rhs) {
+        if (!lhs.context || !rhs.context || !(*lhs.context == *rhs.context))
+            throw HeError(HeError::invalidContext, "ciphertexts have different contexts");
+        if (lhs.polyCount != freshCiphertextPolyCount || lhs.correctionFactor != 1)
+            throw HeError(HeError::invalidCiphertext, "lhs must have 2 polys and correction factor 1");
+        if (rhs.polyCount != freshCiphertextPolyCount || rhs.correctionFactor != 1)
+            throw HeError(HeError::invalidCiphertext, "rhs must have 2 polys and correction factor 1");
+        if (lhs.moduliCount != rhs.moduliCount) throw HeError(HeError::incompatibleCiphertexts, "different poly contexts");
+        if (lhs.moduliCount != lhs.context->ciphertextModuliCount())
+            throw HeError(HeError::unsupportedHeOperation, "ct x ct multiply is supported at the top level only");
+    }
+
+    // lhs *= rhs  ->  lhs becomes a 3-poly ciphertext
+    static void mulAssign(Ciphertext &lhs, const Ciphertext &rhs) {
+        validateMultiply(lhs, rhs);
+        Ciphertext out(lhs.context, 3, lhs.moduliCount);
+        check(hecuda_bfv_multiply(lhs.context->handle(), lhs.data.data(), rhs.data.data(), out.data.data(), 1));
+        lhs = std::move(out);
+    }
+    // batched: lhs[i] *= rhs[i] for all i in one device pass
+    static void mulAssign(std::vector<Ciphertext> &lhs, const std::vector<Ciphertext> &rhs) {
+        if (lhs.size() != rhs.size()) throw HeError(HeError::incompatibleCiphertexts, "batch sizes differ");
+        if (lhs.empty()) return;
+        for (size_t i = 0; i < lhs.size(); ++i) validateMultiply(lhs[i], rhs[i]);
+        const auto ctx = lhs[0].context;
+        const size_t in_words = 2 * lhs[0].polyWords(), out_words = 3 * lhs[0].polyWords();
+        std::vector<uint64_t> a(in_words * lhs.size()), b(in_words * lhs.size()), o(out_words * lhs.size());
+        for (size_t i = 0; i < lhs.size(); ++i) {
+            std::copy(lhs[i].data.begin(), lhs[i].data.end(), a.begin() + i * in_words);
+            std::copy(rhs[i].data.begin(), rhs[i].data.end(), b.begin() + i * in_words);
+        }
+        check(hecuda_bfv_multiply(ctx->handle(), a.data(), b.data(), o.data(), (int64_t)lhs.size()));
+        for (size_t i = 0; i < lhs.size(); ++i) {
+            lhs[i].polyCount = 3;
+            lhs[i].data.assign(o.begin() + i * out_words, o.begin() + (i + 1) * out_words);
+        }
+    }
+
+    // Bfv.relinearize (Bfv.swift:201-219): 3 polys -> 2 polys
+    static void relinearize(Ciphertext &ct, const EvaluationKey &key) {
+        if (ct.correctionFactor != 1) throw HeError(HeError::invalidCiphertext, "correction factor must be 1");
+        if (ct.polyCount != 3) throw HeError(HeError::invalidCiphertext, "ciphertext must have three polys when relinearizing");
+        if (!(*ct.context == *key.context)) throw HeError(HeError::invalidContext, "key belongs to another context");
+        Ciphertext out(ct.context, 2, ct.moduliCount);
+        check(hecuda_bfv_relinearize(ct.context->handle(), key.handle(), ct.data.data(), ct.moduliCount, out.data.data(), 1));
+        ct = std::move(out);
+    }
+
+    // Bfv.modSwitchDown (Bfv.swift:163-171): drops the last modulus of every poly
+    static void modSwitchDown(Ciphertext &ct) {
+        if (ct.correctionFactor != 1) throw HeError(HeError::invalidCiphertext, "correction factor must be 1");
+        if (ct.moduliCount < 2) throw HeError(HeError::invalidPolyContext, "no next context");  // PolyRq.swift:366-368
+        Ciphertext out(ct.context, ct.polyCount, ct.moduliCount - 1);
+        check(hecuda_bfv_mod_switch_down(ct.context->handle(), ct.data.data(), ct.polyCount, ct.moduliCount, out.data.data(), 1));
+        ct = std::move(out);
+    }
+
+    // PolyRq.forwardNtt / inverseNtt (in place; the reference consumes `self` and returns the other format)
+    static void forwardNtt(PolyRq &poly) {
+        check(hecuda_ntt_forward(poly.context->handle(), HECUDA_BASE_Q, poly.data.data(), poly.moduliCount, 1));
+    }
+    static void inverseNtt(PolyRq &poly) {
+        check(hecuda_ntt_inverse(poly.context->handle(), HECUDA_BASE_Q, poly.data.data(), poly.moduliCount, 1));
+    }
+};
+
+}  // namespace he

@@ -1,0 +1,67 @@
+// host_mirror_test.cpp -- exercises the C++ mirror of the reference interface (host/HeScheme.hpp) end to end on a GPU:
+// reads a golden case (written by the Python test from tests/golden/mul_n64.npz), runs mulAssign / relinearize /
+// modSwitchDown and the error paths, and compares with the expected residues.
+//   usage: host_mirror_test <case.bin>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+
+#include "../../swift-homomorphic-encryption_b200/host/HeScheme.hpp"
+
+static std::vector<uint64_t> read_vec(std::ifstream &f) {
+    uint64_t n = 0;
+    f.read((char *)&n, 8);
+    std::vector<uint64_t> v(n);
+    f.read((char *)v.data(), 8 * n);
+    return v;
+}
+
+int main(int argc, char **argv) {
+    if (argc < 2) return 2;
+    std::ifstream f(argv[1], std::ios::binary);
+    if (!f) return 3;
+    auto hdr = read_vec(f);  // n, t, batch
+    auto moduli = read_vec(f), a = read_vec(f), b = read_vec(f), key = read_vec(f);
+    auto product = read_vec(f), relin = read_vec(f), switched = read_vec(f);
+    const int64_t n = (int64_t)hdr[0];
+    const int batch = (int)hdr[2];
+    auto ctx = std::make_shared<const he::Context>(n, moduli, hdr[1]);
+    const int L = ctx->ciphertextModuliCount();
+    const size_t pw = (size_t)L * n;
+    he::EvaluationKey evk(ctx, key);
+    int failures = 0;
+    std::vector<he::Ciphertext> lhs, rhs;
+    for (int i = 0; i < batch; ++i) {
+        he::Ciphertext x(ctx, 2, L), y(ctx, 2, L);
+        std::copy(a.begin() + i * 2 * pw, a.begin() + (i + 1) * 2 * pw, x.data.begin());
+        std::copy(b.begin() + i * 2 * pw, b.begin() + (i + 1) * 2 * pw, y.data.begin());
+        lhs.push_back(x);
+        rhs.push_back(y);
+    }
+    // single-ciphertext path
+    he::Ciphertext one = lhs[0];
+    he::Bfv::mulAssign(one, rhs[0]);
+    failures += std::memcmp(one.data.data(), product.data(), 3 * pw * 8) != 0;
+    // batched path
+    he::Bfv::mulAssign(lhs, rhs);
+    for (int i = 0; i < batch; ++i) failures += std::memcmp(lhs[i].data.data(), product.data() + i * 3 * pw, 3 * pw * 8) != 0;
+    for (int i = 0; i < batch; ++i) {
+        he::Bfv::relinearize(lhs[i], evk);
+        failures += lhs[i].polyCount != 2 || std::memcmp(lhs[i].data.data(), relin.data() + i * 2 * pw, 2 * pw * 8) != 0;
+        he::Bfv::modSwitchDown(lhs[i]);
+        failures += lhs[i].moduliCount != L - 1 ||
+                    std::memcmp(lhs[i].data.data(), switched.data() + i * 2 * (pw - n), 2 * (pw - n) * 8) != 0;
+    }
+    // error behaviour (Bfv+Multiply.swift:66-76, Bfv.swift:205-207)
+    try { he::Bfv::mulAssign(lhs[0], rhs[0]); ++failures; } catch (const he::HeError &e) { failures += e.kind != he::HeError::incompatibleCiphertexts; }
+    try { he::Ciphertext three(ctx, 3, L); he::Bfv::mulAssign(three, rhs[0]); ++failures; } catch (const he::HeError &e) { failures += e.kind != he::HeError::invalidCiphertext; }
+    try { he::Ciphertext two(ctx, 2, L); he::Bfv::relinearize(two, evk); ++failures; } catch (const he::HeError &e) { failures += e.kind != he::HeError::invalidCiphertext; }
+    // NTT round trip
+    he::PolyRq poly(ctx, L);
+    std::copy(a.begin(), a.begin() + pw, poly.data.begin());
+    he::Bfv::forwardNtt(poly);
+    he::Bfv::inverseNtt(poly);
+    failures += std::memcmp(poly.data.data(), a.data(), pw * 8) != 0;
+    std::printf("host mirror: %d failure(s)\n", failures);
+    return failures ? 1 : 0;
+}
