@@ -65,7 +65,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
@@ -95,13 +95,21 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(rows)}
 
 
+def host_threads():
+    """All host threads this process may use (torchrun pins OMP_NUM_THREADS=1, which is not what we want here)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_reference_throughput(n, moduli, t, budget_s=12.0, threads=0):
     """Times the oracle (C restatement of the Swift reference) on a bounded sample of the same workload."""
     from oracle import oracle as orc
 
     ctx = orc.Context(n, moduli, t)
     L = ctx.L
-    cores = threads or orc.num_threads()
+    cores = threads or host_threads()
     probe = max(1, min(cores, 8))
     a = orc.fill_uniform(1, ctx.q, n, probe * 2 * L).reshape(probe, 2, L, n)
     b = orc.fill_uniform(2, ctx.q, n, probe * 2 * L).reshape(probe, 2, L, n)
@@ -128,7 +136,7 @@ def run_reference(args):
 
     ctx = orc.Context(n, moduli, t)
     L = ctx.L
-    cores = orc.num_threads()
+    cores = host_threads()
     sample = max(cores, 2 * cores)  # bounded per-step sample of the batch
     a = orc.fill_uniform(3, ctx.q, n, sample * 2 * L).reshape(sample, 2, L, n)
     b = orc.fill_uniform(4, ctx.q, n, sample * 2 * L).reshape(sample, 2, L, n)
@@ -283,6 +291,51 @@ def main():
                     "frac": stage_model_bytes(n, L) * (value / world) / 1e9 / peak}}
     del ext, buf
 
+    # ---- extra (not the headline): relinearize and multiply+relinearize on the same batch.  The relinearization
+    # key is synthetic (uniform residues, valid Eval-format rows): rank 0 creates it and it reaches the other ranks
+    # by one NCCL broadcast into their key buffers (the only collective of the deployment).
+    extra = {}
+    try:
+        from hecuda import distributed as hd
+
+        K = L + 1
+        if rank == 0:
+            kq = torch.tensor(moduli, dtype=torch.int64, device=dev).view(1, 1, K, 1)
+            key_host = (torch.randint(0, 1 << 62, (L, 2, K, n), generator=gen, device=dev, dtype=torch.int64) % kq)
+            key_host = key_host.cpu().numpy().view(np.uint64)
+        else:
+            key_host = None
+        evk = hd.broadcast_evaluation_key(ctx, key_host, src=0)
+        relin_out = torch.empty((batch, 2, L, n), dtype=torch.int64, device=dev)
+
+        def relin_step():
+            rc = lib.hecuda_bfv_relinearize_device(ctx._h, evk._h, out.data_ptr(), L, relin_out.data_ptr(), batch,
+                                                   stream.cuda_stream)
+            if rc != 0:
+                raise RuntimeError(lib.hecuda_last_error().decode())
+
+        for name, fn in (("relinearize_per_s", relin_step), ("multiply_relinearize_per_s", lambda: (step(), relin_step()))):
+            for _ in range(2):
+                fn()
+            barrier()
+            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            r0.record(stream)
+            reps = max(3, min(args.steps, 10))
+            for _ in range(reps):
+                fn()
+            r1.record(stream)
+            barrier()
+            tt = torch.tensor([r0.elapsed_time(r1)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            extra[name] = world * batch * reps / (float(tt.item()) / 1e3)
+        extra["ntt_forward_per_s_per_gpu"] = ntt_rows / (ntt_ms / 1e3)
+        extra["key_broadcast"] = "nccl" if world > 1 else "local"
+        evk.close()
+        del relin_out
+    except Exception as exc:  # the headline number must survive a failure of the extras
+        extra["error"] = repr(exc)
+
     # ---- e2e: host buffers (pinned), H2D + D2H inside the timed region, through the host-pointer C-ABI call
     e2e = None
     if not args.no_e2e:
@@ -327,6 +380,7 @@ def main():
                        "l2": "inputs+outputs per step (1.4 GB) exceed L2 (126 MB); no explicit flush",
                        "pipeline_chunk": int(os.environ.get("HECUDA_CHUNK", "0")) or "auto"},
             "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "extra": extra,
         }
         print(json.dumps(line))
     if world > 1:
