@@ -10,61 +10,93 @@
 // (context.hpp) as one 128-bit multiply-accumulate pass per output residue followed by ONE Montgomery reduction
 // (the 2^64 factor lives in the constants); the stored residues are the same canonical values.  All kernels are
 // instruction-issue bound (64-bit integer multiplies), not HBM bound -- see DESIGN.md.
+#include <cstdlib>
+
 #include "kernels.cuh"
 
 namespace hecuda {
 
-constexpr int kColsPerThread = 2;
 constexpr int kThreads = 128;
 
-__device__ __forceinline__ ulonglong2 ld2(const u64 *p) { return *reinterpret_cast<const ulonglong2 *>(p); }
-__device__ __forceinline__ void st2(u64 *p, u64 a, u64 b) { *reinterpret_cast<ulonglong2 *>(p) = make_ulonglong2(a, b); }
+// columns per thread: 2 (16-byte accesses) by default; HECUDA_BEHZ_COLS=1 selects 1 (more warps, 8-byte accesses)
+static int cols_per_thread() {
+    static const int v = [] {
+        const char *e = std::getenv("HECUDA_BEHZ_COLS");
+        return (e && e[0] == '1') ? 1 : 2;
+    }();
+    return v;
+}
+
+template <int COLS>
+struct Cols {
+    u64 v[COLS];
+};
+template <int COLS>
+__device__ __forceinline__ Cols<COLS> ldc(const u64 *p) {
+    Cols<COLS> r;
+    if (COLS == 2) {
+        const ulonglong2 t = *reinterpret_cast<const ulonglong2 *>(p);
+        r.v[0] = t.x;
+        r.v[COLS - 1] = t.y;
+    } else {
+        r.v[0] = *p;
+    }
+    return r;
+}
+template <int COLS>
+__device__ __forceinline__ void stc(u64 *p, const u64 (&v)[COLS]) {
+    if (COLS == 2) *reinterpret_cast<ulonglong2 *>(p) = make_ulonglong2(v[0], v[COLS - 1]);
+    else *p = v[0];
+}
 
 // Bounds (checked for the actual moduli by Context::create): every 128-bit accumulator below stays < 2^127 and the
 // Montgomery-reduced sums are < 2p (lift, f_j, out_i: one or two conditional subtractions) or < 4p (alpha).
-template <int L>
+template <int L, int COLS>
 __global__ void __launch_bounds__(kThreads) lift_kernel(const u64 *__restrict__ in, int polys_in, u64 *__restrict__ ext,
                                                        int ext_polys, int out_poly_offset,
                                                        const __grid_constant__ LiftConsts c, int n) {
     constexpr int R = 2 * L + 1;
-    const int coeff = (blockIdx.x * kThreads + threadIdx.x) * kColsPerThread;
+    const int coeff = (blockIdx.x * kThreads + threadIdx.x) * COLS;
     if (coeff >= n) return;
     const int64_t poly = (int64_t)blockIdx.z * gridDim.y + blockIdx.y;  // index among items * polys_in
     const int64_t item = polys_in == 2 ? (poly >> 1) : poly / polys_in;  // (no 64-bit division on the hot path)
     const int pin = (int)(poly - item * polys_in);
     const u64 *src = in + poly * L * n + coeff;
     u64 *dst = ext + ((item * ext_polys + out_poly_offset + pin) * R) * n + coeff;
-    u64 z[kColsPerThread][L];
-    u32 acc_mt[kColsPerThread] = {0, 0};
+    u64 z[COLS][L];
+    u32 acc_mt[COLS];
+#pragma unroll
+    for (int k = 0; k < COLS; ++k) acc_mt[k] = 0;
 #pragma unroll
     for (int i = 0; i < L; ++i) {
-        const ulonglong2 x = ld2(src + (int64_t)i * n);
-        st2(dst + (int64_t)i * n, x.x, x.y);
-        // canonical: z is reinterpreted mod b_j and mod m~ below
-        z[0][i] = shoup_mul(x.x, c.in_w[i], c.in_wp[i], c.q[i]);
-        z[1][i] = shoup_mul(x.y, c.in_w[i], c.in_wp[i], c.q[i]);
-        acc_mt[0] += (u32)z[0][i] * c.punct_mt[i];
-        acc_mt[1] += (u32)z[1][i] * c.punct_mt[i];
-    }
-    u32 r[kColsPerThread];
-    bool neg[kColsPerThread];
+        const Cols<COLS> x = ldc<COLS>(src + (int64_t)i * n);
+        stc<COLS>(dst + (int64_t)i * n, x.v);
 #pragma unroll
-    for (int k = 0; k < kColsPerThread; ++k) {
+        for (int k = 0; k < COLS; ++k) {
+            // canonical: z is reinterpreted mod b_j and mod m~ below
+            z[k][i] = shoup_mul(x.v[k], c.in_w[i], c.in_wp[i], c.q[i]);
+            acc_mt[k] += (u32)z[k][i] * c.punct_mt[i];
+        }
+    }
+    u32 r[COLS];
+    bool neg[COLS];
+#pragma unroll
+    for (int k = 0; k < COLS; ++k) {
         r[k] = acc_mt[k] * c.neg_inv_q_mt;   // [-x' Q^-1]_{m~}, RnsTool.swift:343-348
         neg[k] = r[k] >= 0x80000000u;        // centered representative r - m~ (:357-360)
     }
 #pragma unroll
     for (int j = 0; j <= L; ++j) {
-        u64 o[kColsPerThread];
+        u64 o[COLS];
 #pragma unroll
-        for (int k = 0; k < kColsPerThread; ++k) {
+        for (int k = 0; k < COLS; ++k) {
             const u64 rc = neg[k] ? (u64)r[k] + c.b[j] - 0x100000000ull : (u64)r[k];
             u128 acc = (u128)rc * c.qr[j];
 #pragma unroll
             for (int i = 0; i < L; ++i) mac128(acc, z[k][i], c.mat[j][i]);
             o[k] = csub(mont_reduce(acc, c.b[j], c.b_ninv[j]), c.b[j]);
         }
-        st2(dst + (int64_t)(L + j) * n, o[0], o[1]);
+        stc<COLS>(dst + (int64_t)(L + j) * n, o);
     }
 }
 
@@ -75,61 +107,67 @@ struct TensorConsts {
     u64 p[kMaxRows], ninv[kMaxRows];
 };
 
+template <int COLS>
 __global__ void __launch_bounds__(kThreads) tensor_kernel(const u64 *__restrict__ ext, u64 *__restrict__ ten,
                                                          const __grid_constant__ TensorConsts c, int n) {
     const int R = c.R;
     const int row = blockIdx.y;
     const int64_t item = blockIdx.z;
-    const int coeff = (blockIdx.x * kThreads + threadIdx.x) * kColsPerThread;
+    const int coeff = (blockIdx.x * kThreads + threadIdx.x) * COLS;
     if (coeff >= n) return;
     const u64 p = c.p[row], ninv = c.ninv[row];
     const u64 *e = ext + (item * 4 * R + row) * n + coeff;
     const int64_t ps = (int64_t)R * n;
-    const ulonglong2 a0 = ld2(e), a1 = ld2(e + ps), b0 = ld2(e + 2 * ps), b1 = ld2(e + 3 * ps);
+    const Cols<COLS> a0 = ldc<COLS>(e), a1 = ldc<COLS>(e + ps), b0 = ldc<COLS>(e + 2 * ps), b1 = ldc<COLS>(e + 3 * ps);
     u64 *o = ten + (item * 3 * R + row) * n + coeff;
-    st2(o, csub(mont_reduce((u128)a0.x * b0.x, p, ninv), p), csub(mont_reduce((u128)a0.y * b0.y, p, ninv), p));
-    u128 m0 = (u128)a0.x * b1.x, m1 = (u128)a0.y * b1.y;
-    mac128(m0, a1.x, b0.x);
-    mac128(m1, a1.y, b0.y);
-    st2(o + ps, csub(mont_reduce(m0, p, ninv), p), csub(mont_reduce(m1, p, ninv), p));
-    st2(o + 2 * ps, csub(mont_reduce((u128)a1.x * b1.x, p, ninv), p), csub(mont_reduce((u128)a1.y * b1.y, p, ninv), p));
+    u64 o0[COLS], o1[COLS], o2[COLS];
+#pragma unroll
+    for (int k = 0; k < COLS; ++k) {
+        o0[k] = csub(mont_reduce((u128)a0.v[k] * b0.v[k], p, ninv), p);
+        u128 m = (u128)a0.v[k] * b1.v[k];
+        mac128(m, a1.v[k], b0.v[k]);
+        o1[k] = csub(mont_reduce(m, p, ninv), p);
+        o2[k] = csub(mont_reduce((u128)a1.v[k] * b1.v[k], p, ninv), p);
+    }
+    stc<COLS>(o, o0);
+    stc<COLS>(o + ps, o1);
+    stc<COLS>(o + 2 * ps, o2);
 }
 
-template <int L>
+template <int L, int COLS>
 __global__ void __launch_bounds__(kThreads) floor_kernel(const u64 *__restrict__ in, u64 *__restrict__ out,
                                                         const __grid_constant__ FloorConsts c, int n) {
     constexpr int R = 2 * L + 1;
-    const int coeff = (blockIdx.x * kThreads + threadIdx.x) * kColsPerThread;
+    const int coeff = (blockIdx.x * kThreads + threadIdx.x) * COLS;
     if (coeff >= n) return;
     const int64_t poly = (int64_t)blockIdx.z * gridDim.y + blockIdx.y;
     const u64 *src = in + poly * R * n + coeff;
     u64 *dst = out + poly * L * n + coeff;
-    u64 y[kColsPerThread][L];
+    u64 y[COLS][L];
 #pragma unroll
     for (int i = 0; i < L; ++i) {
-        const ulonglong2 x = ld2(src + (int64_t)i * n);
-        y[0][i] = shoup_mul(x.x, c.inq_w[i], c.inq_wp[i], c.q[i]);
-        y[1][i] = shoup_mul(x.y, c.inq_w[i], c.inq_wp[i], c.q[i]);
+        const Cols<COLS> x = ldc<COLS>(src + (int64_t)i * n);
+#pragma unroll
+        for (int k = 0; k < COLS; ++k) y[k][i] = shoup_mul(x.v[k], c.inq_w[i], c.inq_wp[i], c.q[i]);
     }
     // approximateFloor, RnsTool.swift:378-398: f_j = (x_bj - FBC(x_Q)_j) Q^-1 mod b_j   (kept lazy, < 2 b_j)
-    u64 f[kColsPerThread][L + 1];
+    u64 f[COLS][L + 1];
 #pragma unroll
     for (int j = 0; j <= L; ++j) {
-        const ulonglong2 xb = ld2(src + (int64_t)(L + j) * n);
-        u128 acc0 = (u128)xb.x * c.fq[j], acc1 = (u128)xb.y * c.fq[j];
+        const Cols<COLS> xb = ldc<COLS>(src + (int64_t)(L + j) * n);
 #pragma unroll
-        for (int i = 0; i < L; ++i) {
-            mac128(acc0, y[0][i], c.fmat[j][i]);
-            mac128(acc1, y[1][i], c.fmat[j][i]);
+        for (int k = 0; k < COLS; ++k) {
+            u128 acc = (u128)xb.v[k] * c.fq[j];
+#pragma unroll
+            for (int i = 0; i < L; ++i) mac128(acc, y[k][i], c.fmat[j][i]);
+            f[k][j] = mont_reduce(acc, c.b[j], c.b_ninv[j]);
         }
-        f[0][j] = mont_reduce(acc0, c.b[j], c.b_ninv[j]);
-        f[1][j] = mont_reduce(acc1, c.b[j], c.b_ninv[j]);
     }
     // convertApproximateBskToQ, RnsTool.swift:402-450
     const u64 msk = c.b[L];
-    u64 outv[kColsPerThread][L];
+    u64 outv[L][COLS];
 #pragma unroll
-    for (int k = 0; k < kColsPerThread; ++k) {
+    for (int k = 0; k < COLS; ++k) {
         u64 w[L];
         u128 acc = (u128)f[k][L] * c.a_msk;
 #pragma unroll
@@ -146,11 +184,11 @@ __global__ void __launch_bounds__(kThreads) floor_kernel(const u64 *__restrict__
             u128 o = (u128)alpha_c * (exceeds ? c.b_mod_q[i] : c.neg_b_mod_q[i]);
 #pragma unroll
             for (int kk = 0; kk < L; ++kk) mac128(o, w[kk], c.omat[i][kk]);
-            outv[k][i] = csub(csub(mont_reduce(o, c.q[i], c.q_ninv[i]), 2 * c.q[i]), c.q[i]);
+            outv[i][k] = csub(csub(mont_reduce(o, c.q[i], c.q_ninv[i]), 2 * c.q[i]), c.q[i]);
         }
     }
 #pragma unroll
-    for (int i = 0; i < L; ++i) st2(dst + (int64_t)i * n, outv[0][i], outv[1][i]);
+    for (int i = 0; i < L; ++i) stc<COLS>(dst + (int64_t)i * n, outv[i]);
 }
 
 #define HE_DISPATCH_L(L_, CALL)                                                                                       \
@@ -175,8 +213,8 @@ __global__ void __launch_bounds__(kThreads) floor_kernel(const u64 *__restrict__
     }
 
 // grid over (coefficient pairs, polys) with polys folded into y (<= 32768) and z
-static inline dim3 poly_grid(int64_t n, int64_t polys) {
-    const unsigned gx = (unsigned)((n / kColsPerThread + kThreads - 1) / kThreads);
+static inline dim3 poly_grid(int64_t n, int64_t polys, int cols) {
+    const unsigned gx = (unsigned)((n / cols + kThreads - 1) / kThreads);
     const int64_t gy = polys < 32768 ? polys : 32768;
     return dim3(gx ? gx : 1, (unsigned)gy, (unsigned)((polys + gy - 1) / gy));
 }
@@ -189,10 +227,16 @@ cudaError_t launch_lift(const Context &ctx, const u64 *in, int polys_in, u64 *ex
     // the z dimension must divide exactly: launch in slabs of y = 32768 polys, then the remainder
     while (polys > 0) {
         int64_t slab = polys >= 32768 ? (polys / 32768) * 32768 : polys;
-        const dim3 grid = poly_grid(ctx.n, slab);
+        const int cols = ctx.n >= 2 ? cols_per_thread() : 1;
+        const dim3 grid = poly_grid(ctx.n, slab, cols);
         ++g_kernel_launches;
-        HE_DISPATCH_L(ctx.L, (lift_kernel<LL><<<grid, kThreads, 0, stream>>>(in, polys_in, ext, ext_polys, out_poly_offset,
-                                                                          ctx.lift, (int)ctx.n)));
+        if (cols == 2) {
+            HE_DISPATCH_L(ctx.L, (lift_kernel<LL, 2><<<grid, kThreads, 0, stream>>>(in, polys_in, ext, ext_polys,
+                                                                                 out_poly_offset, ctx.lift, (int)ctx.n)));
+        } else {
+            HE_DISPATCH_L(ctx.L, (lift_kernel<LL, 1><<<grid, kThreads, 0, stream>>>(in, polys_in, ext, ext_polys,
+                                                                                 out_poly_offset, ctx.lift, (int)ctx.n)));
+        }
         // advance whole items only (32768 is even and polys_in is 1 or 2)
         in += slab * pstride_in;
         ext += (slab / polys_in) * (int64_t)ext_polys * (2 * ctx.L + 1) * ctx.n;
@@ -210,13 +254,18 @@ cudaError_t launch_tensor(const Context &ctx, const u64 *ext, u64 *ten, int64_t 
         tc.p[r] = ctx.slots[map.slot[r]].dev.p;
         tc.ninv[r] = ctx.slots[map.slot[r]].dev.ninv;
     }
-    const unsigned gx = (unsigned)((ctx.n / kColsPerThread + kThreads - 1) / kThreads);
+    const int cols = ctx.n >= 2 ? cols_per_thread() : 1;
+    const unsigned gx = (unsigned)((ctx.n / cols + kThreads - 1) / kThreads);
     for (int64_t done = 0; done < items;) {  // gridDim.z <= 65535
         const int64_t chunk = (items - done) > 65535 ? 65535 : (items - done);
         dim3 grid(gx ? gx : 1, (unsigned)tc.R, (unsigned)chunk);
         ++g_kernel_launches;
-        tensor_kernel<<<grid, kThreads, 0, stream>>>(ext + done * 4 * tc.R * ctx.n, ten + done * 3 * tc.R * ctx.n, tc,
-                                                     (int)ctx.n);
+        if (cols == 2)
+            tensor_kernel<2><<<grid, kThreads, 0, stream>>>(ext + done * 4 * tc.R * ctx.n, ten + done * 3 * tc.R * ctx.n, tc,
+                                                            (int)ctx.n);
+        else
+            tensor_kernel<1><<<grid, kThreads, 0, stream>>>(ext + done * 4 * tc.R * ctx.n, ten + done * 3 * tc.R * ctx.n, tc,
+                                                            (int)ctx.n);
         done += chunk;
     }
     return cudaGetLastError();
@@ -227,9 +276,14 @@ cudaError_t launch_floor(const Context &ctx, const u64 *in, u64 *out, int64_t po
     const int R = 2 * ctx.L + 1;
     while (polys > 0) {
         int64_t slab = polys >= 32768 ? (polys / 32768) * 32768 : polys;
-        const dim3 grid = poly_grid(ctx.n, slab);
+        const int cols = ctx.n >= 2 ? cols_per_thread() : 1;
+        const dim3 grid = poly_grid(ctx.n, slab, cols);
         ++g_kernel_launches;
-        HE_DISPATCH_L(ctx.L, (floor_kernel<LL><<<grid, kThreads, 0, stream>>>(in, out, ctx.floor, (int)ctx.n)));
+        if (cols == 2) {
+            HE_DISPATCH_L(ctx.L, (floor_kernel<LL, 2><<<grid, kThreads, 0, stream>>>(in, out, ctx.floor, (int)ctx.n)));
+        } else {
+            HE_DISPATCH_L(ctx.L, (floor_kernel<LL, 1><<<grid, kThreads, 0, stream>>>(in, out, ctx.floor, (int)ctx.n)));
+        }
         in += slab * (int64_t)R * ctx.n;
         out += slab * (int64_t)ctx.L * ctx.n;
         polys -= slab;

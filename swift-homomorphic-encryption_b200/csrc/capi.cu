@@ -174,8 +174,10 @@ cudaError_t relinearize_chunk(const Context &c, u64 *scratch, const u64 *key, co
     cudaError_t e;
     u64 *dig = scratch, *prod = scratch + dig_words * items;
     const int64_t ct_stride = (int64_t)3 * l * c.n;
-    if ((e = launch_ks_digits(c, ct3 + (int64_t)2 * l * c.n, ct_stride, l, dig, items, s)) != cudaSuccess) return e;
-    if ((e = launch_ntt_forward(c, c.map_ks_digits(l), dig, dig, items * (l + 1) * l, s)) != cudaSuccess) return e;
+    // digits: forward NTT that gathers [c2 row j]_{m_r} straight from the ciphertext     (Bfv+Keys.swift:165-179)
+    if ((e = launch_ntt_forward(c, c.map_ks_digits(l, ct_stride), ct3 + (int64_t)2 * l * c.n, dig, items * (l + 1) * l,
+                                s)) != cudaSuccess)
+        return e;
     if ((e = launch_ks_mac(c, dig, key, l, prod, items, s)) != cudaSuccess) return e;
     if ((e = launch_ntt_inverse(c, c.map_ks(l), prod, prod, items * 2 * (l + 1), kScaleMont, s)) != cudaSuccess) return e;
     return launch_ks_finish(c, prod, ct3, ct_stride, l, out, items, s);

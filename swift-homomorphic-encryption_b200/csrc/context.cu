@@ -242,6 +242,8 @@ NttRowMap Context::map_q(int rows) const {
     std::memset(&m, 0, sizeof(m));
     m.rows_per_poly = rows;
     m.group = 1;
+    m.src_mod = 0;
+    m.src_poly_stride = 0;
     for (int r = 0; r < rows; ++r) m.slot[r] = (unsigned char)slot_q(r);
     return m;
 }
@@ -250,6 +252,8 @@ NttRowMap Context::map_qbsk() const {
     std::memset(&m, 0, sizeof(m));
     m.rows_per_poly = 2 * L + 1;
     m.group = 1;
+    m.src_mod = 0;
+    m.src_poly_stride = 0;
     for (int r = 0; r < L; ++r) m.slot[r] = (unsigned char)slot_q(r);
     for (int j = 0; j <= L; ++j) m.slot[L + j] = (unsigned char)slot_bsk(j);
     return m;
@@ -259,6 +263,8 @@ NttRowMap Context::map_ks(int l) const {
     std::memset(&m, 0, sizeof(m));
     m.rows_per_poly = l + 1;
     m.group = 1;
+    m.src_mod = 0;
+    m.src_poly_stride = 0;
     for (int r = 0; r < l; ++r) m.slot[r] = (unsigned char)slot_q(r);
     m.slot[l] = (unsigned char)slot_ks();
     return m;
@@ -268,13 +274,18 @@ NttRowMap Context::map_single(int slot) const {
     std::memset(&m, 0, sizeof(m));
     m.rows_per_poly = 1;
     m.group = 1;
+    m.src_mod = 0;
+    m.src_poly_stride = 0;
     m.slot[0] = (unsigned char)slot;
     return m;
 }
-NttRowMap Context::map_ks_digits(int l) const {
+NttRowMap Context::map_ks_digits(int l, long long target_poly_stride) const {
     NttRowMap m = map_ks(l);
     m.rows_per_poly = (l + 1) * l;
     m.group = l;
+    m.src_mod = l;
+    m.src_poly_stride = target_poly_stride;
+    for (int j = 0; j < l; ++j) m.src_slot[j] = (unsigned char)slot_q(j);
     return m;
 }
 int Context::find_slot(u64 modulus) const {

@@ -45,6 +45,12 @@ struct NttRowMap {       // which modulus slot each row of a polynomial uses:
     int rows_per_poly;   //   slot[((row % rows_per_poly) / group)]
     int group;
     unsigned char slot[kMaxRows + 1];
+    // Optional gather on the input side (forward NTT only), used for key-switch digits (Bfv+Keys.swift:165-179):
+    // output row idx of polynomial k reads source row (idx % src_mod) at in + k * src_poly_stride, whose residues are
+    // mod the modulus in slot src_slot[idx % src_mod] and are re-reduced into the row's modulus where needed.
+    int src_mod;                  // 0 = no gather (input laid out like the output)
+    long long src_poly_stride;    // words
+    unsigned char src_slot[kMaxRows + 1];
 };
 
 // liftQToQBsk (RnsTool.swift:324-368) fused to: z_i = [x_i * in_w_i]_{q_i} (canonical);
@@ -121,7 +127,8 @@ class Context {
     NttRowMap map_qbsk() const;           // [Q, Bsk]
     NttRowMap map_ks(int l) const;        // [q_0..q_{l-1}, q_ks]
     NttRowMap map_single(int slot) const;
-    NttRowMap map_ks_digits(int l) const; // (l+1) x l digit rows, row (r, j) under m_r
+    // (l+1) x l digit rows, row (r, j) = [target row j]_{m_r}; gathered from target polynomials `stride` words apart
+    NttRowMap map_ks_digits(int l, long long target_poly_stride) const;
     int find_slot(u64 modulus) const;
 };
 

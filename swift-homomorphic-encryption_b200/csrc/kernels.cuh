@@ -41,9 +41,6 @@ cudaError_t launch_tensor(const Context &ctx, const u64 *ext, u64 *ten, int64_t 
 cudaError_t launch_floor(const Context &ctx, const u64 *in, u64 *out, int64_t polys, cudaStream_t stream);
 
 // ---- key switching and modulus switching (keyswitch.cu)
-// digits: target rows [item][l][N] inside ct3 (poly index 2 of 3) -> dig[item][l+1][l][N], dig[.][r][j] = [c_j]_{m_r}
-cudaError_t launch_ks_digits(const Context &ctx, const u64 *target, int64_t target_item_stride, int l, u64 *dig,
-                             int64_t items, cudaStream_t stream);
 // mac: dig (Eval) x key -> prod[item][2][l+1][N] (Eval)
 cudaError_t launch_ks_mac(const Context &ctx, const u64 *dig, const u64 *key, int l, u64 *prod, int64_t items,
                           cudaStream_t stream);

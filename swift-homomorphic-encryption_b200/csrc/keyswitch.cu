@@ -10,46 +10,44 @@
 
 namespace hecuda {
 
-// dig[item][r][j][.] = target[item][j][.] reduced into [0, m_r)   (Bfv+Keys.swift:165-172)
-__global__ void __launch_bounds__(256) ks_digits_kernel(const u64 *__restrict__ target, int64_t target_item_stride, int l,
-                                                       u64 *__restrict__ dig, const ModSlot *__restrict__ slots,
-                                                       NttRowMap ks_map, int64_t n) {
-    const int j = blockIdx.y;
-    const int64_t item = blockIdx.z;
-    const int64_t coeff = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (coeff >= n) return;
-    const u64 x = target[item * target_item_stride + (int64_t)j * n + coeff];
-    const u64 qj = slots[ks_map.slot[j]].p;
-    for (int r = 0; r <= l; ++r) {
-        const ModSlot &S = slots[ks_map.slot[r]];
-        const u64 v = qj > S.p ? barrett64(x, S.p, S.mu1) : x;
-        dig[((item * (l + 1) + r) * l + j) * n + coeff] = v;
-    }
-}
+// The digits dig[item][r][j] = NTT_{m_r}([target row j]_{m_r}) are produced by the forward NTT itself, which gathers
+// the target rows on load (NttRowMap::src_mod; Bfv+Keys.swift:165-179) -- there is no separate digit kernel.
 
-// prod[item][comp][r][.] = [ sum_j dig[item][r][j][.] * key[j][comp][keyrow(r)][.] ]_{m_r}   (Bfv+Keys.swift:180-202)
-__global__ void __launch_bounds__(256) ks_mac_kernel(const u64 *__restrict__ dig, const u64 *__restrict__ key, int l, int K,
-                                                    u64 *__restrict__ prod, const ModSlot *__restrict__ slots,
-                                                    NttRowMap ks_map, int64_t n) {
+struct KsMacConsts {
+    int l, K;
+    u64 p[kMaxL + 1], ninv[kMaxL + 1];
+};
+
+// prod[item][comp][r][.] = [ sum_j dig[item][r][j][.] * key[j][comp][keyrow(r)][.] ]_{m_r} * 2^-64   (Bfv+Keys.swift:180-202)
+// 128-bit lazy accumulation like the reference (:187-190), one Montgomery reduction; the 2^-64 is undone by the
+// kScaleMont scaling of the inverse NTT that follows.  sum < l p^2 < 2^127, reduced value < (1 + l/4) p <= 5p.
+__global__ void __launch_bounds__(128) ks_mac_kernel(const u64 *__restrict__ dig, const u64 *__restrict__ key,
+                                                    u64 *__restrict__ prod, const __grid_constant__ KsMacConsts c, int n) {
+    const int l = c.l, K = c.K;
     const int r = blockIdx.y;
     const int64_t item = blockIdx.z;
-    const int64_t coeff = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int coeff = (blockIdx.x * 128 + threadIdx.x) * 2;
     if (coeff >= n) return;
-    const ModSlot &S = slots[ks_map.slot[r]];
     const int key_row = (r == l) ? K - 1 : r;  // Bfv+Keys.swift:153
-    // 128-bit lazy accumulation like the reference (:187-190), Montgomery-reduced: prod = sum * 2^-64, restored by the
-    // kScaleMont scaling of the inverse NTT that follows.  sum < l p^2 < 2^127, reduced value < 2^-64 sum + p < (1 + l/4) p <= 5p.
-    u128 acc0 = 0, acc1 = 0;
+    const u64 p = c.p[r], ninv = c.ninv[r];
+    u128 a00 = 0, a01 = 0, a10 = 0, a11 = 0;
+    const u64 *d = dig + ((item * (l + 1) + r) * l) * n + coeff;
+    const u64 *kj = key + (int64_t)key_row * n + coeff;
     for (int j = 0; j < l; ++j) {
-        const u64 d = dig[((item * (l + 1) + r) * l + j) * n + coeff];
-        const u64 *kj = key + ((int64_t)j * 2 * K + key_row) * n + coeff;
-        mac128(acc0, d, kj[0]);
-        mac128(acc1, d, kj[(int64_t)K * n]);
+        const ulonglong2 dv = *reinterpret_cast<const ulonglong2 *>(d + (int64_t)j * n);
+        const ulonglong2 k0 = __ldg(reinterpret_cast<const ulonglong2 *>(kj + (int64_t)j * 2 * K * n));
+        const ulonglong2 k1 = __ldg(reinterpret_cast<const ulonglong2 *>(kj + ((int64_t)j * 2 + 1) * K * n));
+        mac128(a00, dv.x, k0.x);
+        mac128(a01, dv.y, k0.y);
+        mac128(a10, dv.x, k1.x);
+        mac128(a11, dv.y, k1.y);
     }
     u64 *o = prod + ((item * 2) * (l + 1) + r) * n + coeff;
-    const u64 p = S.p;
-    o[0] = csub(csub(csub(mont_reduce(acc0, p, S.ninv), 4 * p), 2 * p), p);
-    o[(int64_t)(l + 1) * n] = csub(csub(csub(mont_reduce(acc1, p, S.ninv), 4 * p), 2 * p), p);
+    *reinterpret_cast<ulonglong2 *>(o) = make_ulonglong2(csub(csub(csub(mont_reduce(a00, p, ninv), 4 * p), 2 * p), p),
+                                                        csub(csub(csub(mont_reduce(a01, p, ninv), 4 * p), 2 * p), p));
+    *reinterpret_cast<ulonglong2 *>(o + (int64_t)(l + 1) * n) =
+        make_ulonglong2(csub(csub(csub(mont_reduce(a10, p, ninv), 4 * p), 2 * p), p),
+                        csub(csub(csub(mont_reduce(a11, p, ninv), 4 * p), 2 * p), p));
 }
 
 // divide-and-round by the last modulus of `in` (rows c.l), optionally adding `base`, write c.l - 1 rows
@@ -92,33 +90,25 @@ __global__ void __launch_bounds__(256) mod_switch_kernel(const u64 *__restrict__
 
 static inline int pick_threads(int64_t n) { return n >= 256 ? 256 : (n < 32 ? 32 : (int)n); }
 
-cudaError_t launch_ks_digits(const Context &ctx, const u64 *target, int64_t target_item_stride, int l, u64 *dig,
-                             int64_t items, cudaStream_t stream) {
-    if (items == 0) return cudaSuccess;
-    const NttRowMap map = ctx.map_ks(l);
-    const int threads = pick_threads(ctx.n);
-    for (int64_t done = 0; done < items;) {
-        const int64_t chunk = (items - done) > 65535 ? 65535 : (items - done);
-        dim3 grid((unsigned)((ctx.n + threads - 1) / threads), (unsigned)l, (unsigned)chunk);
-        ++g_kernel_launches;
-        ks_digits_kernel<<<grid, threads, 0, stream>>>(target + done * target_item_stride, target_item_stride, l,
-                                                       dig + done * (l + 1) * l * ctx.n, ctx.d_slots, map, ctx.n);
-        done += chunk;
-    }
-    return cudaGetLastError();
-}
-
 cudaError_t launch_ks_mac(const Context &ctx, const u64 *dig, const u64 *key, int l, u64 *prod, int64_t items,
                           cudaStream_t stream) {
     if (items == 0) return cudaSuccess;
+    if (ctx.n < 2) return cudaErrorInvalidValue;
     const NttRowMap map = ctx.map_ks(l);
-    const int threads = pick_threads(ctx.n);
+    KsMacConsts c;
+    c.l = l;
+    c.K = ctx.L + 1;
+    for (int r = 0; r <= l; ++r) {
+        c.p[r] = ctx.slots[map.slot[r]].dev.p;
+        c.ninv[r] = ctx.slots[map.slot[r]].dev.ninv;
+    }
+    const unsigned gx = (unsigned)((ctx.n / 2 + 127) / 128);
     for (int64_t done = 0; done < items;) {
         const int64_t chunk = (items - done) > 65535 ? 65535 : (items - done);
-        dim3 grid((unsigned)((ctx.n + threads - 1) / threads), (unsigned)(l + 1), (unsigned)chunk);
+        dim3 grid(gx ? gx : 1, (unsigned)(l + 1), (unsigned)chunk);
         ++g_kernel_launches;
-        ks_mac_kernel<<<grid, threads, 0, stream>>>(dig + done * (l + 1) * l * ctx.n, key, l, ctx.L + 1,
-                                                    prod + done * 2 * (l + 1) * ctx.n, ctx.d_slots, map, ctx.n);
+        ks_mac_kernel<<<grid, 128, 0, stream>>>(dig + done * (l + 1) * l * ctx.n, key, prod + done * 2 * (l + 1) * ctx.n, c,
+                                                (int)ctx.n);
         done += chunk;
     }
     return cudaGetLastError();

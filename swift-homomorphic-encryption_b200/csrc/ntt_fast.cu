@@ -14,6 +14,10 @@ struct RowList {          // rows (within a polynomial) that one launch handles
     int count;
     unsigned short row[kMaxRowList];
     unsigned char slot[kMaxRowList];
+    // input side (forward only): source row and whether it must be re-reduced into this row's modulus
+    unsigned char src_row[kMaxRowList];
+    unsigned char reduce[kMaxRowList];
+    long long src_poly_stride;  // words between consecutive input polynomials
 };
 
 template <int LOGN, bool NARROW>
@@ -33,12 +37,16 @@ __global__ void __launch_bounds__((1 << LOGN) / 16, (1024 / ((1 << LOGN) / 16)))
     m.mu1 = S.mu1;
     m.np = 0 - S.p;
     m.tw = S.tw;
-    const u64 *src = in + (row << LOGN);
+    const u64 *src = in + poly * rl.src_poly_stride + ((int64_t)rl.src_row[which] << LOGN);
     u64 *dst = out + (row << LOGN);
     u64 x[16];
     {
         constexpr int C = fwd_c(LOGN, 0), LB = fwd_lb(LOGN, 0);
         load_global<LOGN, LB, C>(x, src, tau);
+        if (rl.reduce[which]) {  // gathered key-switch digit whose source modulus is too large for the lazy range
+#pragma unroll
+            for (int r = 0; r < 16; ++r) x[r] = barrett64(x[r], m.p, m.mu1);
+        }
         fwd_pass<LOGN, LB, C, NARROW>(x, tau, m);
         store_smem<LOGN, LB, C>(x, sm, tau);
     }
@@ -126,11 +134,22 @@ __global__ void __launch_bounds__((1 << LOGN) / 16, (1024 / ((1 << LOGN) / 16)))
 static void build_row_lists(const Context &ctx, const NttRowMap &map, RowList &narrow, RowList &wide) {
     narrow.rows_per_poly = wide.rows_per_poly = map.rows_per_poly;
     narrow.count = wide.count = 0;
+    narrow.src_poly_stride = wide.src_poly_stride =
+        map.src_mod ? map.src_poly_stride : (long long)map.rows_per_poly * ctx.n;
     for (int r = 0; r < map.rows_per_poly; ++r) {
         const int slot = map.slot[r / map.group];
-        RowList &l = ctx.slots[slot].dev.bits <= kNarrowBits ? narrow : wide;
+        const bool is_narrow = ctx.slots[slot].dev.bits <= kNarrowBits;
+        RowList &l = is_narrow ? narrow : wide;
         l.row[l.count] = (unsigned short)r;
         l.slot[l.count] = (unsigned char)slot;
+        l.src_row[l.count] = (unsigned char)(map.src_mod ? r % map.src_mod : r);
+        l.reduce[l.count] = 0;
+        if (map.src_mod) {
+            // inputs are residues mod the source modulus: fine as they are while they stay inside the lazy input range
+            // of the butterflies (< 2p NARROW, < 4p WIDE); otherwise re-reduce on load (Bfv+Keys.swift:168-172)
+            const u64 p = ctx.slots[slot].dev.p, src_p = ctx.slots[map.src_slot[r % map.src_mod]].dev.p;
+            l.reduce[l.count] = (src_p > p && (src_p - 1) / p >= (is_narrow ? 2u : 4u)) ? 1 : 0;
+        }
         ++l.count;
     }
 }

@@ -22,7 +22,13 @@ __global__ void ntt_simple_kernel(const u64 *__restrict__ in, u64 *__restrict__ 
     const u64 p = S.p, two_p = 2 * p;
     const u64 *src = in + row * n;
     u64 *dst = out + row * n;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) sm[i] = src[i];
+    if (!INVERSE && map.src_mod) {  // key-switch digit: [target row j]_{m_r}  (Bfv+Keys.swift:165-172)
+        const int idx = (int)(row % map.rows_per_poly);
+        src = in + (row / map.rows_per_poly) * map.src_poly_stride + (int64_t)(idx % map.src_mod) * n;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) sm[i] = barrett64(src[i], p, S.mu1);
+    } else {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) sm[i] = src[i];
+    }
     __syncthreads();
     const int half = n >> 1;
     if (!INVERSE) {
