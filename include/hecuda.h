@@ -119,6 +119,22 @@ int32_t hecuda_bfv_mod_switch_down(const hecuda_context *ctx, const uint64_t *ct
 int32_t hecuda_bfv_mod_switch_down_device(const hecuda_context *ctx, const uint64_t *ct, int32_t poly_count,
                                           int32_t moduli_count, uint64_t *out, int64_t batch, void *stream);
 
+/* ---- Galois automorphisms ----
+ * GaloisKey upload: the _KeySwitchKey for `element` from EvaluationKey.galoisKey.keys (Keys.swift:150-163, generated by
+ * Bfv+Keys.swift:42-49), same L x 2 x K x N Eval layout as the relinearization key.  Use hecuda_evk_create_empty for
+ * an evaluation key that holds Galois keys only. */
+int32_t hecuda_evk_set_galois_key(hecuda_evk *evk, uint32_t element, const uint64_t *key);
+/* Bfv.applyGalois(ciphertext:element:using:) -- Bfv/Bfv.swift:174-198 (rotateColumns / swapRows call this with
+ * GaloisElement.rotatingColumns / swappingRows, HeScheme.swift:1463-1478).  ct, out: batch x 2 x l x N (Coeff). */
+int32_t hecuda_bfv_apply_galois(const hecuda_context *ctx, const hecuda_evk *evk, const uint64_t *ct,
+                                int32_t moduli_count, uint32_t element, uint64_t *out, int64_t batch);
+int32_t hecuda_bfv_apply_galois_device(const hecuda_context *ctx, const hecuda_evk *evk, const uint64_t *ct,
+                                       int32_t moduli_count, uint32_t element, uint64_t *out, int64_t batch, void *stream);
+/* PolyRq.applyGalois(element:) in Coeff (eval_format = 0) or Eval (1) format -- PolyRq/Galois.swift:115-141,151-166.
+ * in, out: poly_count x row_count x N under `base`; out of place. */
+int32_t hecuda_poly_apply_galois(const hecuda_context *ctx, int32_t base, int32_t eval_format, const uint64_t *in,
+                                 uint64_t *out, int32_t row_count, int64_t poly_count, uint32_t element);
+
 /* Bookkeeping for bench.py: number of kernel launches issued by this library in the calling process so far. */
 uint64_t hecuda_kernel_launch_count(void);
 

@@ -1148,3 +1148,72 @@ int orc_decrypt(const orc_context *ctx, const uint64_t *sk, const uint64_t *ct, 
     free(dot);
     return 0;
 }
+
+/* =====================================================================================
+ * Galois automorphisms -- PolyRq/Galois.swift, Bfv/Bfv.swift:174-198, Bfv+Keys.swift:42-49
+ * ===================================================================================== */
+
+/* PolyRq<Coeff>.applyGalois, Galois.swift:115-141 with GaloisCoeffIterator :18-60 */
+void orc_galois_coeff(int64_t n, const uint64_t *moduli, int32_t nmod, int64_t element, const uint64_t *in, uint64_t *out) {
+    const int logn = ilog2((u64)n);
+    for (int r = 0; r < nmod; r++) {
+        i64 raw = 0;
+        for (i64 i = 0; i < n; i++) {
+            const int negate = (raw >> logn) & 1;
+            const i64 oi = raw & (n - 1);
+            const u64 v = in[(i64)r * n + i];
+            out[(i64)r * n + oi] = negate ? neg_mod(v, moduli[r]) : v;
+            raw += element;
+        }
+    }
+}
+/* PolyRq<Eval>.applyGalois, Galois.swift:151-166 with GaloisEvalIterator :62-98 */
+void orc_galois_eval(int64_t n, int32_t nmod, int64_t element, const uint64_t *in, uint64_t *out) {
+    const int logn = ilog2((u64)n);
+    for (i64 i = 0; i < n; i++) {
+        const u64 reversed = orc_reverse_bits((uint32_t)(i + n), logn + 1);
+        u64 raw = ((u64)element * reversed) >> 1;
+        raw &= (u64)(n - 1);
+        const i64 src = logn ? (i64)orc_reverse_bits((uint32_t)raw, logn) : 0;
+        for (int r = 0; r < nmod; r++) out[(i64)r * n + i] = in[(i64)r * n + src];
+    }
+}
+/* GaloisElement.rotatingColumns / swappingRows, Galois.swift:181-211 */
+int64_t orc_galois_element_swapping_rows(int64_t degree) { return (degree << 1) - 1; }
+int64_t orc_galois_element_rotating_columns(int64_t step, int64_t degree) {
+    i64 pos = step < 0 ? -step : step;
+    if (pos >= (degree >> 1) || pos <= 0) return 0;
+    if (step > 0) pos = (degree >> 1) - pos;
+    return (int64_t)orc_pow_mod(3, (u64)pos, (u64)degree << 1);
+}
+/* generateEvaluationKey's Galois branch, Bfv+Keys.swift:42-49 */
+int orc_gen_galois_key(const orc_context *ctx, uint64_t seed, const uint64_t *sk, int64_t element, uint64_t *ksk) {
+    const int K = ctx->L + 1;
+    u64 *switched = (u64 *)malloc(sizeof(u64) * K * ctx->n);
+    orc_galois_eval(ctx->n, K, element, sk, switched);
+    int rc = orc_gen_keyswitch_key(ctx, seed, sk, switched, ksk);
+    free(switched);
+    return rc;
+}
+/* Bfv.applyGalois, Bfv.swift:174-198 */
+int orc_bfv_apply_galois(const orc_context *ctx, const uint64_t *ct, int32_t l, int64_t element, const uint64_t *gkey,
+                         uint64_t *out, int64_t batch, int32_t threads) {
+    const i64 n = ctx->n, psz = (i64)l * n;
+    if (threads <= 0) threads = orc_num_threads();
+    int rc = 0;
+#pragma omp parallel for num_threads(threads) schedule(dynamic, 1)
+    for (i64 k = 0; k < batch; k++) {
+        const u64 *c = ct + k * 2 * psz;
+        u64 *o = out + k * 2 * psz;
+        u64 *tmp = (u64 *)malloc(sizeof(u64) * psz);
+        u64 *upd = (u64 *)malloc(sizeof(u64) * 2 * psz);
+        orc_galois_coeff(n, ctx->q, l, element, c, o);
+        orc_galois_coeff(n, ctx->q, l, element, c + psz, tmp);
+        if (orc_keyswitch_update(ctx, tmp, l, gkey, upd) != 0) rc = -1;
+        orc_poly_add(n, ctx->q, l, o, upd);
+        memcpy(o + psz, upd + psz, sizeof(u64) * psz);
+        free(upd);
+        free(tmp);
+    }
+    return rc;
+}

@@ -108,6 +108,17 @@ int orc_encrypt(const orc_context *, uint64_t seed, const uint64_t *secret_key_e
 int orc_decrypt(const orc_context *, const uint64_t *secret_key_eval, const uint64_t *ct, int32_t npoly,
                 int32_t l, uint64_t *plain);
 
+/* ---- Galois automorphisms: PolyRq/Galois.swift:115-166, Bfv.swift:174-198 ---- */
+void orc_galois_coeff(int64_t n, const uint64_t *moduli, int32_t nmod, int64_t element, const uint64_t *in, uint64_t *out);
+void orc_galois_eval(int64_t n, int32_t nmod, int64_t element, const uint64_t *in, uint64_t *out);
+int64_t orc_galois_element_rotating_columns(int64_t step, int64_t degree); /* 0 on invalid step */
+int64_t orc_galois_element_swapping_rows(int64_t degree);
+/* Galois key for `element`: key-switch key from s(x^element) to s (Bfv+Keys.swift:42-49); layout like the relin key */
+int orc_gen_galois_key(const orc_context *, uint64_t seed, const uint64_t *secret_key_eval, int64_t element, uint64_t *ksk);
+/* applyGalois: ct batch x 2 x l x n (Coeff) -> out batch x 2 x l x n */
+int orc_bfv_apply_galois(const orc_context *, const uint64_t *ct, int32_t l, int64_t element, const uint64_t *galois_key,
+                         uint64_t *out, int64_t batch, int32_t threads);
+
 /* deterministic test inputs: uniform residues row r < moduli[r % nmod] (splitmix64, rejection-free mod) */
 void orc_fill_uniform(uint64_t seed, const uint64_t *moduli, int32_t nmod, int64_t n, uint64_t *data, int64_t rows);
 int orc_num_threads(void);

@@ -88,6 +88,16 @@ def lib():
         L.orc_bfv_mod_switch_down.argtypes = [C.c_void_p, u64p, C.c_int32, C.c_int32, u64p, C.c_int64, C.c_int32]
         L.orc_encrypt.argtypes = [C.c_void_p, C.c_uint64, u64p, u64p, u64p]
         L.orc_decrypt.argtypes = [C.c_void_p, u64p, u64p, C.c_int32, C.c_int32, u64p]
+        L.orc_galois_coeff.restype = None
+        L.orc_galois_coeff.argtypes = [C.c_int64, u64p, C.c_int32, C.c_int64, u64p, u64p]
+        L.orc_galois_eval.restype = None
+        L.orc_galois_eval.argtypes = [C.c_int64, C.c_int32, C.c_int64, u64p, u64p]
+        L.orc_galois_element_rotating_columns.restype = C.c_int64
+        L.orc_galois_element_rotating_columns.argtypes = [C.c_int64, C.c_int64]
+        L.orc_galois_element_swapping_rows.restype = C.c_int64
+        L.orc_galois_element_swapping_rows.argtypes = [C.c_int64]
+        L.orc_gen_galois_key.argtypes = [C.c_void_p, C.c_uint64, u64p, C.c_int64, u64p]
+        L.orc_bfv_apply_galois.argtypes = [C.c_void_p, u64p, C.c_int32, C.c_int64, u64p, u64p, C.c_int64, C.c_int32]
         L.orc_fill_uniform.restype = None
         L.orc_fill_uniform.argtypes = [C.c_uint64, u64p, C.c_int32, C.c_int64, u64p, C.c_int64]
         L.orc_num_threads.restype = C.c_int
@@ -176,6 +186,32 @@ def convert_approximate(n, q, tmod, data):
     out = np.zeros((len(tm), n), dtype=np.uint64)
     lib().orc_convert_approximate(n, _p(q), len(q), _p(tm), len(tm), _p(d), _p(out))
     return out
+
+
+def galois_coeff(n: int, moduli, element: int, data):
+    d = _arr(data).reshape(len(moduli), n)
+    out = np.zeros_like(d)
+    m = _arr(moduli)
+    lib().orc_galois_coeff(n, _p(m), len(m), element, _p(d), _p(out))
+    return out
+
+
+def galois_eval(n: int, nmod: int, element: int, data):
+    d = _arr(data).reshape(nmod, n)
+    out = np.zeros_like(d)
+    lib().orc_galois_eval(n, nmod, element, _p(d), _p(out))
+    return out
+
+
+def galois_element_rotating_columns(step: int, degree: int) -> int:
+    e = int(lib().orc_galois_element_rotating_columns(step, degree))
+    if e == 0:
+        raise ValueError("invalidRotationStep")
+    return e
+
+
+def galois_element_swapping_rows(degree: int) -> int:
+    return int(lib().orc_galois_element_swapping_rows(degree))
 
 
 def fill_uniform(seed: int, moduli, n: int, rows: int):
@@ -290,6 +326,22 @@ class Context:
         l = tgt.shape[0]
         out = np.zeros((2, l, self.n), dtype=np.uint64)
         rc = lib().orc_keyswitch_update(self.h, _p(tgt), l, _p(_arr(ksk)), _p(out))
+        assert rc == 0
+        return out
+
+    def galois_keygen(self, seed: int, sk, element: int):
+        K = self.L + 1
+        gk = np.zeros((self.L, 2, K, self.n), dtype=np.uint64)
+        rc = lib().orc_gen_galois_key(self.h, seed, _p(_arr(sk)), element, _p(gk))
+        assert rc == 0
+        return gk
+
+    def apply_galois(self, ct, element: int, galois_key, threads: int = 0):
+        c = _arr(ct)
+        l = c.shape[-2]
+        c = c.reshape(-1, 2, l, self.n)
+        out = np.zeros_like(c)
+        rc = lib().orc_bfv_apply_galois(self.h, _p(c), l, element, _p(_arr(galois_key)), _p(out), c.shape[0], threads)
         assert rc == 0
         return out
 

@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <new>
 #include <string>
@@ -100,6 +101,8 @@ struct hecuda_evk {
     u64 *d_relin = nullptr;  // L x 2 x K x N, Eval
     size_t words = 0;
     bool loaded = false;
+    std::map<uint32_t, u64 *> galois;  // GaloisKey.keys: element -> key-switch key (Keys.swift:150-163), same layout
+    std::mutex mu;
 };
 
 namespace {
@@ -168,19 +171,41 @@ cudaError_t multiply_chunk(const Context &c, u64 *scratch, const u64 *lhs, const
     return launch_floor(c, ten, out, items * 3, s);
 }
 
-cudaError_t relinearize_chunk(const Context &c, u64 *scratch, const u64 *key, const u64 *ct3, int l, u64 *out,
-                              int64_t items, cudaStream_t s) {
+// _computeKeySwitchingUpdate (Bfv+Keys.swift:123-208) of `target` (l rows per item, items `target_stride` words apart)
+// + the caller's accumulation: out[item][c] = update[c] (+ base[item][c] for the components in base_mask).
+cudaError_t keyswitch_chunk(const Context &c, u64 *scratch, const u64 *key, const u64 *target, int64_t target_stride,
+                            int l, const u64 *base, int64_t base_stride, int base_mask, u64 *out, int64_t items,
+                            cudaStream_t s) {
     const size_t dig_words = (size_t)(l + 1) * l * c.n;
     cudaError_t e;
     u64 *dig = scratch, *prod = scratch + dig_words * items;
-    const int64_t ct_stride = (int64_t)3 * l * c.n;
-    // digits: forward NTT that gathers [c2 row j]_{m_r} straight from the ciphertext     (Bfv+Keys.swift:165-179)
-    if ((e = launch_ntt_forward(c, c.map_ks_digits(l, ct_stride), ct3 + (int64_t)2 * l * c.n, dig, items * (l + 1) * l,
-                                s)) != cudaSuccess)
+    // digits: forward NTT that gathers [target row j]_{m_r} straight from the source      (Bfv+Keys.swift:165-179)
+    if ((e = launch_ntt_forward(c, c.map_ks_digits(l, target_stride), target, dig, items * (l + 1) * l, s)) != cudaSuccess)
         return e;
     if ((e = launch_ks_mac(c, dig, key, l, prod, items, s)) != cudaSuccess) return e;
     if ((e = launch_ntt_inverse(c, c.map_ks(l), prod, prod, items * 2 * (l + 1), kScaleMont, s)) != cudaSuccess) return e;
-    return launch_ks_finish(c, prod, ct3, ct_stride, l, out, items, s);
+    return launch_ks_finish(c, prod, base, base_stride, base_mask, l, out, items, s);
+}
+
+// Bfv.relinearize (Bfv.swift:201-219): key-switch poly 2, add the update to polys 0 and 1
+cudaError_t relinearize_chunk(const Context &c, u64 *scratch, const u64 *key, const u64 *ct3, int l, u64 *out,
+                              int64_t items, cudaStream_t s) {
+    const int64_t ct_stride = (int64_t)3 * l * c.n;
+    return keyswitch_chunk(c, scratch, key, ct3 + (int64_t)2 * l * c.n, ct_stride, l, ct3, ct_stride, 3, out, items, s);
+}
+
+// Bfv.applyGalois (Bfv.swift:174-198): c0' = galois(c0) + update[0], c1' = update[1], update = keyswitch(galois(c1))
+size_t galois_scratch_words(const Context &c, int l) { return relinearize_scratch_words(c, l) + (size_t)l * c.n; }
+cudaError_t apply_galois_chunk(const Context &c, u64 *scratch, const u64 *key, const u64 *ct, int l, unsigned element,
+                               u64 *out, int64_t items, cudaStream_t s) {
+    const int64_t poly = (int64_t)l * c.n, ct_stride = 2 * poly;
+    u64 *perm1 = scratch;                      // items x l x N
+    u64 *ks_scratch = scratch + poly * items;
+    const NttRowMap map = c.map_q(l);
+    cudaError_t e;
+    if ((e = launch_galois_coeff(c, map, element, ct, ct_stride, out, ct_stride, items, s)) != cudaSuccess) return e;
+    if ((e = launch_galois_coeff(c, map, element, ct + poly, ct_stride, perm1, poly, items, s)) != cudaSuccess) return e;
+    return keyswitch_chunk(c, ks_scratch, key, perm1, poly, l, out, ct_stride, 1, out, items, s);
 }
 
 // Generic double-buffered host pipeline: for each chunk, copy inputs in, run `body`, copy outputs out.
@@ -493,6 +518,7 @@ int32_t hecuda_evk_create(const hecuda_context *h, const uint64_t *relin_key, he
 int32_t hecuda_evk_destroy(hecuda_evk *k) {
     if (!k) return HECUDA_OK;
     if (k->d_relin) cudaFree(k->d_relin);
+    for (auto &kv : k->galois) cudaFree(kv.second);
     delete k;
     return HECUDA_OK;
 }
@@ -583,6 +609,112 @@ int32_t hecuda_bfv_mod_switch_down(const hecuda_context *h, const uint64_t *ct, 
     return host_pipeline(h, batch, chunk, 0, in, (u64 *)out, (size_t)polys * (l - 1) * c.n,
                          [&](Workspace &w, const std::vector<const u64 *> &d_in, u64 *d_out, int64_t items) {
                              return launch_mod_switch(c, d_in[0], l, d_out, items * polys, w.stream);
+                         });
+}
+
+
+// ---------------------------------------------------------------- Galois
+
+static bool valid_galois_element(int64_t element, int64_t n) {  // isValidGaloisElement, Galois.swift:100-105
+    return (element & 1) && element > 1 && element < 2 * n;
+}
+
+int32_t hecuda_evk_set_galois_key(hecuda_evk *k, uint32_t element, const uint64_t *key) {
+    if (!k || !key) return fail(HECUDA_ERR_INVALID_ARGUMENT, "null argument");
+    int32_t rc = check_ctx(k->owner);
+    if (rc) return rc;
+    if (!valid_galois_element(element, k->owner->ctx->n)) return fail(HECUDA_ERR_INVALID_ARGUMENT, "invalid Galois element");
+    u64 *d = nullptr;
+    CK(cudaMalloc(&d, k->words * sizeof(u64)));
+    cudaError_t e = cudaMemcpy(d, key, k->words * sizeof(u64), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        cudaFree(d);
+        return cuda_fail(e, "cudaMemcpy(galois key)");
+    }
+    std::lock_guard<std::mutex> g(k->mu);
+    auto it = k->galois.find(element);
+    if (it != k->galois.end()) {
+        cudaFree(it->second);
+        it->second = d;
+    } else {
+        k->galois[element] = d;
+    }
+    return HECUDA_OK;
+}
+
+static int32_t check_galois(const hecuda_context *h, const hecuda_evk *k, const uint64_t *ct, int32_t l, uint32_t element,
+                            uint64_t *out, int64_t batch, const u64 **key) {
+    int32_t rc = check_ctx(h);
+    if (rc) return rc;
+    if (!k) return fail(HECUDA_ERR_MISSING_KEY, "missingGaloisKey");
+    if (k->owner != h) return fail(HECUDA_ERR_INVALID_ARGUMENT, "invalidContext: evaluation key belongs to another context");
+    if (!valid_galois_element(element, h->ctx->n)) return fail(HECUDA_ERR_INVALID_ARGUMENT, "invalid Galois element");
+    if (l < 1 || l > h->ctx->L) return fail(HECUDA_ERR_INVALID_ARGUMENT, "invalidCiphertext: moduli_count out of range");
+    if (batch < 0 || (batch && (!ct || !out))) return fail(HECUDA_ERR_INVALID_ARGUMENT, "invalidCiphertext: null buffer");
+    hecuda_evk *km = const_cast<hecuda_evk *>(k);
+    std::lock_guard<std::mutex> g(km->mu);
+    auto it = km->galois.find(element);
+    if (it == km->galois.end()) return fail(HECUDA_ERR_MISSING_KEY, "missingGaloisElement: " + std::to_string(element));
+    *key = it->second;
+    return HECUDA_OK;
+}
+
+int32_t hecuda_bfv_apply_galois_device(const hecuda_context *h, const hecuda_evk *k, const uint64_t *ct, int32_t l,
+                                       uint32_t element, uint64_t *out, int64_t batch, void *stream) {
+    const u64 *key = nullptr;
+    int32_t rc = check_galois(h, k, ct, l, element, out, batch, &key);
+    if (rc) return rc;
+    if (batch == 0) return HECUDA_OK;
+    const Context &c = *h->ctx;
+    const size_t words = (size_t)2 * l * c.n;
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(h->chunk, batch));
+    cudaStream_t s = (cudaStream_t)stream;
+    u64 *scratch = nullptr;
+    CK(cudaMallocAsync(&scratch, galois_scratch_words(c, l) * (size_t)chunk * sizeof(u64), s));
+    for (int64_t done = 0; done < batch; done += chunk) {
+        const int64_t items = std::min<int64_t>(chunk, batch - done);
+        cudaError_t e = apply_galois_chunk(c, scratch, key, (const u64 *)ct + words * done, l, element,
+                                           (u64 *)out + words * done, items, s);
+        if (e != cudaSuccess) {
+            cudaFreeAsync(scratch, s);
+            return cuda_fail(e, "applyGalois");
+        }
+    }
+    CK(cudaFreeAsync(scratch, s));
+    return HECUDA_OK;
+}
+
+int32_t hecuda_bfv_apply_galois(const hecuda_context *h, const hecuda_evk *k, const uint64_t *ct, int32_t l,
+                                uint32_t element, uint64_t *out, int64_t batch) {
+    const u64 *key = nullptr;
+    int32_t rc = check_galois(h, k, ct, l, element, out, batch, &key);
+    if (rc) return rc;
+    const Context &c = *h->ctx;
+    std::vector<HostIo> in = {{(const u64 *)ct, (size_t)2 * l * c.n}};
+    return host_pipeline(h, batch, h->chunk, galois_scratch_words(c, l), in, (u64 *)out, (size_t)2 * l * c.n,
+                         [&](Workspace &w, const std::vector<const u64 *> &d_in, u64 *d_out, int64_t items) {
+                             return apply_galois_chunk(c, w.buf[0], key, d_in[0], l, element, d_out, items, w.stream);
+                         });
+}
+
+int32_t hecuda_poly_apply_galois(const hecuda_context *h, int32_t base, int32_t eval_format, const uint64_t *in,
+                                 uint64_t *out, int32_t rows, int64_t polys, uint32_t element) {
+    int32_t rc = check_ctx(h);
+    if (rc) return rc;
+    if (polys < 0 || (polys && (!in || !out))) return fail(HECUDA_ERR_INVALID_ARGUMENT, "invalid data / poly_count");
+    if (!valid_galois_element(element, h->ctx->n)) return fail(HECUDA_ERR_INVALID_ARGUMENT, "invalid Galois element");
+    NttRowMap map;
+    std::string err;
+    if (!make_map(*h->ctx, base, rows, map, err)) return fail(HECUDA_ERR_INVALID_ARGUMENT, err);
+    const Context &c = *h->ctx;
+    const size_t words = (size_t)rows * c.n;
+    std::vector<HostIo> hin = {{(const u64 *)in, words}};
+    const int64_t chunk = std::max<int64_t>(1, (int64_t)((size_t)4 * 1024 * 1024 / words));
+    return host_pipeline(h, polys, chunk, 0, hin, (u64 *)out, words,
+                         [&](Workspace &w, const std::vector<const u64 *> &d_in, u64 *d_out, int64_t items) {
+                             return eval_format ? launch_galois_eval(c, rows, element, d_in[0], d_out, items, w.stream)
+                                                : launch_galois_coeff(c, map, element, d_in[0], (int64_t)words, d_out,
+                                                                      (int64_t)words, items, w.stream);
                          });
 }
 

@@ -44,9 +44,16 @@ cudaError_t launch_floor(const Context &ctx, const u64 *in, u64 *out, int64_t po
 // mac: dig (Eval) x key -> prod[item][2][l+1][N] (Eval)
 cudaError_t launch_ks_mac(const Context &ctx, const u64 *dig, const u64 *key, int l, u64 *prod, int64_t items,
                           cudaStream_t stream);
-// finish: out[item][c][i] = base[item][c][i] + divround(prod[item][c])[i]   (base may be null -> no add)
-cudaError_t launch_ks_finish(const Context &ctx, const u64 *prod, const u64 *base, int64_t base_item_stride, int l,
-                             u64 *out, int64_t items, cudaStream_t stream);
+// finish: out[item][c][i] = divround(prod[item][c])[i] (+ base[item][c][i] for the components in base_mask)
+cudaError_t launch_ks_finish(const Context &ctx, const u64 *prod, const u64 *base, int64_t base_item_stride, int base_mask,
+                             int l, u64 *out, int64_t items, cudaStream_t stream);
+// ---- Galois automorphisms (galois.cu): PolyRq.applyGalois in Coeff / Eval format (Galois.swift:115-166)
+cudaError_t launch_galois_coeff(const Context &ctx, const NttRowMap &map, unsigned element, const u64 *in,
+                                int64_t in_poly_stride, u64 *out, int64_t out_poly_stride, int64_t polys,
+                                cudaStream_t stream);
+cudaError_t launch_galois_eval(const Context &ctx, int rows, unsigned element, const u64 *in, u64 *out, int64_t polys,
+                               cudaStream_t stream);
+
 // divideAndRoundQLast over polys x l x N -> polys x (l-1) x N
 cudaError_t launch_mod_switch(const Context &ctx, const u64 *in, int l, u64 *out, int64_t polys, cudaStream_t stream);
 

@@ -66,7 +66,7 @@ __device__ __forceinline__ void divround_column(const u64 *__restrict__ in, cons
 }
 
 __global__ void __launch_bounds__(256) ks_finish_kernel(const u64 *__restrict__ prod, const u64 *__restrict__ base,
-                                                       int64_t base_item_stride, u64 *__restrict__ out,
+                                                       int64_t base_item_stride, int base_mask, u64 *__restrict__ out,
                                                        const __grid_constant__ DivRoundConsts c, int64_t n) {
     const int comp = blockIdx.y;
     const int64_t item = blockIdx.z;
@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(256) ks_finish_kernel(const u64 *__restrict__ 
     if (coeff >= n) return;
     const int l = c.l - 1;
     const u64 *in = prod + ((item * 2 + comp) * c.l) * n + coeff;
-    const u64 *b = base ? base + item * base_item_stride + (int64_t)comp * l * n + coeff : nullptr;
+    const u64 *b = (base && ((base_mask >> comp) & 1)) ? base + item * base_item_stride + (int64_t)comp * l * n + coeff : nullptr;
     u64 *o = out + ((item * 2 + comp) * l) * n + coeff;
     divround_column(in, b, o, c, n);
 }
@@ -114,8 +114,8 @@ cudaError_t launch_ks_mac(const Context &ctx, const u64 *dig, const u64 *key, in
     return cudaGetLastError();
 }
 
-cudaError_t launch_ks_finish(const Context &ctx, const u64 *prod, const u64 *base, int64_t base_item_stride, int l,
-                             u64 *out, int64_t items, cudaStream_t stream) {
+cudaError_t launch_ks_finish(const Context &ctx, const u64 *prod, const u64 *base, int64_t base_item_stride, int base_mask,
+                             int l, u64 *out, int64_t items, cudaStream_t stream) {
     if (items == 0) return cudaSuccess;
     const int threads = pick_threads(ctx.n);
     const DivRoundConsts &c = ctx.ks_divround[l];
@@ -124,7 +124,7 @@ cudaError_t launch_ks_finish(const Context &ctx, const u64 *prod, const u64 *bas
         dim3 grid((unsigned)((ctx.n + threads - 1) / threads), 2, (unsigned)chunk);
         ++g_kernel_launches;
         ks_finish_kernel<<<grid, threads, 0, stream>>>(prod + done * 2 * (l + 1) * ctx.n,
-                                                       base ? base + done * base_item_stride : nullptr, base_item_stride,
+                                                       base ? base + done * base_item_stride : nullptr, base_item_stride, base_mask,
                                                        out + done * 2 * l * ctx.n, c, ctx.n);
         done += chunk;
     }

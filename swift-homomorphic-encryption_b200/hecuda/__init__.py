@@ -57,6 +57,10 @@ SYMBOLS = {
     "hecuda_bfv_relinearize_device": (C.c_int32, [_VP, _VP, _VP, C.c_int32, _VP, C.c_int64, _VP]),
     "hecuda_bfv_mod_switch_down": (C.c_int32, [_VP, _VP, C.c_int32, C.c_int32, _VP, C.c_int64]),
     "hecuda_bfv_mod_switch_down_device": (C.c_int32, [_VP, _VP, C.c_int32, C.c_int32, _VP, C.c_int64, _VP]),
+    "hecuda_evk_set_galois_key": (C.c_int32, [_VP, C.c_uint32, _VP]),
+    "hecuda_bfv_apply_galois": (C.c_int32, [_VP, _VP, _VP, C.c_int32, C.c_uint32, _VP, C.c_int64]),
+    "hecuda_bfv_apply_galois_device": (C.c_int32, [_VP, _VP, _VP, C.c_int32, C.c_uint32, _VP, C.c_int64, _VP]),
+    "hecuda_poly_apply_galois": (C.c_int32, [_VP, C.c_int32, C.c_int32, _VP, _VP, C.c_int32, C.c_int64, C.c_uint32]),
     "hecuda_kernel_launch_count": (C.c_uint64, []),
 }
 
@@ -198,6 +202,13 @@ class EvaluationKey:
             _check(load_library().hecuda_evk_create(context._h, _ptr(key), C.byref(h)))
         self._h = h
 
+    def setGaloisKey(self, element: int, key):
+        """GaloisKey.keys[element] (Keys.swift:150-163): (L, 2, L+1, N) uint64, Eval format."""
+        k = _host(key)
+        if k.size != self.context.L * 2 * (self.context.L + 1) * self.context.degree:
+            raise HeError(-1, "invalidContext: Galois key must be L x 2 x (L+1) x N")
+        _check(load_library().hecuda_evk_set_galois_key(self._h, element, _ptr(k)))
+
     def deviceBuffer(self):
         p, n = C.c_void_p(), C.c_uint64(0)
         _check(load_library().hecuda_evk_device_buffer(self._h, C.byref(p), C.byref(n)))
@@ -257,6 +268,31 @@ class Bfv:
         if out is None:
             out = np.empty(c.shape[:-3] + (polys, l - 1, context.degree), dtype=np.uint64)
         _check(load_library().hecuda_bfv_mod_switch_down(context._h, _ptr(c), polys, l, _ptr(out), batch))
+        return out
+
+    @staticmethod
+    def applyGalois(context: Context, ciphertext, element: int, key: EvaluationKey, out=None):
+        """Bfv.applyGalois (Bfv.swift:174-198): (batch, 2, l, N) -> (batch, 2, l, N)."""
+        c = _host(ciphertext)
+        if c.ndim < 3 or c.shape[-3] != 2 or c.shape[-1] != context.degree:
+            raise HeError(-1, "invalidCiphertext: ciphertext must have two polys when applying galois")
+        if key is None:
+            raise HeError(-5, "missingGaloisKey")
+        l = c.shape[-2]
+        batch = int(np.prod(c.shape[:-3], dtype=np.int64))
+        if out is None:
+            out = np.empty_like(c)
+        _check(load_library().hecuda_bfv_apply_galois(context._h, key._h, _ptr(c), l, element, _ptr(out), batch))
+        return out
+
+    @staticmethod
+    def polyApplyGalois(context: Context, polys, element: int, evalFormat: bool = False, base: int = BASE_Q):
+        """PolyRq.applyGalois(element:) (Galois.swift:115-141 Coeff, :151-166 Eval) on (..., rows, N)."""
+        d = _host(polys)
+        rows = d.shape[-2]
+        out = np.empty_like(d)
+        _check(load_library().hecuda_poly_apply_galois(context._h, base, int(evalFormat), _ptr(d), _ptr(out), rows,
+                                                       d.size // (rows * context.degree), element))
         return out
 
     @staticmethod
