@@ -281,7 +281,10 @@ def main():
     traffic = None
     tr_path = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tr_path):
-        traffic = json.load(open(tr_path)).get("ntt_forward_dram_bytes_per_launch")
+        tr = json.load(open(tr_path))
+        if "ntt_forward_dram_bytes_per_row_narrow" in tr:  # per-row figures from the ncu --set full capture
+            traffic = (tr["ntt_forward_dram_bytes_per_row_narrow"] * ntt_polys * L +
+                       tr["ntt_forward_dram_bytes_per_row_wide"] * ntt_polys * (L + 1))
     roofline = {"bound": "hbm", "kernel": "ntt_forward (extended base [Q,Bsk])", "achieved": ntt_gbs, "peak": peak,
                 "unit": "GB/s", "frac": ntt_gbs / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": ntt_bytes, "rows_per_launch": ntt_rows, "ntt_per_s": ntt_rows / (ntt_ms / 1e3),
