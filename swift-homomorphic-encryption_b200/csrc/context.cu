@@ -36,6 +36,8 @@ static bool build_slot(HostSlot &hs, u64 p, int64_t n, int logn, u64 t, std::vec
     d.bits = bit_length(p);
     d.s_prod = d.bits - 2;
     d.mu_prod = (u64)(((u128)1 << (d.bits + 62)) / p);
+    d.red_shift = d.bits > 7 ? d.bits - 7 : 0;
+    d.red_recip = (u32)((((u128)1) << (d.red_shift + 18)) / p);
     const u64 psi = min_primitive_root(2 * (u64)n, p);
     const u64 psi_inv = invmod(psi, p);
     hs.roots.assign(n, 1);

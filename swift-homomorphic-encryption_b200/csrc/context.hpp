@@ -27,6 +27,8 @@ struct ModSlot {
     u64 mu_prod;      // floor(2^(bits+62) / p)
     int s_prod;       // bits - 2
     int bits;
+    int red_shift;    // bits - 7                      } small-quotient reduction of lazy NTT values (< 512 p),
+    u32 red_recip;    // floor(2^(red_shift+18) / p)   } ntt_fast.cuh::reduce_small
     u64 ninv;         // -p^-1 mod 2^64 (Montgomery)
     u64 r64;          // 2^64 mod p
     // Last inverse-NTT stage: x' = (x + y) c0, y' = (x - y) c1 with c0 = s N^-1, c1 = s N^-1 psi^-(N/2)

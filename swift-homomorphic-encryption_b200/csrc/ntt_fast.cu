@@ -36,6 +36,9 @@ __global__ void __launch_bounds__((1 << LOGN) / 16, (1024 / ((1 << LOGN) / 16)))
     m.two_p = 2 * S.p;
     m.mu1 = S.mu1;
     m.np = 0 - S.p;
+    m.four_p = 4 * S.p;
+    m.red_shift = S.red_shift;
+    m.red_recip = S.red_recip;
     m.tw = S.tw;
     const u64 *src = in + poly * rl.src_poly_stride + ((int64_t)rl.src_row[which] << LOGN);
     u64 *dst = out + (row << LOGN);
@@ -90,6 +93,9 @@ __global__ void __launch_bounds__((1 << LOGN) / 16, (1024 / ((1 << LOGN) / 16)))
     m.two_p = 2 * S.p;
     m.mu1 = S.mu1;
     m.np = 0 - S.p;
+    m.four_p = 4 * S.p;
+    m.red_shift = S.red_shift;
+    m.red_recip = S.red_recip;
     m.tw = S.itw;
     m.c0 = S.inv_scale[scale_mode].c0;
     m.c0p = S.inv_scale[scale_mode].c0p;

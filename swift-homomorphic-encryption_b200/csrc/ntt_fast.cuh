@@ -16,9 +16,12 @@
 // The pass lists below make every shared-memory access conflict-free with the padding phys(e) = e + (e >> 4)
 // and make the global side of the first/last pass fully coalesced (checked by tests/test_ntt_plan.py).
 //
-// Lazy ranges.  NARROW (p < 2^56): forward never reduces until the end (values < (1 + 2 LOGN) p < 2^64), inverse
-// lets values double per stage and Barrett-reduces once when the next pass could overflow.  WIDE (p < 2^62):
-// Harvey's [0,4p) forward / [0,2p) inverse with one conditional subtraction per butterfly.
+// Lazy ranges.  NARROW (p < 2^55): forward never reduces until the end (values < (2 + 2 LOGN) p; the bound analysis
+// below allows up to 4p per twiddle product so a cheaper under-estimated Shoup quotient, shoup_lazy4, could be dropped
+// in -- measured: no gain, the compiler's sequence for it issues as many instructions), inverse lets values double
+// per stage and reduces once at the entry of the pass that could overflow; reductions use a small-quotient estimate
+// (one 32-bit multiply) instead of a 64-bit Barrett because the FMA-heavy pipe (IMAD.WIDE) is the measured bottleneck.  WIDE (p < 2^62): Harvey's [0,4p) forward / [0,2p) inverse
+// with exact quotients and one conditional subtraction per butterfly.
 #pragma once
 #include "context.hpp"
 #include "modarith.cuh"
@@ -27,7 +30,7 @@ namespace hecuda {
 namespace fast {
 
 constexpr int kMinLogN = 10, kMaxLogN = 14;
-constexpr int kNarrowBits = 56;  // moduli below 2^56 take the reduction-free butterflies
+constexpr int kNarrowBits = 55;  // moduli below 2^55 take the reduction-free butterflies (lazy values < 512 p < 2^64)
 
 HE_HD constexpr int plan_passes(int logn) { return logn == 10 ? 3 : 4; }
 // stage counts of the forward passes, in execution order; the inverse runs the mirrored list
@@ -50,27 +53,38 @@ HE_HD constexpr int inv_lb(int logn, int k) {
     for (int i = 0; i < k; ++i) u0 += inv_c(logn, i);
     return u0;
 }
-// NARROW inverse: bound (in units of p) on the values entering pass k, and whether pass k reduces on entry.
-// Invariant: a stage with inputs < b p needs 2 b p < 2^64, i.e. b <= 128 for p < 2^56.
+// NARROW inverse bounds, in units of p.  A stage with inputs < b p outputs x' < 2 b p and y' < 4p, so the bound
+// evolves as b -> max(2b, 4), and needs 2 b p < 2^64, i.e. b <= 256 for p < 2^55.
+HE_HD constexpr int inv_stage_bound(int b) { return 2 * b > 4 ? 2 * b : 4; }
+HE_HD constexpr int inv_bound_after(int b, int stages) {
+    for (int i = 0; i < stages; ++i) b = inv_stage_bound(b);
+    return b;
+}
+HE_HD constexpr bool inv_pass_fits(int b, int stages) {  // every stage of the pass sees inputs <= 256 p
+    for (int i = 0; i < stages; ++i) {
+        if (b > 256) return false;
+        b = inv_stage_bound(b);
+    }
+    return true;
+}
+// whether pass k reduces its inputs on entry, and the bound on its inputs after that
 HE_HD constexpr bool inv_reduce_at(int logn, int k) {
     int b = 1;
     bool red = false;
     for (int i = 0; i <= k; ++i) {
         const int c = inv_c(logn, i);
-        red = (b << (c - 1)) > 128;
+        red = !inv_pass_fits(b, c);
         if (red) b = 1;
-        b <<= c;
+        b = inv_bound_after(b, c);
     }
     return red;
 }
-
-// bound (units of p) on the inputs of inverse pass k after its entry reduction (if any)
 HE_HD constexpr int inv_bound_in(int logn, int k) {
     int b = 1;
     for (int i = 0; i <= k; ++i) {
         const int c = inv_c(logn, i);
-        if ((b << (c - 1)) > 128) b = 1;
-        if (i < k) b <<= c;
+        if (!inv_pass_fits(b, c)) b = 1;
+        if (i < k) b = inv_bound_after(b, c);
     }
     return b;
 }
@@ -156,6 +170,9 @@ HE_HD void store_global(const u64 (&x)[16], u64 *dst, int tau) {
 struct RowMod {
     u64 p, two_p, mu1;
     u64 np;  // 2^64 - p: lets the Shoup product be all multiply-adds (x*w + q*np)
+    u64 four_p;
+    int red_shift;   // bits(p) - 7
+    u32 red_recip;   // floor(2^(red_shift + 18) / p) < 2^12
     const ulonglong2 *tw;
     u64 c0, c0p, c1, c1p;  // inverse: final-stage scalings
 };
@@ -163,6 +180,24 @@ struct RowMod {
 // ------------------------------------------------------------------------------------------------ forward
 // x*w mod p in [0, 2p) for any x (Shoup), written as multiply-adds only
 HE_HD u64 shoup_lazy_np(u64 x, u64 w, u64 wp, u64 np) { return x * w + mulhi64(x, wp) * np; }
+
+// floor(a b / 2^64) - {0,1,2}: three of the four partial products (drops lo*lo and the low halves of the cross terms)
+HE_HD u64 mulhi64_lo3(u64 a, u64 b) {
+    const u32 al = (u32)a, ah = (u32)(a >> 32), bl = (u32)b, bh = (u32)(b >> 32);
+    const u64 t1 = (u64)ah * bl, t2 = (u64)al * bh;
+    return (u64)ah * bh + (t1 >> 32) + (t2 >> 32);
+}
+// x*w mod p in [0, 4p) for any x: Shoup with the under-estimated quotient above
+HE_HD u64 shoup_lazy4(u64 x, u64 w, u64 wp, u64 np) { return x * w + mulhi64_lo3(x, wp) * np; }
+
+// x mod p for x < 512 p, p < 2^55: quotient estimated with one 32-bit multiply (never above, at most 2 below)
+HE_HD u64 reduce_small(u64 x, const u64 p, const int shift, const u32 recip) {
+    const u32 xs = (u32)(x >> shift);            // < 2^16
+    const u32 qhat = (xs * recip) >> 18;         // < 2^10
+    u64 r = x - (u64)qhat * p;                   // [0, 3p)
+    r = csub(r, 2 * p);
+    return csub(r, p);
+}
 
 template <bool NARROW>
 HE_HD void ct_butterfly(u64 &x, u64 &y, const ulonglong2 w, const RowMod &m) {
@@ -206,7 +241,7 @@ template <int LOGN, bool NARROW>
 HE_HD void fwd_finish(u64 (&x)[16], const RowMod &m) {
 #pragma unroll
     for (int r = 0; r < 16; ++r) {
-        if (NARROW) x[r] = barrett64(x[r], m.p, m.mu1);       // < (1 + 2 LOGN) p
+        if (NARROW) x[r] = reduce_small(x[r], m.p, m.red_shift, m.red_recip);  // < (2 + 4 LOGN) p
         else x[r] = csub(csub(x[r], m.two_p), m.p);           // < 4p
     }
 }
@@ -231,7 +266,7 @@ HE_HD void inv_stage(u64 (&x)[16], const int base, const int hi, const RowMod &m
     constexpr int HH = 1 << J;
     constexpr bool kLast = (LB + J == LOGN - 1);
     constexpr int kGroups = 1 << (LOGN - 1 - LB - J);
-    const u64 kp = m.p * (u64)(BIN << J);
+    const u64 kp = m.p * (u64)inv_bound_after(BIN, J);  // inputs of this stage are < kp
 #pragma unroll
     for (int grp = 0; grp < (1 << (C - 1 - J)); ++grp) {
         if (!kLast) {
@@ -273,7 +308,7 @@ HE_HD void inv_pass(u64 (&x)[16], int tau, const RowMod &m) {
 template <int BIN>
 HE_HD void inv_reduce(u64 (&x)[16], const RowMod &m) {
 #pragma unroll
-    for (int r = 0; r < 16; ++r) x[r] = barrett64(x[r], m.p, m.mu1);
+    for (int r = 0; r < 16; ++r) x[r] = reduce_small(x[r], m.p, m.red_shift, m.red_recip);  // < 512 p
 }
 
 }  // namespace fast

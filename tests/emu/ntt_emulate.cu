@@ -108,6 +108,9 @@ int main(int argc, char **argv) {
     m.two_p = 2 * p;
     m.mu1 = (u64)(((unsigned __int128)1 << 64) / p);
     m.np = 0 - p;
+    m.four_p = 4 * p;
+    m.red_shift = host::bit_length(p) > 7 ? host::bit_length(p) - 7 : 0;
+    m.red_recip = (u32)((((unsigned __int128)1) << (m.red_shift + 18)) / p);
     m.tw = inverse ? itw.data() : tw.data();
     u64 n_inv = host::invmod((u64)n % p, p);
     if (t) n_inv = host::mulmod(n_inv, t % p, p);
