@@ -135,6 +135,28 @@ int32_t hecuda_bfv_apply_galois_device(const hecuda_context *ctx, const hecuda_e
 int32_t hecuda_poly_apply_galois(const hecuda_context *ctx, int32_t base, int32_t eval_format, const uint64_t *in,
                                  uint64_t *out, int32_t row_count, int64_t poly_count, uint32_t element);
 
+/* ---- lazy ciphertext x plaintext inner product ----
+ * Bfv.innerProduct(ciphertexts:plaintexts:) -- Bfv/Bfv.swift:476-505 (lazyMultiply :388-400 over
+ * PolyRq.addingLazyProduct, PolyRq.swift:210-225; reduceInPlace/reduceToCiphertext :365-394), batched over
+ * `out_count` plaintext rows that share the same `term_count` ciphertexts (the MulPir first-dimension scan,
+ * PrivateInformationRetrieval/IndexPir/PirUtil.swift:437-442).  All operands in Eval format.
+ *   ciphertexts: term_count x poly_count x l x N       plaintexts: out_count x term_count x l x N
+ *   present:     out_count x term_count bytes, 0 = nil plaintext (skipped, Bfv.swift:493); NULL = all present
+ *   out:         out_count x poly_count x l x N        out[o] = sum_k ciphertexts[k] * plaintexts[o][k]  (mod q) */
+int32_t hecuda_bfv_inner_product_plaintexts(const hecuda_context *ctx, const uint64_t *ciphertexts, int32_t poly_count,
+                                            int32_t moduli_count, int64_t term_count, const uint64_t *plaintexts,
+                                            const uint8_t *present, uint64_t *out, int64_t out_count);
+int32_t hecuda_bfv_inner_product_plaintexts_device(const hecuda_context *ctx, const uint64_t *ciphertexts,
+                                                   int32_t poly_count, int32_t moduli_count, int64_t term_count,
+                                                   const uint64_t *plaintexts, const uint8_t *present, uint64_t *out,
+                                                   int64_t out_count, void *stream);
+/* Plaintext.convertToEvalFormat(moduliCount:) -- Plaintext.swift:149-171 (database preprocessing): `count` coefficient
+ * plaintexts of N values < t  ->  count x l x N residues in Eval format. */
+int32_t hecuda_plaintext_to_eval(const hecuda_context *ctx, const uint64_t *plain, int32_t moduli_count, uint64_t *out,
+                                 int64_t count);
+int32_t hecuda_plaintext_to_eval_device(const hecuda_context *ctx, const uint64_t *plain, int32_t moduli_count,
+                                        uint64_t *out, int64_t count, void *stream);
+
 /* Bookkeeping for bench.py: number of kernel launches issued by this library in the calling process so far. */
 uint64_t hecuda_kernel_launch_count(void);
 

@@ -1217,3 +1217,73 @@ int orc_bfv_apply_galois(const orc_context *ctx, const uint64_t *ct, int32_t l, 
     }
     return rc;
 }
+
+/* =====================================================================================
+ * Lazy ciphertext-plaintext inner product -- Bfv/Bfv.swift:402-505, Plaintext.swift:149-171
+ * ===================================================================================== */
+
+/* Plaintext.convertToEvalFormat(moduliCount:), Plaintext.swift:149-171: centered lift of the t-residues to each
+ * q_i (values >= (t+1)/2 get + (q_i - t), RnsTool.swift:168 tIncrement) followed by the forward NTT. */
+int orc_plaintext_to_eval(const orc_context *ctx, const uint64_t *plain, int32_t l, uint64_t *out) {
+    const i64 n = ctx->n;
+    if (l < 1 || l > ctx->L) return -1;
+    const u64 t = ctx->t, threshold = (t + 1) / 2;
+    for (int r = 0; r < l; r++) {
+        const u64 inc = ctx->q[r] - t;
+        u64 *row = out + (i64)r * n;
+        for (i64 c = 0; c < n; c++) row[c] = plain[c] < threshold ? plain[c] : plain[c] + inc;
+        ntt_forward_row(ctx->qt[r], row);
+    }
+    return 0;
+}
+
+/* Bfv.innerProduct(ciphertexts:plaintexts:), Bfv.swift:476-505 with lazyMultiply :388-400, reduceInPlace :365-377 and
+ * reduceToCiphertext :380-394, evaluated for `out_count` independent plaintext rows against the same `terms`
+ * ciphertexts (the MulPir first-dimension scan, IndexPir/PirUtil.swift:437-442).
+ *   cts: terms x npoly x l x n (Eval); pts: out_count x terms x l x n (Eval); present: out_count x terms flags
+ *   (0 = nil plaintext, skipped, :493) or NULL; out: out_count x npoly x l x n (Eval). */
+int orc_inner_product_plain(const orc_context *ctx, const uint64_t *cts, int32_t npoly, int32_t l, int64_t terms,
+                            const uint64_t *pts, const uint8_t *present, uint64_t *out, int64_t out_count,
+                            int32_t threads) {
+    const i64 n = ctx->n;
+    if (l < 1 || l > ctx->L || npoly < 1) return -1;
+    if (threads <= 0) threads = orc_num_threads();
+    /* maxLazyProductAccumulationCount, PolyContext.swift:246-253 */
+    u64 qmax = 0;
+    for (int r = 0; r < l; r++) qmax = ctx->q[r] > qmax ? ctx->q[r] : qmax;
+    const u128 max_product = (u128)(qmax - 1) * (qmax - 1);
+    const u128 max_count128 = ((~(u128)0) - qmax) / max_product;
+    const i64 max_count = max_count128 > (u128)INT64_MAX ? INT64_MAX : (i64)max_count128;
+#pragma omp parallel for num_threads(threads) schedule(dynamic, 1)
+    for (i64 o = 0; o < out_count; o++) {
+        u128 *acc = (u128 *)calloc((size_t)npoly * l * n, sizeof(u128));
+        i64 reduce_count = 0;
+        for (i64 k = 0; k < terms; k++) {
+            if (present && !present[o * terms + k]) continue;
+            const u64 *pt = pts + (o * terms + k) * l * n;
+            for (int p = 0; p < npoly; p++) {
+                const u64 *ct = cts + ((k * npoly + p) * l) * n;
+                u128 *a = acc + (i64)p * l * n;
+                for (i64 i = 0; i < (i64)l * n; i++) a[i] += (u128)ct[i] * pt[i]; /* addingLazyProduct, PolyRq.swift:210-225 */
+            }
+            if (++reduce_count >= max_count) {
+                reduce_count = 0;
+                for (int p = 0; p < npoly; p++)
+                    for (int r = 0; r < l; r++) {
+                        modulus_t m = modulus_make(ctx->q[r]);
+                        u128 *a = acc + ((i64)p * l + r) * n;
+                        for (i64 c = 0; c < n; c++) a[c] = reduce_double(&m, a[c]);
+                    }
+            }
+        }
+        for (int p = 0; p < npoly; p++)
+            for (int r = 0; r < l; r++) {
+                modulus_t m = modulus_make(ctx->q[r]);
+                const u128 *a = acc + ((i64)p * l + r) * n;
+                u64 *dst = out + ((o * npoly + p) * l + r) * n;
+                for (i64 c = 0; c < n; c++) dst[c] = reduce_double(&m, a[c]);
+            }
+        free(acc);
+    }
+    return 0;
+}

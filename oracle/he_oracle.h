@@ -119,6 +119,11 @@ int orc_gen_galois_key(const orc_context *, uint64_t seed, const uint64_t *secre
 int orc_bfv_apply_galois(const orc_context *, const uint64_t *ct, int32_t l, int64_t element, const uint64_t *galois_key,
                          uint64_t *out, int64_t batch, int32_t threads);
 
+/* ---- lazy ciphertext x plaintext inner product: Bfv.swift:402-505, Plaintext.swift:149-171 ---- */
+int orc_plaintext_to_eval(const orc_context *, const uint64_t *plain /* n values < t */, int32_t l, uint64_t *out /* l x n */);
+int orc_inner_product_plain(const orc_context *, const uint64_t *cts, int32_t npoly, int32_t l, int64_t terms,
+                            const uint64_t *pts, const uint8_t *present, uint64_t *out, int64_t out_count, int32_t threads);
+
 /* deterministic test inputs: uniform residues row r < moduli[r % nmod] (splitmix64, rejection-free mod) */
 void orc_fill_uniform(uint64_t seed, const uint64_t *moduli, int32_t nmod, int64_t n, uint64_t *data, int64_t rows);
 int orc_num_threads(void);

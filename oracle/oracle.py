@@ -98,6 +98,9 @@ def lib():
         L.orc_galois_element_swapping_rows.argtypes = [C.c_int64]
         L.orc_gen_galois_key.argtypes = [C.c_void_p, C.c_uint64, u64p, C.c_int64, u64p]
         L.orc_bfv_apply_galois.argtypes = [C.c_void_p, u64p, C.c_int32, C.c_int64, u64p, u64p, C.c_int64, C.c_int32]
+        L.orc_plaintext_to_eval.argtypes = [C.c_void_p, u64p, C.c_int32, u64p]
+        L.orc_inner_product_plain.argtypes = [C.c_void_p, u64p, C.c_int32, C.c_int32, C.c_int64, u64p,
+                                              C.POINTER(C.c_uint8), u64p, C.c_int64, C.c_int32]
         L.orc_fill_uniform.restype = None
         L.orc_fill_uniform.argtypes = [C.c_uint64, u64p, C.c_int32, C.c_int64, u64p, C.c_int64]
         L.orc_num_threads.restype = C.c_int
@@ -342,6 +345,26 @@ class Context:
         c = c.reshape(-1, 2, l, self.n)
         out = np.zeros_like(c)
         rc = lib().orc_bfv_apply_galois(self.h, _p(c), l, element, _p(_arr(galois_key)), _p(out), c.shape[0], threads)
+        assert rc == 0
+        return out
+
+    def plaintext_to_eval(self, plain, l: int = 0):
+        l = l or self.L
+        out = np.zeros((l, self.n), dtype=np.uint64)
+        rc = lib().orc_plaintext_to_eval(self.h, _p(_arr(plain)), l, _p(out))
+        assert rc == 0
+        return out
+
+    def inner_product_plain(self, cts, pts, present=None, threads: int = 0):
+        c = _arr(cts)  # (terms, npoly, l, n)
+        terms, npoly, l = c.shape[0], c.shape[1], c.shape[2]
+        p = _arr(pts).reshape(-1, terms, l, self.n)
+        out = np.zeros((p.shape[0], npoly, l, self.n), dtype=np.uint64)
+        pres = None
+        if present is not None:
+            pa = np.ascontiguousarray(np.asarray(present, dtype=np.uint8)).reshape(p.shape[0], terms)
+            pres = pa.ctypes.data_as(C.POINTER(C.c_uint8))
+        rc = lib().orc_inner_product_plain(self.h, _p(c), npoly, l, terms, _p(p), pres, _p(out), p.shape[0], threads)
         assert rc == 0
         return out
 

@@ -718,6 +718,96 @@ int32_t hecuda_poly_apply_galois(const hecuda_context *h, int32_t base, int32_t 
                          });
 }
 
+// ---------------------------------------------------------------- lazy ct x pt inner product
+
+static int32_t check_ip(const hecuda_context *h, const uint64_t *cts, int32_t polys, int32_t l, int64_t terms,
+                        const uint64_t *pts, uint64_t *out, int64_t out_count) {
+    int32_t rc = check_ctx(h);
+    if (rc) return rc;
+    if (polys < 1 || polys > 3) return fail(HECUDA_ERR_INVALID_ARGUMENT, "invalidCiphertext: poly_count must be 1..3");
+    if (l < 1 || l > h->ctx->L) return fail(HECUDA_ERR_INVALID_ARGUMENT, "invalidCiphertext: moduli_count out of range");
+    if (terms < 1) return fail(HECUDA_ERR_INVALID_ARGUMENT, "Empty ciphertexts");  // precondition, Bfv.swift:481-483
+    if (out_count < 0 || (out_count && (!cts || !pts || !out))) return fail(HECUDA_ERR_INVALID_ARGUMENT, "null buffer");
+    if (h->ctx->n < 2) return fail(HECUDA_ERR_UNSUPPORTED, "degree too small");
+    return HECUDA_OK;
+}
+
+int32_t hecuda_bfv_inner_product_plaintexts_device(const hecuda_context *h, const uint64_t *cts, int32_t polys,
+                                                   int32_t l, int64_t terms, const uint64_t *pts,
+                                                   const uint8_t *present, uint64_t *out, int64_t out_count,
+                                                   void *stream) {
+    int32_t rc = check_ip(h, cts, polys, l, terms, pts, out, out_count);
+    if (rc) return rc;
+    cudaError_t e = launch_inner_product_plain(*h->ctx, (const u64 *)cts, polys, l, terms, (const u64 *)pts, present,
+                                               (u64 *)out, out_count, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "inner_product");
+    return HECUDA_OK;
+}
+
+int32_t hecuda_bfv_inner_product_plaintexts(const hecuda_context *h, const uint64_t *cts, int32_t polys, int32_t l,
+                                            int64_t terms, const uint64_t *pts, const uint8_t *present, uint64_t *out,
+                                            int64_t out_count) {
+    int32_t rc = check_ip(h, cts, polys, l, terms, pts, out, out_count);
+    if (rc) return rc;
+    if (out_count == 0) return HECUDA_OK;
+    const Context &c = *h->ctx;
+    // the query ciphertexts (and the presence flags) are shared by every output row: upload once
+    const size_t ct_words = (size_t)terms * polys * l * c.n;
+    u64 *d_cts = nullptr;
+    unsigned char *d_present = nullptr;
+    CK(cudaMalloc(&d_cts, ct_words * sizeof(u64)));
+    cudaError_t e = cudaMemcpy(d_cts, cts, ct_words * sizeof(u64), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && present) {
+        e = cudaMalloc(&d_present, (size_t)out_count * terms);
+        if (e == cudaSuccess) e = cudaMemcpy(d_present, present, (size_t)out_count * terms, cudaMemcpyHostToDevice);
+    }
+    if (e != cudaSuccess) {
+        cudaFree(d_cts);
+        cudaFree(d_present);
+        return cuda_fail(e, "inner_product upload");
+    }
+    const size_t pt_words = (size_t)terms * l * c.n;
+    std::vector<HostIo> in = {{(const u64 *)pts, pt_words}};
+    const int64_t chunk = std::max<int64_t>(1, (int64_t)((size_t)32 * 1024 * 1024 / pt_words));
+    int64_t done_items = 0;  // host_pipeline calls the body in order, one chunk at a time
+    rc = host_pipeline(h, out_count, chunk, 0, in, (u64 *)out, (size_t)polys * l * c.n,
+                       [&](Workspace &w, const std::vector<const u64 *> &d_in, u64 *d_out, int64_t items) {
+                           const unsigned char *pr = d_present ? d_present + done_items * terms : nullptr;
+                           done_items += items;
+                           return launch_inner_product_plain(c, d_cts, polys, l, terms, d_in[0], pr, d_out, items, w.stream);
+                       });
+    cudaDeviceSynchronize();
+    cudaFree(d_cts);
+    cudaFree(d_present);
+    return rc;
+}
+
+int32_t hecuda_plaintext_to_eval_device(const hecuda_context *h, const uint64_t *plain, int32_t l, uint64_t *out,
+                                        int64_t count, void *stream) {
+    int32_t rc = check_ctx(h);
+    if (rc) return rc;
+    if (l < 1 || l > h->ctx->L) return fail(HECUDA_ERR_INVALID_ARGUMENT, "invalidPolyContext: moduli_count out of range");
+    if (count < 0 || (count && (!plain || !out))) return fail(HECUDA_ERR_INVALID_ARGUMENT, "null buffer");
+    cudaError_t e = launch_plaintext_to_eval(*h->ctx, (const u64 *)plain, l, (u64 *)out, count, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "plaintext_to_eval");
+    return HECUDA_OK;
+}
+
+int32_t hecuda_plaintext_to_eval(const hecuda_context *h, const uint64_t *plain, int32_t l, uint64_t *out,
+                                 int64_t count) {
+    int32_t rc = check_ctx(h);
+    if (rc) return rc;
+    if (l < 1 || l > h->ctx->L) return fail(HECUDA_ERR_INVALID_ARGUMENT, "invalidPolyContext: moduli_count out of range");
+    if (count < 0 || (count && (!plain || !out))) return fail(HECUDA_ERR_INVALID_ARGUMENT, "null buffer");
+    const Context &c = *h->ctx;
+    std::vector<HostIo> in = {{(const u64 *)plain, (size_t)c.n}};
+    const int64_t chunk = std::max<int64_t>(1, (int64_t)((size_t)4 * 1024 * 1024 / ((size_t)l * c.n)));
+    return host_pipeline(h, count, chunk, 0, in, (u64 *)out, (size_t)l * c.n,
+                         [&](Workspace &w, const std::vector<const u64 *> &d_in, u64 *d_out, int64_t items) {
+                             return launch_plaintext_to_eval(c, d_in[0], l, d_out, items, w.stream);
+                         });
+}
+
 uint64_t hecuda_kernel_launch_count(void) { return g_kernel_launches.load(); }
 
 }  // extern "C"

@@ -1,0 +1,142 @@
+// innerprod.cu -- lazy ciphertext x plaintext inner products and plaintext Eval conversion.
+//
+//   Bfv.innerProduct(ciphertexts:plaintexts:)   Bfv/Bfv.swift:476-505  (lazyMultiply :388-400, reduce :365-394)
+//   PolyRq.addingLazyProduct                    PolyRq/PolyRq.swift:210-225
+//   Plaintext.convertToEvalFormat               Plaintext.swift:149-171
+//
+// out[o][p][r][c] = sum_k cts[k][p][r][c] * pts[o][k][r][c] mod q_r over the present plaintexts -- the MulPir
+// first-dimension scan (IndexPir/PirUtil.swift:437-442): `out_count` database rows against the same `terms` query
+// ciphertexts.  The plaintexts are streamed from HBM exactly once (ld.global.cs); the ciphertexts are re-read through
+// L2.  128-bit lazy accumulation like the reference, one double-word Barrett at the end (and every max_terms terms).
+#include "kernels.cuh"
+
+namespace hecuda {
+
+struct IpConsts {
+    int l;
+    long long max_terms;  // maxLazyProductAccumulationCount (PolyContext.swift:246-253)
+    u64 p[kMaxL], mu_hi[kMaxL], mu_lo[kMaxL];
+};
+
+__device__ __forceinline__ u128w to_w(u128 v) {
+    u128w r;
+    r.lo = (u64)v;
+    r.hi = (u64)(v >> 64);
+    return r;
+}
+
+template <int NPOLY>
+__global__ void __launch_bounds__(128) inner_product_plain_kernel(const u64 *__restrict__ cts, const u64 *__restrict__ pts,
+                                                                 const unsigned char *__restrict__ present,
+                                                                 u64 *__restrict__ out,
+                                                                 const __grid_constant__ IpConsts c, int n,
+                                                                 long long terms) {
+    const int coeff = (blockIdx.x * 128 + threadIdx.x) * 2;
+    if (coeff >= n) return;
+    const int r = blockIdx.y, l = c.l;
+    const long long o = blockIdx.z;
+    const u64 p = c.p[r], mu_hi = c.mu_hi[r], mu_lo = c.mu_lo[r];
+    u128 acc[NPOLY][2];
+#pragma unroll
+    for (int q = 0; q < NPOLY; ++q) acc[q][0] = acc[q][1] = 0;
+    const u64 *pt = pts + ((o * terms) * l + r) * (long long)n + coeff;
+    const u64 *ct = cts + (long long)r * n + coeff;
+    const long long pt_stride = (long long)l * n, ct_stride = (long long)NPOLY * l * n;
+    const unsigned char *pres = present ? present + o * terms : nullptr;
+    long long since_reduce = 0;
+#pragma unroll 4
+    for (long long k = 0; k < terms; ++k) {
+        if (pres && !pres[k]) continue;  // nil plaintext (Bfv.swift:493), uniform across the block
+        const ulonglong2 pv = __ldcs(reinterpret_cast<const ulonglong2 *>(pt + k * pt_stride));
+#pragma unroll
+        for (int q = 0; q < NPOLY; ++q) {
+            const ulonglong2 cv = __ldg(reinterpret_cast<const ulonglong2 *>(ct + k * ct_stride + (long long)q * pt_stride));
+            mac128(acc[q][0], cv.x, pv.x);
+            mac128(acc[q][1], cv.y, pv.y);
+        }
+        if (++since_reduce >= c.max_terms) {  // reduceInPlace, Bfv.swift:365-377
+            since_reduce = 0;
+#pragma unroll
+            for (int q = 0; q < NPOLY; ++q) {
+                acc[q][0] = barrett128(to_w(acc[q][0]), p, mu_hi, mu_lo);
+                acc[q][1] = barrett128(to_w(acc[q][1]), p, mu_hi, mu_lo);
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < NPOLY; ++q) {  // reduceToCiphertext, Bfv.swift:380-394
+        u64 *dst = out + (((o * NPOLY + q) * l + r) * (long long)n) + coeff;
+        *reinterpret_cast<ulonglong2 *>(dst) = make_ulonglong2(barrett128(to_w(acc[q][0]), p, mu_hi, mu_lo),
+                                                               barrett128(to_w(acc[q][1]), p, mu_hi, mu_lo));
+    }
+}
+
+cudaError_t launch_inner_product_plain(const Context &ctx, const u64 *cts, int npoly, int l, int64_t terms, const u64 *pts,
+                                       const unsigned char *present, u64 *out, int64_t out_count, cudaStream_t stream) {
+    if (out_count == 0) return cudaSuccess;
+    if (npoly < 1 || npoly > 3 || l < 1 || l > ctx.L || ctx.n < 2) return cudaErrorInvalidValue;
+    IpConsts c;
+    c.l = l;
+    u64 qmax = 0;
+    for (int r = 0; r < l; ++r) {
+        const ModSlot &S = ctx.slots[ctx.slot_q(r)].dev;
+        c.p[r] = S.p;
+        c.mu_hi[r] = S.mu_hi;
+        c.mu_lo[r] = S.mu_lo;
+        qmax = S.p > qmax ? S.p : qmax;
+    }
+    const u128 max_product = (u128)(qmax - 1) * (qmax - 1);
+    const u128 max_count = ((~(u128)0) - qmax) / max_product;
+    c.max_terms = max_count > (u128)0x7fffffffffffffffLL ? 0x7fffffffffffffffLL : (long long)max_count;
+    const unsigned gx = (unsigned)((ctx.n / 2 + 127) / 128);
+    for (int64_t done = 0; done < out_count;) {
+        const int64_t chunk = (out_count - done) > 65535 ? 65535 : (out_count - done);
+        dim3 grid(gx ? gx : 1, (unsigned)l, (unsigned)chunk);
+        const u64 *pt = pts + done * terms * l * ctx.n;
+        const unsigned char *pr = present ? present + done * terms : nullptr;
+        u64 *o = out + done * npoly * l * ctx.n;
+        ++g_kernel_launches;
+        switch (npoly) {
+            case 1: inner_product_plain_kernel<1><<<grid, 128, 0, stream>>>(cts, pt, pr, o, c, (int)ctx.n, terms); break;
+            case 2: inner_product_plain_kernel<2><<<grid, 128, 0, stream>>>(cts, pt, pr, o, c, (int)ctx.n, terms); break;
+            default: inner_product_plain_kernel<3><<<grid, 128, 0, stream>>>(cts, pt, pr, o, c, (int)ctx.n, terms); break;
+        }
+        done += chunk;
+    }
+    return cudaGetLastError();
+}
+
+// Plaintext.convertToEvalFormat, Plaintext.swift:149-171: centered lift mod each q_r (the forward NTT follows)
+__global__ void __launch_bounds__(256) plaintext_lift_kernel(const u64 *__restrict__ plain, u64 *__restrict__ out,
+                                                            const __grid_constant__ IpConsts c, u64 t, int n) {
+    const int coeff = blockIdx.x * blockDim.x + threadIdx.x;
+    if (coeff >= n) return;
+    const int r = blockIdx.y;
+    const long long item = blockIdx.z;
+    const u64 v = plain[item * n + coeff];
+    const u64 threshold = (t + 1) >> 1;  // RnsTool.tThreshold, RnsTool.swift:123-125
+    out[(item * c.l + r) * n + coeff] = v < threshold ? v : v + (c.p[r] - t);  // tIncrement, RnsTool.swift:168
+}
+
+cudaError_t launch_plaintext_to_eval(const Context &ctx, const u64 *plain, int l, u64 *out, int64_t count,
+                                     cudaStream_t stream) {
+    if (count == 0) return cudaSuccess;
+    if (l < 1 || l > ctx.L) return cudaErrorInvalidValue;
+    IpConsts c;
+    c.l = l;
+    c.max_terms = 0;
+    for (int r = 0; r < l; ++r) c.p[r] = ctx.slots[ctx.slot_q(r)].dev.p;
+    const int threads = ctx.n >= 256 ? 256 : (ctx.n < 32 ? 32 : (int)ctx.n);
+    for (int64_t done = 0; done < count;) {
+        const int64_t chunk = (count - done) > 65535 ? 65535 : (count - done);
+        dim3 grid((unsigned)((ctx.n + threads - 1) / threads), (unsigned)l, (unsigned)chunk);
+        ++g_kernel_launches;
+        plaintext_lift_kernel<<<grid, threads, 0, stream>>>(plain + done * ctx.n, out + done * l * ctx.n, c, ctx.t, (int)ctx.n);
+        done += chunk;
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    return launch_ntt_forward(ctx, ctx.map_q(l), out, out, count * l, stream);
+}
+
+}  // namespace hecuda

@@ -54,6 +54,12 @@ cudaError_t launch_galois_coeff(const Context &ctx, const NttRowMap &map, unsign
 cudaError_t launch_galois_eval(const Context &ctx, int rows, unsigned element, const u64 *in, u64 *out, int64_t polys,
                                cudaStream_t stream);
 
+// ---- lazy ct x pt inner product and plaintext Eval conversion (innerprod.cu): Bfv.swift:476-505, Plaintext.swift:149-171
+cudaError_t launch_inner_product_plain(const Context &ctx, const u64 *cts, int npoly, int l, int64_t terms, const u64 *pts,
+                                       const unsigned char *present, u64 *out, int64_t out_count, cudaStream_t stream);
+cudaError_t launch_plaintext_to_eval(const Context &ctx, const u64 *plain, int l, u64 *out, int64_t count,
+                                     cudaStream_t stream);
+
 // divideAndRoundQLast over polys x l x N -> polys x (l-1) x N
 cudaError_t launch_mod_switch(const Context &ctx, const u64 *in, int l, u64 *out, int64_t polys, cudaStream_t stream);
 

@@ -61,6 +61,11 @@ SYMBOLS = {
     "hecuda_bfv_apply_galois": (C.c_int32, [_VP, _VP, _VP, C.c_int32, C.c_uint32, _VP, C.c_int64]),
     "hecuda_bfv_apply_galois_device": (C.c_int32, [_VP, _VP, _VP, C.c_int32, C.c_uint32, _VP, C.c_int64, _VP]),
     "hecuda_poly_apply_galois": (C.c_int32, [_VP, C.c_int32, C.c_int32, _VP, _VP, C.c_int32, C.c_int64, C.c_uint32]),
+    "hecuda_bfv_inner_product_plaintexts": (C.c_int32, [_VP, _VP, C.c_int32, C.c_int32, C.c_int64, _VP, _VP, _VP, C.c_int64]),
+    "hecuda_bfv_inner_product_plaintexts_device": (C.c_int32, [_VP, _VP, C.c_int32, C.c_int32, C.c_int64, _VP, _VP, _VP,
+                                                                C.c_int64, _VP]),
+    "hecuda_plaintext_to_eval": (C.c_int32, [_VP, _VP, C.c_int32, _VP, C.c_int64]),
+    "hecuda_plaintext_to_eval_device": (C.c_int32, [_VP, _VP, C.c_int32, _VP, C.c_int64, _VP]),
     "hecuda_kernel_launch_count": (C.c_uint64, []),
 }
 
@@ -293,6 +298,34 @@ class Bfv:
         out = np.empty_like(d)
         _check(load_library().hecuda_poly_apply_galois(context._h, base, int(evalFormat), _ptr(d), _ptr(out), rows,
                                                        d.size // (rows * context.degree), element))
+        return out
+
+    @staticmethod
+    def innerProduct(context: Context, ciphertexts, plaintexts, present=None):
+        """Bfv.innerProduct(ciphertexts:plaintexts:) (Bfv.swift:476-505), batched over plaintext rows:
+        ciphertexts (terms, polys, l, N) Eval; plaintexts (rows, terms, l, N) Eval; present (rows, terms) flags
+        (False = nil plaintext) -> (rows, polys, l, N) Eval."""
+        c, p = _host(ciphertexts), _host(plaintexts)
+        if c.ndim != 4 or c.shape[-1] != context.degree:
+            raise HeError(-1, "invalidCiphertext: expected (terms, polys, l, N)")
+        terms, polys, l = c.shape[0], c.shape[1], c.shape[2]
+        p = p.reshape(-1, terms, l, context.degree)
+        out = np.empty((p.shape[0], polys, l, context.degree), dtype=np.uint64)
+        pres = None
+        if present is not None:
+            pres = np.ascontiguousarray(np.asarray(present, dtype=np.uint8)).reshape(p.shape[0], terms)
+        _check(load_library().hecuda_bfv_inner_product_plaintexts(
+            context._h, _ptr(c), polys, l, terms, _ptr(p), C.c_void_p(pres.ctypes.data) if pres is not None else None,
+            _ptr(out), p.shape[0]))
+        return out
+
+    @staticmethod
+    def plaintextToEval(context: Context, plaintexts, moduliCount: int = 0):
+        """Plaintext.convertToEvalFormat (Plaintext.swift:149-171): (count, N) values < t -> (count, l, N) Eval."""
+        d = _host(plaintexts).reshape(-1, context.degree)
+        l = moduliCount or context.L
+        out = np.empty((d.shape[0], l, context.degree), dtype=np.uint64)
+        _check(load_library().hecuda_plaintext_to_eval(context._h, _ptr(d), l, _ptr(out), d.shape[0]))
         return out
 
     @staticmethod
