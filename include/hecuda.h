@@ -150,6 +150,13 @@ int32_t hecuda_bfv_inner_product_plaintexts_device(const hecuda_context *ctx, co
                                                    int32_t poly_count, int32_t moduli_count, int64_t term_count,
                                                    const uint64_t *plaintexts, const uint8_t *present, uint64_t *out,
                                                    int64_t out_count, void *stream);
+/* Bfv.innerProduct(_:_:) over ciphertext pairs -- Bfv/Bfv.swift:315-361 (BEHZ multiply with a shared lazy accumulator,
+ * one dropExtendedBase for the whole sum), batched over `group_count` independent inner products of `pair_count` pairs:
+ * lhs, rhs: group_count x pair_count x 2 x L x N (Coeff, top level); out: group_count x 3 x L x N (Coeff). */
+int32_t hecuda_bfv_inner_product(const hecuda_context *ctx, const uint64_t *lhs, const uint64_t *rhs, uint64_t *out,
+                                 int64_t pair_count, int64_t group_count);
+int32_t hecuda_bfv_inner_product_device(const hecuda_context *ctx, const uint64_t *lhs, const uint64_t *rhs, uint64_t *out,
+                                        int64_t pair_count, int64_t group_count, void *stream);
 /* Plaintext.convertToEvalFormat(moduliCount:) -- Plaintext.swift:149-171 (database preprocessing): `count` coefficient
  * plaintexts of N values < t  ->  count x l x N residues in Eval format. */
 int32_t hecuda_plaintext_to_eval(const hecuda_context *ctx, const uint64_t *plain, int32_t moduli_count, uint64_t *out,

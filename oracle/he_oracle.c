@@ -1287,3 +1287,65 @@ int orc_inner_product_plain(const orc_context *ctx, const uint64_t *cts, int32_t
     }
     return 0;
 }
+
+/* Bfv.innerProduct(_:_:) over ciphertext pairs, Bfv.swift:315-361: lazy 128-bit accumulation of the tensor products in
+ * [Q, Bsk] (lazyMultiply :319-331), reduceToCiphertext (:380-394), one dropExtendedBase (Bfv+Multiply.swift:31-48).
+ * lhs, rhs: groups x pairs x 2 x L x n (Coeff); out: groups x 3 x L x n (Coeff). */
+int orc_bfv_inner_product(const orc_context *ctx, const uint64_t *lhs, const uint64_t *rhs, uint64_t *out, int64_t pairs,
+                          int64_t groups, int32_t threads) {
+    const i64 n = ctx->n;
+    const int L = ctx->L, R = 2 * L + 1;
+    const orc_rnstool *rt = ctx->tools[L];
+    const i64 psz = (i64)R * n, ct_in = (i64)2 * L * n;
+    if (threads <= 0) threads = orc_num_threads();
+    /* maxProductCount = maxLazyProductAccumulationCount(qBsk) / 2, Bfv.swift:331 */
+    u64 pmax = 0;
+    for (int r = 0; r < R; r++) pmax = rt->qbsk[r] > pmax ? rt->qbsk[r] : pmax;
+    const u128 max_lazy = ((~(u128)0) - pmax) / ((u128)(pmax - 1) * (pmax - 1));
+    const i64 max_count = (i64)((max_lazy / 2) > (u128)INT64_MAX ? (u128)INT64_MAX : (max_lazy / 2));
+#pragma omp parallel for num_threads(threads) schedule(dynamic, 1)
+    for (i64 g = 0; g < groups; g++) {
+        u128 *acc = (u128 *)calloc((size_t)3 * psz, sizeof(u128));
+        u64 *buf = (u64 *)malloc(sizeof(u64) * psz * 4);
+        u64 *l0 = buf, *l1 = buf + psz, *r0 = buf + 2 * psz, *r1 = buf + 3 * psz;
+        i64 count = 0;
+        for (i64 k = 0; k < pairs; k++) {
+            const u64 *a = lhs + (g * pairs + k) * ct_in, *b = rhs + (g * pairs + k) * ct_in;
+            behz_poly(ctx, a, l0);
+            behz_poly(ctx, a + (i64)L * n, l1);
+            behz_poly(ctx, b, r0);
+            behz_poly(ctx, b + (i64)L * n, r1);
+            for (i64 i = 0; i < psz; i++) {
+                acc[i] += (u128)l0[i] * r0[i];
+                acc[psz + i] += (u128)l0[i] * r1[i];
+                acc[psz + i] += (u128)l1[i] * r0[i];
+                acc[2 * psz + i] += (u128)l1[i] * r1[i];
+            }
+            if (++count >= (max_count > 0 ? max_count : 1)) {
+                count = 0;
+                for (int p = 0; p < 3; p++)
+                    for (int r = 0; r < R; r++) {
+                        modulus_t m = modulus_make(rt->qbsk[r]);
+                        u128 *ar = acc + (i64)p * psz + (i64)r * n;
+                        for (i64 c = 0; c < n; c++) ar[c] = reduce_double(&m, ar[c]);
+                    }
+            }
+        }
+        u64 *sum = (u64 *)malloc(sizeof(u64) * psz);
+        u64 tvec[2 * ORC_MAX_MODULI];
+        for (int r = 0; r < R; r++) tvec[r] = ctx->t;
+        for (int p = 0; p < 3; p++) {
+            for (int r = 0; r < R; r++) {
+                modulus_t m = modulus_make(rt->qbsk[r]);
+                for (i64 c = 0; c < n; c++) sum[(i64)r * n + c] = reduce_double(&m, acc[(i64)p * psz + (i64)r * n + c]);
+            }
+            poly_mul_scalar_rows(n, rt->qbsk, R, sum, tvec);
+            for (int r = 0; r < R; r++) ntt_inverse_row(rt->qbsk_tables[r], sum + (i64)r * n);
+            orc_rnstool_floor(rt, sum, out + (g * 3 + p) * (i64)L * n);
+        }
+        free(sum);
+        free(buf);
+        free(acc);
+    }
+    return 0;
+}

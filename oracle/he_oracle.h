@@ -124,6 +124,9 @@ int orc_plaintext_to_eval(const orc_context *, const uint64_t *plain /* n values
 int orc_inner_product_plain(const orc_context *, const uint64_t *cts, int32_t npoly, int32_t l, int64_t terms,
                             const uint64_t *pts, const uint8_t *present, uint64_t *out, int64_t out_count, int32_t threads);
 
+int orc_bfv_inner_product(const orc_context *, const uint64_t *lhs, const uint64_t *rhs, uint64_t *out, int64_t pairs,
+                          int64_t groups, int32_t threads);
+
 /* deterministic test inputs: uniform residues row r < moduli[r % nmod] (splitmix64, rejection-free mod) */
 void orc_fill_uniform(uint64_t seed, const uint64_t *moduli, int32_t nmod, int64_t n, uint64_t *data, int64_t rows);
 int orc_num_threads(void);

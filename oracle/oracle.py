@@ -101,6 +101,7 @@ def lib():
         L.orc_plaintext_to_eval.argtypes = [C.c_void_p, u64p, C.c_int32, u64p]
         L.orc_inner_product_plain.argtypes = [C.c_void_p, u64p, C.c_int32, C.c_int32, C.c_int64, u64p,
                                               C.POINTER(C.c_uint8), u64p, C.c_int64, C.c_int32]
+        L.orc_bfv_inner_product.argtypes = [C.c_void_p, u64p, u64p, u64p, C.c_int64, C.c_int64, C.c_int32]
         L.orc_fill_uniform.restype = None
         L.orc_fill_uniform.argtypes = [C.c_uint64, u64p, C.c_int32, C.c_int64, u64p, C.c_int64]
         L.orc_num_threads.restype = C.c_int
@@ -365,6 +366,13 @@ class Context:
             pa = np.ascontiguousarray(np.asarray(present, dtype=np.uint8)).reshape(p.shape[0], terms)
             pres = pa.ctypes.data_as(C.POINTER(C.c_uint8))
         rc = lib().orc_inner_product_plain(self.h, _p(c), npoly, l, terms, _p(p), pres, _p(out), p.shape[0], threads)
+        assert rc == 0
+        return out
+
+    def inner_product(self, lhs, rhs, threads: int = 0):
+        a, b = _arr(lhs), _arr(rhs)  # (groups, pairs, 2, L, n)
+        out = np.zeros((a.shape[0], 3, self.L, self.n), dtype=np.uint64)
+        rc = lib().orc_bfv_inner_product(self.h, _p(a), _p(b), _p(out), a.shape[1], a.shape[0], threads)
         assert rc == 0
         return out
 

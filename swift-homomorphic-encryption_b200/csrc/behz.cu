@@ -134,6 +134,64 @@ __global__ void __launch_bounds__(kThreads) tensor_kernel(const u64 *__restrict_
     stc<COLS>(o + 2 * ps, o2);
 }
 
+// Sum of tensor products over `pairs` ciphertext pairs (Bfv.innerProduct(_:_:), Bfv.swift:315-361: lazyMultiply
+// accumulates l0 r0, l0 r1 + l1 r0, l1 r1 in DoubleWidth, reduceToCiphertext reduces once).  ext[group][pair][4][R][N]
+// (Eval) -> ten[group][3][R][N] in Montgomery form like tensor_kernel.  max_pairs bounds the lazy accumulation
+// (maxLazyProductAccumulationCount / 2, Bfv.swift:331); beyond it the accumulators are Barrett-reduced in place.
+struct TensorSumConsts {
+    int R;
+    long long max_pairs;
+    u64 p[kMaxRows], ninv[kMaxRows], mu1[kMaxRows], mu_hi[kMaxRows], mu_lo[kMaxRows];
+};
+
+__global__ void __launch_bounds__(kThreads) tensor_sum_kernel(const u64 *__restrict__ ext, u64 *__restrict__ ten,
+                                                             const __grid_constant__ TensorSumConsts c, int n,
+                                                             long long pairs) {
+    const int R = c.R;
+    const int row = blockIdx.y;
+    const int64_t group = blockIdx.z;
+    const int coeff = (blockIdx.x * kThreads + threadIdx.x) * 2;
+    if (coeff >= n) return;
+    const u64 p = c.p[row], ninv = c.ninv[row];
+    const int64_t ps = (int64_t)R * n;
+    const u64 *e = ext + (group * pairs * 4 * R + row) * n + coeff;
+    u128 a0[2] = {0, 0}, a1[2] = {0, 0}, a2[2] = {0, 0};
+    long long since = 0;
+    for (long long k = 0; k < pairs; ++k, e += 4 * ps) {
+        const Cols<2> l0 = ldc<2>(e), l1 = ldc<2>(e + ps), r0 = ldc<2>(e + 2 * ps), r1 = ldc<2>(e + 3 * ps);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            mac128(a0[j], l0.v[j], r0.v[j]);
+            mac128(a1[j], l0.v[j], r1.v[j]);
+            mac128(a1[j], l1.v[j], r0.v[j]);
+            mac128(a2[j], l1.v[j], r1.v[j]);
+        }
+        if (++since >= c.max_pairs) {  // reduceInPlace, Bfv.swift:365-377
+            since = 0;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                u128w w0 = {(u64)a0[j], (u64)(a0[j] >> 64)}, w1 = {(u64)a1[j], (u64)(a1[j] >> 64)},
+                      w2 = {(u64)a2[j], (u64)(a2[j] >> 64)};
+                a0[j] = barrett128(w0, p, c.mu_hi[row], c.mu_lo[row]);
+                a1[j] = barrett128(w1, p, c.mu_hi[row], c.mu_lo[row]);
+                a2[j] = barrett128(w2, p, c.mu_hi[row], c.mu_lo[row]);
+            }
+        }
+    }
+    u64 *o = ten + (group * 3 * R + row) * n + coeff;
+    u64 o0[2], o1[2], o2[2];
+    const u64 mu1 = c.mu1[row];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {  // sums < 2^127 (max_pairs) -> Montgomery result < 2^63 + p; one single-word Barrett
+        o0[j] = barrett64(mont_reduce(a0[j], p, ninv), p, mu1);
+        o1[j] = barrett64(mont_reduce(a1[j], p, ninv), p, mu1);
+        o2[j] = barrett64(mont_reduce(a2[j], p, ninv), p, mu1);
+    }
+    stc<2>(o, o0);
+    stc<2>(o + ps, o1);
+    stc<2>(o + 2 * ps, o2);
+}
+
 template <int L, int COLS>
 __global__ void __launch_bounds__(kThreads) floor_kernel(const u64 *__restrict__ in, u64 *__restrict__ out,
                                                         const __grid_constant__ FloorConsts c, int n) {
@@ -266,6 +324,39 @@ cudaError_t launch_tensor(const Context &ctx, const u64 *ext, u64 *ten, int64_t 
         else
             tensor_kernel<1><<<grid, kThreads, 0, stream>>>(ext + done * 4 * tc.R * ctx.n, ten + done * 3 * tc.R * ctx.n, tc,
                                                             (int)ctx.n);
+        done += chunk;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_tensor_sum(const Context &ctx, const u64 *ext, u64 *ten, int64_t pairs, int64_t groups,
+                              cudaStream_t stream) {
+    if (groups == 0) return cudaSuccess;
+    if (ctx.n < 2 || pairs < 1) return cudaErrorInvalidValue;
+    TensorSumConsts tc;
+    tc.R = 2 * ctx.L + 1;
+    const NttRowMap map = ctx.map_qbsk();
+    u64 pmax = 0;
+    for (int r = 0; r < tc.R; ++r) {
+        const ModSlot &S = ctx.slots[map.slot[r]].dev;
+        tc.p[r] = S.p;
+        tc.ninv[r] = S.ninv;
+        tc.mu1[r] = S.mu1;
+        tc.mu_hi[r] = S.mu_hi;
+        tc.mu_lo[r] = S.mu_lo;
+        pmax = S.p > pmax ? S.p : pmax;
+    }
+    // each pair adds < 2 p^2 to the middle accumulator; keep every accumulator below 2^127
+    const u128 per_pair = 2 * (u128)pmax * pmax;
+    const u128 cap = (((u128)1) << 127) / per_pair;
+    tc.max_pairs = cap < 1 ? 1 : (cap > (u128)0x7fffffffLL ? 0x7fffffffLL : (long long)cap);
+    const unsigned gx = (unsigned)((ctx.n / 2 + kThreads - 1) / kThreads);
+    for (int64_t done = 0; done < groups;) {
+        const int64_t chunk = (groups - done) > 65535 ? 65535 : (groups - done);
+        dim3 grid(gx ? gx : 1, (unsigned)tc.R, (unsigned)chunk);
+        ++g_kernel_launches;
+        tensor_sum_kernel<<<grid, kThreads, 0, stream>>>(ext + done * pairs * 4 * tc.R * ctx.n, ten + done * 3 * tc.R * ctx.n,
+                                                         tc, (int)ctx.n, pairs);
         done += chunk;
     }
     return cudaGetLastError();

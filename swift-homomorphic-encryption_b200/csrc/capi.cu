@@ -808,6 +808,77 @@ int32_t hecuda_plaintext_to_eval(const hecuda_context *h, const uint64_t *plain,
                          });
 }
 
+// ---------------------------------------------------------------- ct x ct inner product
+
+// Bfv.innerProduct(_:_:) (Bfv.swift:315-361): sum of the tensor products of `pairs` ciphertext pairs in [Q, Bsk],
+// then ONE dropExtendedBase -- instead of `pairs` full multiplies.
+static cudaError_t inner_product_chunk(const Context &c, u64 *scratch, const u64 *lhs, const u64 *rhs, int64_t pairs,
+                                       u64 *out, int64_t groups, cudaStream_t s) {
+    const int R = 2 * c.L + 1;
+    const size_t poly_words = (size_t)R * c.n;
+    const int64_t items = groups * pairs;
+    u64 *ext = scratch, *ten = scratch + 4 * poly_words * items;
+    const NttRowMap map = c.map_qbsk();
+    cudaError_t e;
+    if ((e = launch_lift(c, lhs, 2, ext, 4, 0, items, s)) != cudaSuccess) return e;
+    if ((e = launch_lift(c, rhs, 2, ext, 4, 2, items, s)) != cudaSuccess) return e;
+    if ((e = launch_ntt_forward(c, map, ext, ext, items * 4 * R, s)) != cudaSuccess) return e;
+    if ((e = launch_tensor_sum(c, ext, ten, pairs, groups, s)) != cudaSuccess) return e;
+    if ((e = launch_ntt_inverse(c, map, ten, ten, groups * 3 * R, kScaleTMont, s)) != cudaSuccess) return e;
+    return launch_floor(c, ten, out, groups * 3, s);
+}
+static size_t inner_product_scratch_words(const Context &c, int64_t pairs) {
+    return (size_t)(4 * pairs + 3) * (2 * c.L + 1) * c.n;
+}
+
+static int32_t check_ipc(const hecuda_context *h, const uint64_t *lhs, const uint64_t *rhs, uint64_t *out, int64_t pairs,
+                         int64_t groups) {
+    int32_t rc = check_ctx(h);
+    if (rc) return rc;
+    if (pairs < 1) return fail(HECUDA_ERR_INVALID_ARGUMENT, "Empty ciphertexts");
+    if (groups < 0 || (groups && (!lhs || !rhs || !out))) return fail(HECUDA_ERR_INVALID_ARGUMENT, "invalidCiphertext: null buffer");
+    if (h->ctx->n < 2) return fail(HECUDA_ERR_UNSUPPORTED, "degree too small");
+    return HECUDA_OK;
+}
+
+int32_t hecuda_bfv_inner_product_device(const hecuda_context *h, const uint64_t *lhs, const uint64_t *rhs, uint64_t *out,
+                                        int64_t pairs, int64_t groups, void *stream) {
+    int32_t rc = check_ipc(h, lhs, rhs, out, pairs, groups);
+    if (rc) return rc;
+    if (groups == 0) return HECUDA_OK;
+    const Context &c = *h->ctx;
+    const size_t in_words = (size_t)pairs * 2 * c.L * c.n, out_words = (size_t)3 * c.L * c.n;
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(std::max<int64_t>(1, h->chunk / pairs), groups));
+    cudaStream_t s = (cudaStream_t)stream;
+    u64 *scratch = nullptr;
+    CK(cudaMallocAsync(&scratch, inner_product_scratch_words(c, pairs) * (size_t)chunk * sizeof(u64), s));
+    for (int64_t done = 0; done < groups; done += chunk) {
+        const int64_t g = std::min<int64_t>(chunk, groups - done);
+        cudaError_t e = inner_product_chunk(c, scratch, (const u64 *)lhs + in_words * done, (const u64 *)rhs + in_words * done,
+                                            pairs, (u64 *)out + out_words * done, g, s);
+        if (e != cudaSuccess) {
+            cudaFreeAsync(scratch, s);
+            return cuda_fail(e, "innerProduct");
+        }
+    }
+    CK(cudaFreeAsync(scratch, s));
+    return HECUDA_OK;
+}
+
+int32_t hecuda_bfv_inner_product(const hecuda_context *h, const uint64_t *lhs, const uint64_t *rhs, uint64_t *out,
+                                 int64_t pairs, int64_t groups) {
+    int32_t rc = check_ipc(h, lhs, rhs, out, pairs, groups);
+    if (rc) return rc;
+    const Context &c = *h->ctx;
+    const size_t in_words = (size_t)pairs * 2 * c.L * c.n;
+    std::vector<HostIo> in = {{(const u64 *)lhs, in_words}, {(const u64 *)rhs, in_words}};
+    const int64_t chunk = std::max<int64_t>(1, h->chunk / pairs);
+    return host_pipeline(h, groups, chunk, inner_product_scratch_words(c, pairs), in, (u64 *)out, (size_t)3 * c.L * c.n,
+                         [&](Workspace &w, const std::vector<const u64 *> &d_in, u64 *d_out, int64_t g) {
+                             return inner_product_chunk(c, w.buf[0], d_in[0], d_in[1], pairs, d_out, g, w.stream);
+                         });
+}
+
 uint64_t hecuda_kernel_launch_count(void) { return g_kernel_launches.load(); }
 
 }  // extern "C"

@@ -37,6 +37,9 @@ cudaError_t launch_lift(const Context &ctx, const u64 *in, int polys_in, u64 *ex
                         int64_t items, cudaStream_t stream);
 // tensor: ext[item][4][R][N] (Eval) -> ten[item][3][R][N]
 cudaError_t launch_tensor(const Context &ctx, const u64 *ext, u64 *ten, int64_t items, cudaStream_t stream);
+// tensor sum: ext[group][pair][4][R][N] (Eval) -> ten[group][3][R][N]  (Bfv.innerProduct(_:_:), Bfv.swift:315-361)
+cudaError_t launch_tensor_sum(const Context &ctx, const u64 *ext, u64 *ten, int64_t pairs, int64_t groups,
+                              cudaStream_t stream);
 // floor: polys x R x N (Coeff, already scaled by t) -> polys x L x N
 cudaError_t launch_floor(const Context &ctx, const u64 *in, u64 *out, int64_t polys, cudaStream_t stream);
 

@@ -64,6 +64,8 @@ SYMBOLS = {
     "hecuda_bfv_inner_product_plaintexts": (C.c_int32, [_VP, _VP, C.c_int32, C.c_int32, C.c_int64, _VP, _VP, _VP, C.c_int64]),
     "hecuda_bfv_inner_product_plaintexts_device": (C.c_int32, [_VP, _VP, C.c_int32, C.c_int32, C.c_int64, _VP, _VP, _VP,
                                                                 C.c_int64, _VP]),
+    "hecuda_bfv_inner_product": (C.c_int32, [_VP, _VP, _VP, _VP, C.c_int64, C.c_int64]),
+    "hecuda_bfv_inner_product_device": (C.c_int32, [_VP, _VP, _VP, _VP, C.c_int64, C.c_int64, _VP]),
     "hecuda_plaintext_to_eval": (C.c_int32, [_VP, _VP, C.c_int32, _VP, C.c_int64]),
     "hecuda_plaintext_to_eval_device": (C.c_int32, [_VP, _VP, C.c_int32, _VP, C.c_int64, _VP]),
     "hecuda_kernel_launch_count": (C.c_uint64, []),
@@ -317,6 +319,16 @@ class Bfv:
         _check(load_library().hecuda_bfv_inner_product_plaintexts(
             context._h, _ptr(c), polys, l, terms, _ptr(p), C.c_void_p(pres.ctypes.data) if pres is not None else None,
             _ptr(out), p.shape[0]))
+        return out
+
+    @staticmethod
+    def innerProductCiphertexts(context: Context, lhs, rhs):
+        """Bfv.innerProduct(_:_:) (Bfv.swift:315-361): (groups, pairs, 2, L, N) x same -> (groups, 3, L, N)."""
+        a, b = _host(lhs), _host(rhs)
+        if a.ndim != 5 or a.shape != b.shape or a.shape[2:] != (2, context.L, context.degree):
+            raise HeError(-1, f"invalidCiphertext: expected (groups, pairs, 2, {context.L}, {context.degree})")
+        out = np.empty((a.shape[0], 3, context.L, context.degree), dtype=np.uint64)
+        _check(load_library().hecuda_bfv_inner_product(context._h, _ptr(a), _ptr(b), _ptr(out), a.shape[1], a.shape[0]))
         return out
 
     @staticmethod

@@ -76,3 +76,19 @@ def test_inner_product_errors():
     with pytest.raises(hecuda.HeError):  # moduli count above the ciphertext context
         hecuda.Bfv.innerProduct(g, np.zeros((2, 2, 3, n), dtype=np.uint64), np.zeros((1, 2, 3, n), dtype=np.uint64))
     g.close()
+
+
+@pytest.mark.parametrize("n,nmod,pairs,groups", [(16, 3, 4, 2), (64, 4, 1, 3), (4096, 4, 8, 2), (8192, 4, 5, 2)])
+def test_ct_ct_inner_product_matches_oracle(n, nmod, pairs, groups):
+    """Bfv.innerProduct(_:_:) (Bfv.swift:315-361); RlweBenchmark uses 8 ct x ct terms (RlweBenchmark.swift:816-820)."""
+    moduli = orc.generate_primes([55] * nmod, False, n)
+    t = orc.generate_primes([12], True, 1)[0]
+    g, o = hecuda.Context(n, moduli, t), orc.Context(n, moduli, t)
+    L = o.L
+    lhs = orc.fill_uniform(3, moduli[:L], n, groups * pairs * 2 * L).reshape(groups, pairs, 2, L, n)
+    rhs = orc.fill_uniform(4, moduli[:L], n, groups * pairs * 2 * L).reshape(groups, pairs, 2, L, n)
+    got = hecuda.Bfv.innerProductCiphertexts(g, lhs, rhs)
+    assert np.array_equal(got, o.inner_product(lhs, rhs))
+    if pairs == 1:
+        assert np.array_equal(got, hecuda.Bfv.mulAssign(g, lhs[:, 0], rhs[:, 0]))
+    g.close()

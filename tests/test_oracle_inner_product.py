@@ -67,3 +67,25 @@ def test_plaintext_to_eval_and_inner_product_decrypts():
         prod = negacyclic_mul(ms[k], ps[k], t)
         expect = [(a + b) % t for a, b in zip(expect, prod)]
     assert ctx.decrypt(sk, coeff).tolist() == expect
+
+
+def test_ct_ct_inner_product_decrypts_and_matches_single_multiply():
+    n = 32
+    moduli = orc.generate_primes([55, 55, 55, 55], False, n)
+    t = orc.generate_primes([10], True, 1)[0]
+    ctx = orc.Context(n, moduli, t)
+    L = ctx.L
+    rnd = random.Random(6)
+    sk, _ = ctx.keygen(1, relin=False)
+    pairs = 3
+    ms = [[rnd.randrange(t) for _ in range(n)] for _ in range(2 * pairs)]
+    lhs = np.stack([ctx.encrypt(10 + k, sk, ms[2 * k]) for k in range(pairs)])[None]
+    rhs = np.stack([ctx.encrypt(20 + k, sk, ms[2 * k + 1]) for k in range(pairs)])[None]
+    out = ctx.inner_product(lhs, rhs)[0]
+    expect = [0] * n
+    for k in range(pairs):
+        expect = [(a + b) % t for a, b in zip(expect, negacyclic_mul(ms[2 * k], ms[2 * k + 1], t))]
+    assert ctx.decrypt(sk, out).tolist() == expect
+    # with a single pair the inner product IS the multiply (same tensor, same dropExtendedBase)
+    one = ctx.inner_product(lhs[:, :1], rhs[:, :1])[0]
+    assert np.array_equal(one, ctx.mul(lhs[0, :1], rhs[0, :1])[0])
