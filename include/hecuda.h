@@ -135,6 +135,11 @@ int32_t hecuda_bfv_apply_galois_device(const hecuda_context *ctx, const hecuda_e
 int32_t hecuda_poly_apply_galois(const hecuda_context *ctx, int32_t base, int32_t eval_format, const uint64_t *in,
                                  uint64_t *out, int32_t row_count, int64_t poly_count, uint32_t element);
 
+/* PolyRq<Coeff>.multiplyPowerOfX(_:) -- PolyRq/PolyRq.swift:398-422 (MulPir query expansion, PirUtil.swift:204-241):
+ * multiplication by X^power (power may be negative) in Z_q[X]/(X^N + 1); in, out: poly_count x row_count x N. */
+int32_t hecuda_poly_multiply_power_of_x(const hecuda_context *ctx, int32_t base, const uint64_t *in, uint64_t *out,
+                                        int32_t row_count, int64_t poly_count, int64_t power);
+
 /* ---- lazy ciphertext x plaintext inner product ----
  * Bfv.innerProduct(ciphertexts:plaintexts:) -- Bfv/Bfv.swift:476-505 (lazyMultiply :388-400 over
  * PolyRq.addingLazyProduct, PolyRq.swift:210-225; reduceInPlace/reduceToCiphertext :365-394), batched over

@@ -1349,3 +1349,18 @@ int orc_bfv_inner_product(const orc_context *ctx, const uint64_t *lhs, const uin
     }
     return 0;
 }
+
+/* PolyRq<Coeff>.multiplyPowerOfX, PolyRq.swift:398-422: multiplication by X^power in Z_q[X]/(X^N + 1) (power may be
+ * negative): rotate the coefficient columns and negate the wrapped ones. */
+void orc_multiply_power_of_x(int64_t n, const uint64_t *moduli, int32_t nmod, int64_t power, const uint64_t *in,
+                             uint64_t *out) {
+    const i64 two_n = 2 * n;
+    i64 s = power % two_n;
+    if (s < 0) s += two_n;
+    for (int r = 0; r < nmod; r++)
+        for (i64 i = 0; i < n; i++) {
+            const i64 raw = (i + s) % two_n;
+            const u64 v = in[(i64)r * n + i];
+            out[(i64)r * n + (raw % n)] = raw >= n ? neg_mod(v, moduli[r]) : v;
+        }
+}

@@ -127,6 +127,9 @@ int orc_inner_product_plain(const orc_context *, const uint64_t *cts, int32_t np
 int orc_bfv_inner_product(const orc_context *, const uint64_t *lhs, const uint64_t *rhs, uint64_t *out, int64_t pairs,
                           int64_t groups, int32_t threads);
 
+void orc_multiply_power_of_x(int64_t n, const uint64_t *moduli, int32_t nmod, int64_t power, const uint64_t *in,
+                             uint64_t *out); /* PolyRq.swift:398-422 */
+
 /* deterministic test inputs: uniform residues row r < moduli[r % nmod] (splitmix64, rejection-free mod) */
 void orc_fill_uniform(uint64_t seed, const uint64_t *moduli, int32_t nmod, int64_t n, uint64_t *data, int64_t rows);
 int orc_num_threads(void);

@@ -102,6 +102,8 @@ def lib():
         L.orc_inner_product_plain.argtypes = [C.c_void_p, u64p, C.c_int32, C.c_int32, C.c_int64, u64p,
                                               C.POINTER(C.c_uint8), u64p, C.c_int64, C.c_int32]
         L.orc_bfv_inner_product.argtypes = [C.c_void_p, u64p, u64p, u64p, C.c_int64, C.c_int64, C.c_int32]
+        L.orc_multiply_power_of_x.restype = None
+        L.orc_multiply_power_of_x.argtypes = [C.c_int64, u64p, C.c_int32, C.c_int64, u64p, u64p]
         L.orc_fill_uniform.restype = None
         L.orc_fill_uniform.argtypes = [C.c_uint64, u64p, C.c_int32, C.c_int64, u64p, C.c_int64]
         L.orc_num_threads.restype = C.c_int
@@ -216,6 +218,14 @@ def galois_element_rotating_columns(step: int, degree: int) -> int:
 
 def galois_element_swapping_rows(degree: int) -> int:
     return int(lib().orc_galois_element_swapping_rows(degree))
+
+
+def multiply_power_of_x(n: int, moduli, power: int, data):
+    d = _arr(data).reshape(len(moduli), n)
+    out = np.zeros_like(d)
+    m = _arr(moduli)
+    lib().orc_multiply_power_of_x(n, _p(m), len(m), power, _p(d), _p(out))
+    return out
 
 
 def fill_uniform(seed: int, moduli, n: int, rows: int):

@@ -879,6 +879,24 @@ int32_t hecuda_bfv_inner_product(const hecuda_context *h, const uint64_t *lhs, c
                          });
 }
 
+int32_t hecuda_poly_multiply_power_of_x(const hecuda_context *h, int32_t base, const uint64_t *in, uint64_t *out,
+                                        int32_t rows, int64_t polys, int64_t power) {
+    int32_t rc = check_ctx(h);
+    if (rc) return rc;
+    if (polys < 0 || (polys && (!in || !out))) return fail(HECUDA_ERR_INVALID_ARGUMENT, "invalid data / poly_count");
+    NttRowMap map;
+    std::string err;
+    if (!make_map(*h->ctx, base, rows, map, err)) return fail(HECUDA_ERR_INVALID_ARGUMENT, err);
+    const Context &c = *h->ctx;
+    const size_t words = (size_t)rows * c.n;
+    std::vector<HostIo> hin = {{(const u64 *)in, words}};
+    const int64_t chunk = std::max<int64_t>(1, (int64_t)((size_t)4 * 1024 * 1024 / words));
+    return host_pipeline(h, polys, chunk, 0, hin, (u64 *)out, words,
+                         [&](Workspace &w, const std::vector<const u64 *> &d_in, u64 *d_out, int64_t items) {
+                             return launch_multiply_power_of_x(c, map, power, d_in[0], d_out, items, w.stream);
+                         });
+}
+
 uint64_t hecuda_kernel_launch_count(void) { return g_kernel_launches.load(); }
 
 }  // extern "C"

@@ -42,6 +42,40 @@ __global__ void __launch_bounds__(256) galois_eval_kernel(const u64 *__restrict_
     out[base + i] = in[base + src];
 }
 
+// PolyRq<Coeff>.multiplyPowerOfX (PolyRq.swift:398-422) as a gather: out[c] = +-in[(c - s) mod N], s = power mod 2N
+__global__ void __launch_bounds__(256) monomial_kernel(const u64 *__restrict__ in, u64 *__restrict__ out,
+                                                      const __grid_constant__ GaloisConsts c, int logn, unsigned s) {
+    const int n = 1 << logn;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const int row = blockIdx.y;
+    const int64_t base = ((int64_t)blockIdx.z * c.rows + row) * n;
+    const unsigned raw = ((unsigned)e - s) & (2u * n - 1u);
+    const u64 v = in[base + (raw & (n - 1u))];
+    out[base + e] = (raw >= (unsigned)n && v != 0) ? c.p[row] - v : v;
+}
+
+cudaError_t launch_multiply_power_of_x(const Context &ctx, const NttRowMap &map, long long power, const u64 *in, u64 *out,
+                                       int64_t polys, cudaStream_t stream) {
+    if (polys == 0) return cudaSuccess;
+    GaloisConsts c;
+    c.rows = map.rows_per_poly;
+    for (int r = 0; r < c.rows; ++r) c.p[r] = ctx.slots[map.slot[r]].dev.p;
+    const long long two_n = 2 * ctx.n;
+    long long s = power % two_n;
+    if (s < 0) s += two_n;
+    const int threads = ctx.n >= 256 ? 256 : (ctx.n < 32 ? 32 : (int)ctx.n);
+    for (int64_t done = 0; done < polys;) {
+        const int64_t chunk = (polys - done) > 65535 ? 65535 : (polys - done);
+        dim3 grid((unsigned)((ctx.n + threads - 1) / threads), (unsigned)c.rows, (unsigned)chunk);
+        ++g_kernel_launches;
+        monomial_kernel<<<grid, threads, 0, stream>>>(in + done * c.rows * ctx.n, out + done * c.rows * ctx.n, c, ctx.logn,
+                                                      (unsigned)s);
+        done += chunk;
+    }
+    return cudaGetLastError();
+}
+
 static unsigned inverse_mod_pow2(unsigned g, unsigned two_n) {  // g odd
     unsigned inv = g;
     for (int i = 0; i < 5; ++i) inv *= 2u - g * inv;

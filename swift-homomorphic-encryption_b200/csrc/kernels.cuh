@@ -54,6 +54,8 @@ cudaError_t launch_ks_finish(const Context &ctx, const u64 *prod, const u64 *bas
 cudaError_t launch_galois_coeff(const Context &ctx, const NttRowMap &map, unsigned element, const u64 *in,
                                 int64_t in_poly_stride, u64 *out, int64_t out_poly_stride, int64_t polys,
                                 cudaStream_t stream);
+cudaError_t launch_multiply_power_of_x(const Context &ctx, const NttRowMap &map, long long power, const u64 *in, u64 *out,
+                                       int64_t polys, cudaStream_t stream);
 cudaError_t launch_galois_eval(const Context &ctx, int rows, unsigned element, const u64 *in, u64 *out, int64_t polys,
                                cudaStream_t stream);
 

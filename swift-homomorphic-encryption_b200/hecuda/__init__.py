@@ -64,6 +64,7 @@ SYMBOLS = {
     "hecuda_bfv_inner_product_plaintexts": (C.c_int32, [_VP, _VP, C.c_int32, C.c_int32, C.c_int64, _VP, _VP, _VP, C.c_int64]),
     "hecuda_bfv_inner_product_plaintexts_device": (C.c_int32, [_VP, _VP, C.c_int32, C.c_int32, C.c_int64, _VP, _VP, _VP,
                                                                 C.c_int64, _VP]),
+    "hecuda_poly_multiply_power_of_x": (C.c_int32, [_VP, C.c_int32, _VP, _VP, C.c_int32, C.c_int64, C.c_int64]),
     "hecuda_bfv_inner_product": (C.c_int32, [_VP, _VP, _VP, _VP, C.c_int64, C.c_int64]),
     "hecuda_bfv_inner_product_device": (C.c_int32, [_VP, _VP, _VP, _VP, C.c_int64, C.c_int64, _VP]),
     "hecuda_plaintext_to_eval": (C.c_int32, [_VP, _VP, C.c_int32, _VP, C.c_int64]),
@@ -319,6 +320,16 @@ class Bfv:
         _check(load_library().hecuda_bfv_inner_product_plaintexts(
             context._h, _ptr(c), polys, l, terms, _ptr(p), C.c_void_p(pres.ctypes.data) if pres is not None else None,
             _ptr(out), p.shape[0]))
+        return out
+
+    @staticmethod
+    def multiplyPowerOfX(context: Context, polys, power: int, base: int = BASE_Q):
+        """PolyRq.multiplyPowerOfX (PolyRq.swift:398-422) on (..., rows, N) Coeff polynomials."""
+        d = _host(polys)
+        rows = d.shape[-2]
+        out = np.empty_like(d)
+        _check(load_library().hecuda_poly_multiply_power_of_x(context._h, base, _ptr(d), _ptr(out), rows,
+                                                              d.size // (rows * context.degree), power))
         return out
 
     @staticmethod

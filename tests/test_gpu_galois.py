@@ -79,3 +79,17 @@ def test_apply_galois_matches_oracle_and_decrypts(n, bits, nmod):
         hecuda.Bfv.applyGalois(g, np.zeros((1, 3, L, n), dtype=np.uint64), 3, key)
     key.close()
     g.close()
+
+
+@pytest.mark.parametrize("n", [8, 64, 8192])
+def test_multiply_power_of_x_matches_oracle(n):
+    moduli = primes(55, 4, n)
+    g = hecuda.Context(n, moduli, 2)
+    q = moduli[:3]
+    x = orc.fill_uniform(n + 1, q, n, 2 * 3).reshape(2, 3, n)
+    x[0, :, 0] = 0
+    for power in (0, 1, -1, n // 2, n, n + 3, -(n + 3), 2 * n, 5 * n + 1, -7 * n - 2):
+        got = hecuda.Bfv.multiplyPowerOfX(g, x, power)
+        assert np.array_equal(got[0], orc.multiply_power_of_x(n, q, power, x[0])), power
+        assert np.array_equal(got[1], orc.multiply_power_of_x(n, q, power, x[1])), power
+    g.close()

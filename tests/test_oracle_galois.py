@@ -61,3 +61,20 @@ def test_apply_galois_decrypts_to_automorphism(n, bits, nmod):
             low = ctx.mod_switch_down(ct[None])
             out_low = ctx.apply_galois(low, element, gk)[0]
             assert ctx.decrypt(sk, out_low).tolist() == expect.tolist()
+
+
+def test_multiply_power_of_x_kats():  # PolyRqTests.swift:179-244
+    moduli, data = [2, 3, 5], [[0, 1, 0, 1], [0, 1, 2, 0], [0, 1, 2, 3]]
+    neg = [orc.multiply_power_of_x(4, moduli, -i, data).tolist() for i in range(8)]
+    pos = [orc.multiply_power_of_x(4, moduli, i, data).tolist() for i in range(8)]
+    assert neg[0] == data and pos[0] == data
+    assert neg[1] == [[1, 0, 1, 0], [1, 2, 0, 0], [1, 2, 3, 0]]
+    assert neg[2] == [[0, 1, 0, 1], [2, 0, 0, 2], [2, 3, 0, 4]]
+    assert neg[3] == [[1, 0, 1, 0], [0, 0, 2, 1], [3, 0, 4, 3]]
+    assert pos[1] == [[1, 0, 1, 0], [0, 0, 1, 2], [2, 0, 1, 2]]
+    assert pos[2] == [[0, 1, 0, 1], [1, 0, 0, 1], [3, 2, 0, 1]]
+    assert pos[3] == [[1, 0, 1, 0], [2, 1, 0, 0], [4, 3, 2, 0]]
+    for ys in (neg, pos):  # X^(i+N) = -X^i
+        for i in range(4):
+            z = orc.poly_op("add", 4, moduli, ys[i], ys[i + 4])
+            assert not z.any()
