@@ -103,13 +103,34 @@ def host_threads():
         return max(1, os.cpu_count() or 1)
 
 
+def best_thread_count(ctx, n, L):
+    """All logical CPUs or half of them (one per physical core), whichever runs the oracle faster on a short probe --
+    the CPU baseline should get its best configuration."""
+    from oracle import oracle as orc
+
+    full = host_threads()
+    candidates = sorted({full, max(1, full // 2)}, reverse=True)
+    best, best_rate = full, 0.0
+    for c in candidates:
+        k = 2 * c
+        a = orc.fill_uniform(11, ctx.q, n, k * 2 * L).reshape(k, 2, L, n)
+        b = orc.fill_uniform(12, ctx.q, n, k * 2 * L).reshape(k, 2, L, n)
+        ctx.mul(a[:c], b[:c], threads=c)  # warm the threads / page in
+        t0 = time.perf_counter()
+        ctx.mul(a, b, threads=c)
+        rate = k / (time.perf_counter() - t0)
+        if rate > best_rate:
+            best, best_rate = c, rate
+    return best
+
+
 def cpu_reference_throughput(n, moduli, t, budget_s=12.0, threads=0):
     """Times the oracle (C restatement of the Swift reference) on a bounded sample of the same workload."""
     from oracle import oracle as orc
 
     ctx = orc.Context(n, moduli, t)
     L = ctx.L
-    cores = threads or host_threads()
+    cores = threads or best_thread_count(ctx, n, L)
     probe = max(1, min(cores, 8))
     a = orc.fill_uniform(1, ctx.q, n, probe * 2 * L).reshape(probe, 2, L, n)
     b = orc.fill_uniform(2, ctx.q, n, probe * 2 * L).reshape(probe, 2, L, n)
@@ -136,7 +157,7 @@ def run_reference(args):
 
     ctx = orc.Context(n, moduli, t)
     L = ctx.L
-    cores = host_threads()
+    cores = best_thread_count(ctx, n, L)
     sample = max(cores, 2 * cores)  # bounded per-step sample of the batch
     a = orc.fill_uniform(3, ctx.q, n, sample * 2 * L).reshape(sample, 2, L, n)
     b = orc.fill_uniform(4, ctx.q, n, sample * 2 * L).reshape(sample, 2, L, n)
