@@ -34,6 +34,7 @@ extern "C" {
 
 typedef struct hecuda_context hecuda_context; /* Context<Bfv<UInt64>>, Context.swift:19 */
 typedef struct hecuda_evk hecuda_evk;         /* EvaluationKey<Bfv<UInt64>>, Keys.swift:66-99,222 */
+typedef struct hecuda_pir_database hecuda_pir_database; /* ProcessedDatabase<Bfv<UInt64>>, IndexPir/IndexPirDatabase.swift */
 
 enum {
     HECUDA_OK = 0,
@@ -168,6 +169,45 @@ int32_t hecuda_plaintext_to_eval(const hecuda_context *ctx, const uint64_t *plai
                                  int64_t count);
 int32_t hecuda_plaintext_to_eval_device(const hecuda_context *ctx, const uint64_t *plain, int32_t moduli_count,
                                         uint64_t *out, int64_t count, void *stream);
+
+/* ---- MulPir index-PIR server ----
+ * Device-resident ProcessedDatabase: `count` optional plaintexts in the order MulPirServer.process emits them
+ * (IndexPir/MulPir.swift:433-556: chunk-major, then column-major over the first dimension).  plaintexts is
+ * count x L x N in Eval format (eval_format = 1) or count x N coefficient vectors with values < t (eval_format = 0,
+ * converted on the device as Plaintext.convertToEvalFormat does, Plaintext.swift:149-171).  present[i] = 0 marks a
+ * `nil` plaintext (skipped by the inner product, Bfv.swift:488-494); NULL = all present. */
+int32_t hecuda_pir_database_create(const hecuda_context *ctx, const uint64_t *plaintexts, int32_t eval_format,
+                                   const uint8_t *present, int64_t count, hecuda_pir_database **out);
+int32_t hecuda_pir_database_destroy(hecuda_pir_database *db);
+int32_t hecuda_pir_database_device_buffer(hecuda_pir_database *db, void **device_ptr, uint64_t *bytes);
+
+/* PirUtil.expand(ciphertexts:outputCount:using:) -- IndexPir/PirUtil.swift:321-355 (expandCiphertext :249-304,
+ * expandCiphertextForOneStep :204-236).  ciphertexts: ciphertext_count x 2 x L x N (Coeff); out: output_count x 2 x L x N,
+ * output i encrypting the constant polynomial whose constant is coefficient i of the inputs (x 2^ceilLog2(count)).
+ * The Galois keys come from `evk` (hecuda_evk_set_galois_key); the largest configured element <= 2^(logN-logStep+1)+1
+ * is applied repeatedly, HECUDA_ERR_MISSING_KEY if none fits (HeError.missingGaloisKey, :216-220). */
+int32_t hecuda_mulpir_expand(const hecuda_context *ctx, const hecuda_evk *evk, const uint64_t *ciphertexts,
+                             int32_t ciphertext_count, int64_t output_count, uint64_t *out);
+int32_t hecuda_mulpir_expand_device(const hecuda_context *ctx, const hecuda_evk *evk, const uint64_t *ciphertexts,
+                                    int32_t ciphertext_count, int64_t output_count, uint64_t *out, void *stream);
+
+/* PirUtil.computeResponse(to:using:databases:parameter:context:) -- IndexPir/PirUtil.swift:490-568 with
+ * computeResponseForOneChunk (:408-486): expand the query, forward-NTT the first dimension, one ct x pt inner product
+ * per database column, one ct x ct inner product + relinearize per further dimension, modSwitchDownToSingle
+ * (HeScheme.swift:1481-1485).  dimensions = IndexPirParameter.dimensions, chunk_count =
+ * ceil(encodedEntrySize / bytesPerPlaintext) (:507); query: query_ciphertext_count x 2 x L x N (Coeff) holding
+ * indices_count queries; database_count is 1 or >= indices_count (PirError.invalidBatchSize otherwise, :498-500).
+ * out: indices_count x chunk_count x 2 x 1 x N (Coeff, single modulus q_0) = Response.ciphertexts. */
+int32_t hecuda_mulpir_compute_response(const hecuda_context *ctx, const hecuda_evk *evk,
+                                       const hecuda_pir_database *const *databases, int32_t database_count,
+                                       const int32_t *dimensions, int32_t dimension_count, int32_t chunk_count,
+                                       const uint64_t *query, int32_t query_ciphertext_count, int32_t indices_count,
+                                       uint64_t *out);
+int32_t hecuda_mulpir_compute_response_device(const hecuda_context *ctx, const hecuda_evk *evk,
+                                              const hecuda_pir_database *const *databases, int32_t database_count,
+                                              const int32_t *dimensions, int32_t dimension_count, int32_t chunk_count,
+                                              const uint64_t *query, int32_t query_ciphertext_count,
+                                              int32_t indices_count, uint64_t *out, void *stream);
 
 /* Bookkeeping for bench.py: number of kernel launches issued by this library in the calling process so far. */
 uint64_t hecuda_kernel_launch_count(void);

@@ -16,8 +16,7 @@
 #include <string>
 #include <vector>
 
-#include "context.hpp"
-#include "kernels.cuh"
+#include "capi_internal.hpp"
 
 namespace hecuda {
 std::atomic<unsigned long long> g_kernel_launches{0};
@@ -25,9 +24,10 @@ std::atomic<unsigned long long> g_kernel_launches{0};
 
 using namespace hecuda;
 
-namespace {
+namespace hecuda {
+namespace api {
 
-thread_local std::string tl_error;
+static thread_local std::string tl_error;
 
 int32_t fail(int32_t code, const std::string &msg) {
     tl_error = msg;
@@ -36,85 +36,15 @@ int32_t fail(int32_t code, const std::string &msg) {
 int32_t cuda_fail(cudaError_t e, const char *what) {
     return fail(HECUDA_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
 }
-#define CK(expr)                                          \
-    do {                                                  \
-        cudaError_t e_ = (expr);                          \
-        if (e_ != cudaSuccess) return cuda_fail(e_, #expr); \
-    } while (0)
+const char *last_error_cstr() { return tl_error.c_str(); }
 
-// Scratch for one in-flight chunk.  Grows on demand, never shrinks.
-struct Workspace {
-    cudaStream_t stream = nullptr;
-    bool owns_stream = false;
-    u64 *buf[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    size_t cap[6] = {0, 0, 0, 0, 0, 0};
-    cudaError_t reserve(int i, size_t words) {
-        if (cap[i] >= words) return cudaSuccess;
-        if (buf[i]) {
-            cudaError_t e = cudaFree(buf[i]);
-            if (e != cudaSuccess) return e;
-            buf[i] = nullptr;
-            cap[i] = 0;
-        }
-        cudaError_t e = cudaMalloc(&buf[i], words * sizeof(u64));
-        if (e == cudaSuccess) cap[i] = words;
-        return e;
-    }
-    void release() {
-        for (int i = 0; i < 6; ++i)
-            if (buf[i]) cudaFree(buf[i]);
-        if (owns_stream && stream) cudaStreamDestroy(stream);
-    }
-};
+}  // namespace api
+}  // namespace hecuda
 
-}  // namespace
+using namespace hecuda::api;
 
-struct hecuda_context {
-    Context *ctx = nullptr;
-    int64_t chunk = 32;  // ciphertexts per pipeline stage
-    std::mutex mu;
-    std::vector<Workspace *> free_ws;  // pooled workspaces (each with its own stream)
-    Workspace *acquire() {
-        std::lock_guard<std::mutex> g(mu);
-        if (!free_ws.empty()) {
-            Workspace *w = free_ws.back();
-            free_ws.pop_back();
-            return w;
-        }
-        Workspace *w = new (std::nothrow) Workspace();
-        if (!w) return nullptr;
-        if (cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking) != cudaSuccess) {
-            delete w;
-            return nullptr;
-        }
-        w->owns_stream = true;
-        return w;
-    }
-    void release(Workspace *w) {
-        std::lock_guard<std::mutex> g(mu);
-        free_ws.push_back(w);
-    }
-};
-
-struct hecuda_evk {
-    const hecuda_context *owner = nullptr;
-    u64 *d_relin = nullptr;  // L x 2 x K x N, Eval
-    size_t words = 0;
-    bool loaded = false;
-    std::map<uint32_t, u64 *> galois;  // GaloisKey.keys: element -> key-switch key (Keys.swift:150-163), same layout
-    std::mutex mu;
-};
-
-namespace {
-
-struct WsGuard {
-    hecuda_context *h;
-    Workspace *w;
-    WsGuard(const hecuda_context *hc) : h(const_cast<hecuda_context *>(hc)), w(h->acquire()) {}
-    ~WsGuard() {
-        if (w) h->release(w);
-    }
-};
+namespace hecuda {
+namespace api {
 
 int32_t check_ctx(const hecuda_context *h) {
     if (!h || !h->ctx) return fail(HECUDA_ERR_INVALID_ARGUMENT, "invalidContext: null context");
@@ -208,6 +138,32 @@ cudaError_t apply_galois_chunk(const Context &c, u64 *scratch, const u64 *key, c
     return keyswitch_chunk(c, ks_scratch, key, perm1, poly, l, out, ct_stride, 1, out, items, s);
 }
 
+// Bfv.innerProduct(_:_:) (Bfv.swift:315-361): sum of the tensor products of `pairs` ciphertext pairs in [Q, Bsk],
+// then ONE dropExtendedBase -- instead of `pairs` full multiplies.
+cudaError_t inner_product_chunk(const Context &c, u64 *scratch, const u64 *lhs, const u64 *rhs, int64_t pairs,
+                                       u64 *out, int64_t groups, cudaStream_t s) {
+    const int R = 2 * c.L + 1;
+    const size_t poly_words = (size_t)R * c.n;
+    const int64_t items = groups * pairs;
+    u64 *ext = scratch, *ten = scratch + 4 * poly_words * items;
+    const NttRowMap map = c.map_qbsk();
+    cudaError_t e;
+    if ((e = launch_lift(c, lhs, 2, ext, 4, 0, items, s)) != cudaSuccess) return e;
+    if ((e = launch_lift(c, rhs, 2, ext, 4, 2, items, s)) != cudaSuccess) return e;
+    if ((e = launch_ntt_forward(c, map, ext, ext, items * 4 * R, s)) != cudaSuccess) return e;
+    if ((e = launch_tensor_sum(c, ext, ten, pairs, groups, s)) != cudaSuccess) return e;
+    if ((e = launch_ntt_inverse(c, map, ten, ten, groups * 3 * R, kScaleTMont, s)) != cudaSuccess) return e;
+    return launch_floor(c, ten, out, groups * 3, s);
+}
+size_t inner_product_scratch_words(const Context &c, int64_t pairs) {
+    return (size_t)(4 * pairs + 3) * (2 * c.L + 1) * c.n;
+}
+
+}  // namespace api
+}  // namespace hecuda
+
+namespace {
+
 // Generic double-buffered host pipeline: for each chunk, copy inputs in, run `body`, copy outputs out.
 struct HostIo {
     const u64 *src;  // host
@@ -260,7 +216,7 @@ int32_t host_pipeline(const hecuda_context *h, int64_t batch, int64_t chunk_hint
 extern "C" {
 
 int32_t hecuda_version(void) { return 100; }
-const char *hecuda_last_error(void) { return tl_error.c_str(); }
+const char *hecuda_last_error(void) { return last_error_cstr(); }
 
 int32_t hecuda_device_count(int32_t *count) {
     if (!count) return fail(HECUDA_ERR_INVALID_ARGUMENT, "null count");
@@ -809,27 +765,6 @@ int32_t hecuda_plaintext_to_eval(const hecuda_context *h, const uint64_t *plain,
 }
 
 // ---------------------------------------------------------------- ct x ct inner product
-
-// Bfv.innerProduct(_:_:) (Bfv.swift:315-361): sum of the tensor products of `pairs` ciphertext pairs in [Q, Bsk],
-// then ONE dropExtendedBase -- instead of `pairs` full multiplies.
-static cudaError_t inner_product_chunk(const Context &c, u64 *scratch, const u64 *lhs, const u64 *rhs, int64_t pairs,
-                                       u64 *out, int64_t groups, cudaStream_t s) {
-    const int R = 2 * c.L + 1;
-    const size_t poly_words = (size_t)R * c.n;
-    const int64_t items = groups * pairs;
-    u64 *ext = scratch, *ten = scratch + 4 * poly_words * items;
-    const NttRowMap map = c.map_qbsk();
-    cudaError_t e;
-    if ((e = launch_lift(c, lhs, 2, ext, 4, 0, items, s)) != cudaSuccess) return e;
-    if ((e = launch_lift(c, rhs, 2, ext, 4, 2, items, s)) != cudaSuccess) return e;
-    if ((e = launch_ntt_forward(c, map, ext, ext, items * 4 * R, s)) != cudaSuccess) return e;
-    if ((e = launch_tensor_sum(c, ext, ten, pairs, groups, s)) != cudaSuccess) return e;
-    if ((e = launch_ntt_inverse(c, map, ten, ten, groups * 3 * R, kScaleTMont, s)) != cudaSuccess) return e;
-    return launch_floor(c, ten, out, groups * 3, s);
-}
-static size_t inner_product_scratch_words(const Context &c, int64_t pairs) {
-    return (size_t)(4 * pairs + 3) * (2 * c.L + 1) * c.n;
-}
 
 static int32_t check_ipc(const hecuda_context *h, const uint64_t *lhs, const uint64_t *rhs, uint64_t *out, int64_t pairs,
                          int64_t groups) {

@@ -69,6 +69,15 @@ SYMBOLS = {
     "hecuda_bfv_inner_product_device": (C.c_int32, [_VP, _VP, _VP, _VP, C.c_int64, C.c_int64, _VP]),
     "hecuda_plaintext_to_eval": (C.c_int32, [_VP, _VP, C.c_int32, _VP, C.c_int64]),
     "hecuda_plaintext_to_eval_device": (C.c_int32, [_VP, _VP, C.c_int32, _VP, C.c_int64, _VP]),
+    "hecuda_pir_database_create": (C.c_int32, [_VP, _VP, C.c_int32, _VP, C.c_int64, C.POINTER(_VP)]),
+    "hecuda_pir_database_destroy": (C.c_int32, [_VP]),
+    "hecuda_pir_database_device_buffer": (C.c_int32, [_VP, C.POINTER(_VP), C.POINTER(C.c_uint64)]),
+    "hecuda_mulpir_expand": (C.c_int32, [_VP, _VP, _VP, C.c_int32, C.c_int64, _VP]),
+    "hecuda_mulpir_expand_device": (C.c_int32, [_VP, _VP, _VP, C.c_int32, C.c_int64, _VP, _VP]),
+    "hecuda_mulpir_compute_response": (C.c_int32, [_VP, _VP, C.POINTER(_VP), C.c_int32, C.POINTER(C.c_int32), C.c_int32,
+                                                   C.c_int32, _VP, C.c_int32, C.c_int32, _VP]),
+    "hecuda_mulpir_compute_response_device": (C.c_int32, [_VP, _VP, C.POINTER(_VP), C.c_int32, C.POINTER(C.c_int32),
+                                                          C.c_int32, C.c_int32, _VP, C.c_int32, C.c_int32, _VP, _VP]),
     "hecuda_kernel_launch_count": (C.c_uint64, []),
 }
 

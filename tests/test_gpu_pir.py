@@ -1,0 +1,177 @@
+"""GPU parity for the MulPir server row: PirUtil.expand and computeResponse through the C ABI,
+bit-exact against oracle/pir_oracle.py (pinned on the reference's MulPir / Expansion / IndexPir tests), plus the
+reference's own end-to-end property: the decrypted response is the database entry."""
+import random
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import hecuda
+from hecuda import pir
+from oracle import oracle as orc
+from oracle import pir_oracle as opir
+
+TEST_MODULI_BITS = [55, 52, 62, 58]  # TestUtils.testCoefficientModuli for UInt64 (TestUtilities.swift:312-317)
+
+
+def contexts(n, bits, t):
+    moduli = orc.generate_primes(bits, False, n)
+    return hecuda.Context(n, moduli, t), orc.Context(n, moduli, t)
+
+
+def load_keys(g, o, sk, relin, elements, seed=100):
+    key = hecuda.EvaluationKey(g, relin)
+    okeys = {}
+    for i, e in enumerate(elements):
+        okeys[e] = o.galois_keygen(seed + i, sk, e)
+        key.setGaloisKey(e, okeys[e])
+    return key, okeys
+
+
+@pytest.mark.parametrize("n,bits,t", [(16, TEST_MODULI_BITS, 1153), (64, [55, 55, 55], 65537), (1024, [50, 50, 50], 17)])
+@pytest.mark.parametrize("compression", ["noCompression", "hybridCompression", "maxCompression"])
+def test_expand_matches_oracle(n, bits, t, compression):
+    g, o = contexts(n, bits, t)
+    sk, _ = o.keygen(5, relin=False)
+    rng = random.Random(n)
+    counts = sorted({1, 2, 3, 5, n // 2 + 1, n - 1, n, n + 1, n + 2, 2 * n, 2 * n + 5} if n <= 64 else {37, 200})
+    for count in counts:
+        # a single output needs no key; its configuration names 2^(logN+1)+1, which is not a valid element
+        elements = [e for e in opir.evaluation_key_config(count, n, compression) if e < 2 * n]
+        key, okeys = load_keys(g, o, sk, None, elements)
+        ones = [i for i in range(count) if rng.random() < 0.3]
+        cts = opir.compress_binary_inputs(o, count, ones, sk, 300 + count)
+        expected = np.stack(opir.expand(o, cts, count, okeys))
+        got = pir.PirUtil.expand(g, np.stack(cts), count, key)
+        assert np.array_equal(got, expected), f"outputCount {count}"
+        for index in (0, count // 2, count - 1):  # ExpansionTests: constant polynomial with the queried bit
+            dec = o.decrypt(sk, got[index])
+            assert int(dec[0]) == (1 if index in ones else 0) and not dec[1:].any()
+        key.close()
+    g.close()
+
+
+def test_expand_errors():
+    g, o = contexts(16, TEST_MODULI_BITS, 1153)
+    sk, _ = o.keygen(5, relin=False)
+    cts = np.stack(opir.compress_binary_inputs(o, 8, [1], sk, 1))
+    key, _ = load_keys(g, o, sk, None, [9])          # only x -> x^9: cannot serve logStep 1 (target 17)... 9 <= 17 applies twice
+    pir.PirUtil.expand(g, cts, 2, key)
+    key.close()
+    key, _ = load_keys(g, o, sk, None, [17])         # logStep 2 needs an element <= 9
+    with pytest.raises(hecuda.HeError) as err:
+        pir.PirUtil.expand(g, cts, 4, key)
+    assert "missingGaloisKey" in str(err.value)
+    with pytest.raises(hecuda.HeError):              # outputCount must fit the ciphertext count (PirUtil.swift:326-327)
+        pir.PirUtil.expand(g, cts, 17, key)
+    key.close()
+    g.close()
+
+
+CONFIGS = [
+    dict(entry_size=1, dims=2, uneven=False, compression="noCompression"),
+    dict(entry_size=8, dims=2, uneven=False, compression="noCompression"),
+    dict(entry_size=24, dims=2, uneven=True, compression="noCompression"),
+    dict(entry_size=24, dims=1, uneven=True, compression="noCompression"),
+    dict(entry_size=24, dims=1, uneven=True, compression="hybridCompression"),
+    dict(entry_size=24, dims=1, uneven=True, compression="maxCompression"),
+    dict(entry_size=47, dims=2, uneven=True, compression="hybridCompression"),   # 3 chunks, two dimensions
+]
+
+
+@pytest.mark.parametrize("encoding", [False, True])
+@pytest.mark.parametrize("cfg", CONFIGS)
+def test_index_pir_matches_oracle_and_decrypts(cfg, encoding):
+    """IndexPirTests.indexPirTest configurations on the reference's test context (N=16, t=1153)."""
+    g, o = contexts(16, TEST_MODULI_BITS, 1153)
+    rng = random.Random(cfg["entry_size"] * 3 + cfg["dims"] + 17 * encoding)
+    config = pir.IndexPirConfig(100, cfg["entry_size"], cfg["dims"], 2, cfg["uneven"], cfg["compression"], encoding)
+    param = pir.MulPir.generateParameter(config, g)
+    oparam = opir.generate_parameter(opir.IndexPirConfig(100, cfg["entry_size"], cfg["dims"], 2, cfg["uneven"],
+                                                         cfg["compression"], encoding), o.n, o.t)
+    assert param.dimensions == oparam.dimensions
+    database = [bytes(rng.randrange(256) for _ in range(rng.randint(1, cfg["entry_size"]) if encoding else cfg["entry_size"]))
+                for _ in range(100)]
+    sk, relin = o.keygen(31)
+    key, okeys = load_keys(g, o, sk, relin, param.evaluationKeyConfig.galoisElements)
+    server = pir.MulPirServer(param, g, [pir.MulPirServer.process(database, g, param)])
+    odb = opir.process_database(o, oparam, database)
+    for trial, batch in enumerate((2, 1)):
+        indices = rng.sample(range(100), batch)
+        query = opir.generate_query(o, oparam, indices, sk, 500 + 10 * trial)
+        expected = opir.compute_response(o, query, batch, okeys, relin, [odb], oparam)
+        got = server.computeResponse(np.stack(query), key, indicesCount=batch)
+        assert got.shape == (batch, server.chunkCount, 2, 1, 16)
+        for qi in range(batch):
+            for chunk in range(server.chunkCount):
+                assert np.array_equal(got[qi, chunk], expected[qi][chunk]), (qi, chunk)
+        reply = [[got[qi, c] for c in range(server.chunkCount)] for qi in range(batch)]
+        assert opir.decrypt_response(o, oparam, reply, indices, sk) == [database[i] for i in indices]
+    key.close()
+    g.close()
+
+
+def test_index_pir_one_database_per_query_and_errors():
+    g, o = contexts(16, TEST_MODULI_BITS, 1153)
+    rng = random.Random(4)
+    config = pir.IndexPirConfig(40, 4, 2, 2, False, "noCompression", False)
+    param = pir.MulPir.generateParameter(config, g)
+    oparam = opir.generate_parameter(opir.IndexPirConfig(40, 4, 2, 2, False, "noCompression", False), o.n, o.t)
+    dbs = [[bytes(rng.randrange(256) for _ in range(4)) for _ in range(40)] for _ in range(2)]
+    sk, relin = o.keygen(8)
+    key, okeys = load_keys(g, o, sk, relin, param.evaluationKeyConfig.galoisElements)
+    server = pir.MulPirServer(param, g, [pir.MulPirServer.process(d, g, param) for d in dbs])
+    indices = [7, 33]
+    query = opir.generate_query(o, oparam, indices, sk, 77)
+    got = server.computeResponse(np.stack(query), key, indicesCount=2)
+    expected = opir.compute_response(o, query, 2, okeys, relin, [opir.process_database(o, oparam, d) for d in dbs], oparam)
+    for qi in range(2):
+        assert np.array_equal(got[qi, 0], expected[qi][0])
+        assert opir.decrypt_response(o, oparam, [[got[qi, 0]]], [indices[qi]], sk) == [dbs[qi][indices[qi]]]
+    # PirError.invalidBatchSize: 2 databases cannot serve 3 queries (PirUtil.swift:498-500)
+    three = opir.generate_query(o, opir.IndexPirParameter(40, 4, oparam.dimensions, 3), [1, 2, 3], sk, 5)
+    with pytest.raises(hecuda.HeError) as err:
+        server.computeResponse(np.stack(three), key, indicesCount=3)
+    assert "invalidBatchSize" in str(err.value)
+    # PirError.invalidDatabasePlaintextCount (MulPir.swift:352-358)
+    with pytest.raises(pir.PirError):
+        pir.MulPirServer(param, g, [pir.ProcessedDatabase(g, np.zeros((3, 16), dtype=np.uint64))])
+    # no relinearization key for a two-dimensional database
+    bare = hecuda.EvaluationKey(g, None)
+    for e, k in okeys.items():
+        bare.setGaloisKey(e, k)
+    with pytest.raises(hecuda.HeError) as err:
+        server.computeResponse(np.stack(query), bare, indicesCount=2)
+    assert "missingRelinearizationKey" in str(err.value)
+    bare.close()
+    key.close()
+    g.close()
+
+
+@pytest.mark.parametrize("n,bits,t,entries,entry_size,compression", [
+    (4096, [27, 28, 28], 17, 30000, 1, "hybridCompression"),      # EncryptionParametersConfig.defaultPir (BenchmarkMetricExtensions.swift:60-63)
+    (4096, [27, 28, 28], 17, 300, 3000, "noCompression"),         # entries larger than a plaintext: 2 chunks
+    (8192, [55, 55, 55, 55], 65537, 5000, 100, "maxCompression"),
+])
+def test_index_pir_production_sizes(n, bits, t, entries, entry_size, compression):
+    g, o = contexts(n, bits, t)
+    rng = random.Random(entries)
+    config = pir.IndexPirConfig(entries, entry_size, 2, 1, True, compression, False)
+    param = pir.MulPir.generateParameter(config, g)
+    oparam = opir.generate_parameter(opir.IndexPirConfig(entries, entry_size, 2, 1, True, compression, False), n, t)
+    database = [bytes(rng.randrange(256) for _ in range(entry_size)) for _ in range(entries)]
+    sk, relin = o.keygen(13)
+    key, okeys = load_keys(g, o, sk, relin, param.evaluationKeyConfig.galoisElements)
+    server = pir.MulPirServer(param, g, [pir.MulPirServer.process(database, g, param)])
+    index = rng.randrange(entries)
+    query = opir.generate_query(o, oparam, [index], sk, 900)
+    got = server.computeResponse(np.stack(query), key)
+    reply = [[got[0, c] for c in range(server.chunkCount)]]
+    assert opir.decrypt_response(o, oparam, reply, [index], sk) == [database[index]]
+    expected = opir.compute_response(o, query, 1, okeys, relin, [opir.process_database(o, oparam, database)], oparam)
+    for c in range(server.chunkCount):
+        assert np.array_equal(got[0, c], expected[0][c])
+    key.close()
+    g.close()
