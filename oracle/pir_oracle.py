@@ -366,7 +366,7 @@ def expand_ciphertext_for_one_step(ctx: O.Context, ct: np.ndarray, log_step: int
     count = 1 << (log2(target - 1) - log2(element - 1))
     c1, current = ct, 1
     for _ in range(count):
-        c1 = ctx.apply_galois(c1, element, galois_keys[element])[0]
+        c1 = ctx.apply_galois(c1, element, galois_keys[element], threads=1)[0]
         current = current * element % (2 * n)
     assert current == target
     difference = _sub(ctx, ct, c1, l)
@@ -420,14 +420,14 @@ def compute_response_for_one_chunk(ctx, dim0_query_eval: np.ndarray, remaining_q
         nxt = []
         for group in range(0, len(results), size):
             vector1 = np.stack(results[group:group + size])
-            product = ctx.inner_product(vector0[None], vector1[None])[0]
-            nxt.append(ctx.relinearize(product, relin_key)[0])
+            product = ctx.inner_product(vector0[None], vector1[None], threads=1)[0]
+            nxt.append(ctx.relinearize(product, relin_key, threads=1)[0])
         results = nxt
         start += size
     assert len(results) == 1
     ct = results[0]
     while ct.shape[-2] > 1:                                                  # modSwitchDownToSingle (HeScheme.swift:1481)
-        ct = ctx.mod_switch_down(ct)[0]
+        ct = ctx.mod_switch_down(ct, threads=1)[0]
     return ct
 
 
