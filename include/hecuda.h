@@ -34,6 +34,7 @@ extern "C" {
 
 typedef struct hecuda_context hecuda_context; /* Context<Bfv<UInt64>>, Context.swift:19 */
 typedef struct hecuda_evk hecuda_evk;         /* EvaluationKey<Bfv<UInt64>>, Keys.swift:66-99,222 */
+typedef struct hecuda_pnns_matrix hecuda_pnns_matrix;   /* PlaintextMatrix<Bfv<UInt64>, Eval>, .diagonal packing */
 typedef struct hecuda_pir_database hecuda_pir_database; /* ProcessedDatabase<Bfv<UInt64>>, IndexPir/IndexPirDatabase.swift */
 
 enum {
@@ -208,6 +209,31 @@ int32_t hecuda_mulpir_compute_response_device(const hecuda_context *ctx, const h
                                               const int32_t *dimensions, int32_t dimension_count, int32_t chunk_count,
                                               const uint64_t *query, int32_t query_ciphertext_count,
                                               int32_t indices_count, uint64_t *out, void *stream);
+
+/* ---- PNNS server: encrypted vector x plaintext matrix ----
+ * Device-resident PlaintextMatrix in `.diagonal(babyStepGiantStep:)` packing (PrivateNearestNeighborSearch/
+ * PlaintextMatrix.swift:417-482): nextPowerOfTwo(column_count) * ceil(row_count / N) plaintexts in the order the
+ * reference stores them, either as coefficient vectors (count x N, eval_format = 0; converted on the device like
+ * Plaintext.convertToEvalFormat, MatrixMultiplication.swift:206-208) or as count x L x N Eval plaintexts.
+ * baby_step / giant_step = BabyStepGiantStep (MatrixMultiplication.swift:26-62). */
+int32_t hecuda_pnns_matrix_create(const hecuda_context *ctx, const uint64_t *plaintexts, int32_t eval_format,
+                                  int64_t row_count, int64_t column_count, int32_t baby_step, int32_t giant_step,
+                                  hecuda_pnns_matrix **out);
+int32_t hecuda_pnns_matrix_destroy(hecuda_pnns_matrix *matrix);
+int32_t hecuda_pnns_matrix_result_count(const hecuda_pnns_matrix *matrix, int64_t *count); /* ceil(row_count / N) */
+
+/* PlaintextMatrix.mulTranspose(vector:using:) -- MatrixMultiplication.swift:131-226, for `batch` dense-row query
+ * ciphertexts (batch x 2 x L x N, Coeff) that share `evk`: babyStep-1 rotateColumns(by: -1), forward NTTs, one
+ * ct x pt inner product per (result ciphertext, giant step), rotateColumnsAndSum(by: -babyStep)
+ * (_HomomorphicEncryptionExtras/HeScheme.swift:113-134; the Galois keys for both rotations must be in `evk`,
+ * HECUDA_ERR_MISSING_KEY otherwise).  mod_switch_to_single = 1 appends Server.computeResponse's
+ * modSwitchDownToSingle (Server.swift:79-80).  out: batch x result_count x 2 x (1 or L) x N (Coeff). */
+int32_t hecuda_pnns_mul_transpose_vector(const hecuda_context *ctx, const hecuda_evk *evk, const hecuda_pnns_matrix *matrix,
+                                         const uint64_t *vectors, int64_t batch, int32_t mod_switch_to_single,
+                                         uint64_t *out);
+int32_t hecuda_pnns_mul_transpose_vector_device(const hecuda_context *ctx, const hecuda_evk *evk,
+                                                const hecuda_pnns_matrix *matrix, const uint64_t *vectors, int64_t batch,
+                                                int32_t mod_switch_to_single, uint64_t *out, void *stream);
 
 /* Bookkeeping for bench.py: number of kernel launches issued by this library in the calling process so far. */
 uint64_t hecuda_kernel_launch_count(void);

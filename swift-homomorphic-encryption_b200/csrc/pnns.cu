@@ -1,0 +1,319 @@
+// pnns.cu -- PNNS server: encrypted-vector x plaintext-matrix product on one device.
+//
+//   PlaintextMatrix.mulTranspose(vector:using:)    PrivateNearestNeighborSearch/MatrixMultiplication.swift:131-226
+//   BabyStepGiantStep                              MatrixMultiplication.swift:26-62
+//   rotateColumnsAndSum                            _HomomorphicEncryptionExtras/HeScheme.swift:113-134
+//   Server.computeResponse post-processing         PrivateNearestNeighborSearch/Server.swift:61-88
+//
+// The matrix stays in HBM in Eval format, re-ordered once so that every (result ciphertext, giant step) pair owns
+// `babyStep` consecutive plaintexts (absent ones flagged), which makes step 2 of the algorithm a single launch of the
+// streaming ct x pt inner-product kernel per query vector.  Query vectors that share an evaluation key are batched
+// through the rotation chains (babyStep - 1 rotations by -1, giantStep - 1 rotations by -babyStep).
+#include <algorithm>
+
+#include "capi_internal.hpp"
+
+using namespace hecuda;
+using namespace hecuda::api;
+
+struct hecuda_pnns_matrix {
+    const hecuda_context *owner = nullptr;
+    u64 *d_plain = nullptr;              // [result][giant][baby] x L x N, Eval
+    unsigned char *d_present = nullptr;  // [result][giant][baby]
+    int64_t row_count = 0, column_count = 0, result_count = 0;
+    int baby = 0, giant = 0, dimension = 0;
+};
+
+namespace {
+
+struct RowConsts {
+    int rows;
+    u64 p[kMaxRows];
+};
+
+// acc[item] (+)= src[item * src_stride]   over ciphertexts of 2 x rows x N
+__global__ void __launch_bounds__(256) accumulate_kernel(u64 *__restrict__ acc, const u64 *__restrict__ src,
+                                                        int64_t src_item_stride, const __grid_constant__ RowConsts c,
+                                                        int n, int add) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const int pr = blockIdx.y;
+    const int64_t ct_words = (int64_t)2 * c.rows * n;
+    const int64_t off = (int64_t)pr * n + e;
+    const u64 v = src[(int64_t)blockIdx.z * src_item_stride + off];
+    u64 *dst = acc + (int64_t)blockIdx.z * ct_words + off;
+    if (add) {
+        const u64 p = c.p[pr % c.rows];
+        const u64 s = *dst + v;
+        *dst = s >= p ? s - p : s;
+    } else {
+        *dst = v;
+    }
+}
+
+cudaError_t launch_accumulate(const Context &c, int l, u64 *acc, const u64 *src, int64_t src_item_stride, int64_t items,
+                              bool add, cudaStream_t s) {
+    RowConsts rc;
+    const NttRowMap map = c.map_q(l);
+    rc.rows = l;
+    for (int r = 0; r < l; ++r) rc.p[r] = c.slots[map.slot[r]].dev.p;
+    const int threads = c.n >= 256 ? 256 : (c.n < 32 ? 32 : (int)c.n);
+    const int64_t ct_words = (int64_t)2 * l * c.n;
+    for (int64_t done = 0; done < items;) {
+        const int64_t chunk = std::min<int64_t>(items - done, 65535);
+        dim3 grid((unsigned)((c.n + threads - 1) / threads), (unsigned)(2 * l), (unsigned)chunk);
+        ++g_kernel_launches;
+        accumulate_kernel<<<grid, threads, 0, s>>>(acc + done * ct_words, src + done * src_item_stride, src_item_stride, rc,
+                                                   (int)c.n, add ? 1 : 0);
+        done += chunk;
+    }
+    return cudaGetLastError();
+}
+
+// GaloisElement.rotatingColumns(by:degree:) (PolyRq/Galois.swift:195-212)
+unsigned rotating_columns(int step, int64_t degree) {
+    unsigned positive = (unsigned)(step < 0 ? -step : step);
+    if (step > 0) positive = (unsigned)(degree >> 1) - positive;
+    unsigned long long g = 1, base = 3, mod = 2ull * (unsigned long long)degree;
+    for (unsigned e = positive; e; e >>= 1) {
+        if (e & 1) g = g * base % mod;
+        base = base * base % mod;
+    }
+    return (unsigned)g;
+}
+
+int32_t find_key(const hecuda_evk *k, unsigned element, const u64 **key) {
+    hecuda_evk *km = const_cast<hecuda_evk *>(k);
+    std::lock_guard<std::mutex> g(km->mu);
+    auto it = km->galois.find(element);
+    if (it == km->galois.end()) return fail(HECUDA_ERR_MISSING_KEY, "missingGaloisElement: " + std::to_string(element));
+    *key = it->second;
+    return HECUDA_OK;
+}
+
+struct Tmp {
+    cudaStream_t s;
+    std::vector<void *> ptrs;
+    explicit Tmp(cudaStream_t stream) : s(stream) {}
+    ~Tmp() {
+        for (void *p : ptrs) cudaFreeAsync(p, s);
+    }
+    cudaError_t alloc(u64 **out, size_t words) {
+        cudaError_t e = cudaMallocAsync((void **)out, std::max<size_t>(words, 1) * sizeof(u64), s);
+        if (e == cudaSuccess) ptrs.push_back(*out);
+        return e;
+    }
+};
+
+int32_t mul_transpose_device(const hecuda_context *h, const hecuda_evk *k, const hecuda_pnns_matrix *m, const u64 *d_vec,
+                             int64_t batch, bool to_single, u64 *d_out, cudaStream_t s) {
+    const Context &c = *h->ctx;
+    const int L = c.L;
+    const int64_t n = c.n;
+    const size_t ct_words = (size_t)2 * L * n;
+    const int baby = m->baby, giant = m->giant;
+    const int64_t results = m->result_count;
+    const u64 *key1 = nullptr, *keyb = nullptr;
+    const unsigned e1 = n > 2 ? rotating_columns(-1, n) : 0, eb = rotating_columns(-baby, n);
+    int32_t rc;
+    if (baby > 1 && (rc = find_key(k, e1, &key1))) return rc;
+    if (giant > 1 && (rc = find_key(k, eb, &keyb))) return rc;
+    Tmp tmp(s);
+    u64 *states = nullptr, *rotated = nullptr, *ip = nullptr, *acc[2] = {nullptr, nullptr}, *scratch = nullptr, *ms = nullptr;
+    const int64_t gal_items = std::max<int64_t>(batch, batch * results);
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(h->chunk, gal_items));
+    CK(tmp.alloc(&states, ct_words * baby * batch));
+    CK(tmp.alloc(&rotated, ct_words * baby * batch));
+    CK(tmp.alloc(&ip, ct_words * results * giant * batch));
+    CK(tmp.alloc(&acc[0], ct_words * results * batch));
+    CK(tmp.alloc(&acc[1], ct_words * results * batch));
+    CK(tmp.alloc(&scratch, galois_scratch_words(c, L) * (size_t)chunk));
+    CK(tmp.alloc(&ms, ct_words * results * batch));
+    cudaError_t e;
+    // 1) v_j = theta^j(v): states[j][b]                                    (MatrixMultiplication.swift:180-189)
+    CK(cudaMemcpyAsync(states, d_vec, ct_words * batch * sizeof(u64), cudaMemcpyDeviceToDevice, s));
+    for (int j = 1; j < baby; ++j)
+        for (int64_t done = 0; done < batch; done += chunk) {
+            const int64_t items = std::min<int64_t>(chunk, batch - done);
+            if ((e = apply_galois_chunk(c, scratch, key1, states + ct_words * ((j - 1) * batch + done), L, e1,
+                                        states + ct_words * (j * batch + done), items, s)) != cudaSuccess)
+                return cuda_fail(e, "rotateColumns");
+        }
+    // convertToEvalFormat (:190-193), then [j][b] -> [b][j] so that each vector's states are consecutive
+    const NttRowMap map = c.map_q(L);
+    if ((e = launch_ntt_forward(c, map, states, states, (int64_t)baby * batch * 2 * L, s)) != cudaSuccess) return cuda_fail(e, "ntt");
+    if (batch == 1) {
+        std::swap(states, rotated);
+    } else {
+        for (int j = 0; j < baby; ++j)
+            CK(cudaMemcpy2DAsync(rotated + ct_words * j, ct_words * baby * sizeof(u64), states + ct_words * j * batch,
+                                 ct_words * sizeof(u64), ct_words * sizeof(u64), (size_t)batch, cudaMemcpyDeviceToDevice, s));
+    }
+    // 2) w_k: one inner product per (result ciphertext, giant step)                         (:197-216)
+    for (int64_t b = 0; b < batch; ++b)
+        if ((e = launch_inner_product_plain(c, rotated + ct_words * baby * b, 2, L, baby, m->d_plain, m->d_present,
+                                            ip + ct_words * results * giant * b, results * giant, s)) != cudaSuccess)
+            return cuda_fail(e, "innerProduct(ciphertexts:plaintexts:)");
+    if ((e = launch_ntt_inverse(c, map, ip, ip, batch * results * giant * 2 * L, kScalePlain, s)) != cudaSuccess)
+        return cuda_fail(e, "ntt");
+    // 3) rotateColumnsAndSum(by: -babyStep): Horner over the giant steps, all (vector, result) pairs at once (:218-226)
+    const int64_t items = batch * results;
+    int cur = 0;
+    if ((e = launch_accumulate(c, L, acc[cur], ip + ct_words * (giant - 1), (int64_t)ct_words * giant, items, false, s)) != cudaSuccess)
+        return cuda_fail(e, "sum");
+    for (int g = giant - 2; g >= 0; --g) {
+        for (int64_t done = 0; done < items; done += chunk) {
+            const int64_t part = std::min<int64_t>(chunk, items - done);
+            if ((e = apply_galois_chunk(c, scratch, keyb, acc[cur] + ct_words * done, L, eb, acc[cur ^ 1] + ct_words * done,
+                                        part, s)) != cudaSuccess)
+                return cuda_fail(e, "rotateColumns");
+        }
+        cur ^= 1;
+        if ((e = launch_accumulate(c, L, acc[cur], ip + ct_words * g, (int64_t)ct_words * giant, items, true, s)) != cudaSuccess)
+            return cuda_fail(e, "sum");
+    }
+    // Server.computeResponse: modSwitchDownToSingle (Server.swift:79-80)
+    if (!to_single || L == 1) {
+        CK(cudaMemcpyAsync(d_out, acc[cur], ct_words * items * sizeof(u64), cudaMemcpyDeviceToDevice, s));
+        return HECUDA_OK;
+    }
+    const u64 *src = acc[cur];
+    for (int l = L; l > 1; --l) {
+        u64 *dst = l == 2 ? d_out : (src == ms ? acc[cur] : ms);
+        if ((e = launch_mod_switch(c, src, l, dst, items * 2, s)) != cudaSuccess) return cuda_fail(e, "modSwitchDown");
+        src = dst;
+    }
+    return HECUDA_OK;
+}
+
+int32_t check_args(const hecuda_context *h, const hecuda_evk *k, const hecuda_pnns_matrix *m, const void *vectors,
+                   int64_t batch, const void *out) {
+    int32_t rc = check_ctx(h);
+    if (rc) return rc;
+    if (!m || m->owner != h) return fail(HECUDA_ERR_INVALID_ARGUMENT, "wrongContext: plaintext matrix belongs to another context");
+    if (!k) return fail(HECUDA_ERR_MISSING_KEY, "missingGaloisKey");
+    if (k->owner != h) return fail(HECUDA_ERR_INVALID_ARGUMENT, "invalidContext: evaluation key belongs to another context");
+    if (batch < 0 || (batch && (!vectors || !out))) return fail(HECUDA_ERR_INVALID_ARGUMENT, "invalidCiphertext: null buffer");
+    return HECUDA_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t hecuda_pnns_matrix_create(const hecuda_context *h, const uint64_t *plaintexts, int32_t eval_format,
+                                  int64_t row_count, int64_t column_count, int32_t baby_step, int32_t giant_step,
+                                  hecuda_pnns_matrix **out) {
+    int32_t rc = check_ctx(h);
+    if (rc) return rc;
+    if (!out || !plaintexts) return fail(HECUDA_ERR_INVALID_ARGUMENT, "null argument");
+    *out = nullptr;
+    const Context &c = *h->ctx;
+    const int64_t n = c.n;
+    if (row_count < 1 || column_count < 1 || column_count > n / 2)  // PnnsError.invalidMatrixDimensions (PlaintextMatrix.swift:429-431)
+        return fail(HECUDA_ERR_INVALID_ARGUMENT, "invalidMatrixDimensions");
+    int64_t dimension = 1;
+    while (dimension < column_count) dimension <<= 1;
+    if (baby_step < 1 || giant_step < 1 || baby_step < giant_step || (int64_t)baby_step * giant_step < dimension ||
+        (int64_t)baby_step * (giant_step - 1) >= dimension || baby_step >= n / 2)
+        return fail(HECUDA_ERR_INVALID_ARGUMENT, "wrongMatrixPacking: babyStep / giantStep do not cover the padded dimension");
+    const int64_t results = (row_count + n - 1) / n;  // plaintextsPerColumnCount / resultCiphertextCount
+    const int64_t count = dimension * results;       // PlaintextMatrix.plaintextCount, .diagonal (:269-273)
+    const int64_t slots = results * giant_step * baby_step;
+    const size_t row_words = (size_t)c.L * n, in_words = eval_format ? row_words : (size_t)n;
+    hecuda_pnns_matrix *m = new (std::nothrow) hecuda_pnns_matrix();
+    if (!m) return fail(HECUDA_ERR_CUDA, "out of host memory");
+    m->owner = h;
+    m->row_count = row_count;
+    m->column_count = column_count;
+    m->result_count = results;
+    m->baby = baby_step;
+    m->giant = giant_step;
+    m->dimension = (int)dimension;
+    std::vector<unsigned char> present((size_t)slots, 0);
+    u64 *d_in = nullptr;
+    cudaError_t e = cudaMalloc(&m->d_plain, row_words * slots * sizeof(u64));
+    if (e == cudaSuccess) e = cudaMemset(m->d_plain, 0, row_words * slots * sizeof(u64));
+    if (e == cudaSuccess) e = cudaMalloc(&m->d_present, (size_t)slots);
+    if (e == cudaSuccess) e = cudaMalloc(&d_in, in_words * count * sizeof(u64));
+    if (e == cudaSuccess) e = cudaMemcpy(d_in, plaintexts, in_words * count * sizeof(u64), cudaMemcpyHostToDevice);
+    // plaintext index resultCount * (j + babyStep * g) + r  ->  slot (r, g, j)      (MatrixMultiplication.swift:203-205)
+    for (int64_t r = 0; e == cudaSuccess && r < results; ++r)
+        for (int g = 0; e == cudaSuccess && g < giant_step; ++g) {
+            const int64_t terms = std::min<int64_t>(baby_step, dimension - (int64_t)baby_step * g);
+            const int64_t slot = (r * giant_step + g) * baby_step;
+            const u64 *src = d_in + in_words * (results * ((int64_t)baby_step * g) + r);
+            if (eval_format) {
+                e = cudaMemcpy2D(m->d_plain + row_words * slot, row_words * sizeof(u64), src, row_words * results * sizeof(u64),
+                                 row_words * sizeof(u64), (size_t)terms, cudaMemcpyDeviceToDevice);
+            } else {  // Plaintext.convertToEvalFormat per row (:206-208); gather the strided rows first
+                u64 *d_rows = nullptr;
+                e = cudaMalloc(&d_rows, (size_t)n * terms * sizeof(u64));
+                if (e == cudaSuccess)
+                    e = cudaMemcpy2D(d_rows, n * sizeof(u64), src, n * results * sizeof(u64), n * sizeof(u64), (size_t)terms,
+                                     cudaMemcpyDeviceToDevice);
+                if (e == cudaSuccess) e = launch_plaintext_to_eval(c, d_rows, c.L, m->d_plain + row_words * slot, terms, nullptr);
+                if (e == cudaSuccess) e = cudaStreamSynchronize(nullptr);
+                cudaFree(d_rows);
+            }
+            for (int64_t j = 0; j < terms; ++j) present[(size_t)(slot + j)] = 1;
+        }
+    if (e == cudaSuccess) e = cudaMemcpy(m->d_present, present.data(), (size_t)slots, cudaMemcpyHostToDevice);
+    cudaFree(d_in);
+    if (e != cudaSuccess) {
+        hecuda_pnns_matrix_destroy(m);
+        return cuda_fail(e, "pnns matrix upload");
+    }
+    *out = m;
+    return HECUDA_OK;
+}
+
+int32_t hecuda_pnns_matrix_destroy(hecuda_pnns_matrix *m) {
+    if (!m) return HECUDA_OK;
+    if (m->d_plain) cudaFree(m->d_plain);
+    if (m->d_present) cudaFree(m->d_present);
+    delete m;
+    return HECUDA_OK;
+}
+
+int32_t hecuda_pnns_matrix_result_count(const hecuda_pnns_matrix *m, int64_t *count) {
+    if (!m || !count) return fail(HECUDA_ERR_INVALID_ARGUMENT, "null argument");
+    *count = m->result_count;
+    return HECUDA_OK;
+}
+
+int32_t hecuda_pnns_mul_transpose_vector_device(const hecuda_context *h, const hecuda_evk *k, const hecuda_pnns_matrix *m,
+                                                const uint64_t *vectors, int64_t batch, int32_t mod_switch_to_single,
+                                                uint64_t *out, void *stream) {
+    int32_t rc = check_args(h, k, m, vectors, batch, out);
+    if (rc || batch == 0) return rc;
+    return mul_transpose_device(h, k, m, (const u64 *)vectors, batch, mod_switch_to_single != 0, (u64 *)out, (cudaStream_t)stream);
+}
+
+int32_t hecuda_pnns_mul_transpose_vector(const hecuda_context *h, const hecuda_evk *k, const hecuda_pnns_matrix *m,
+                                         const uint64_t *vectors, int64_t batch, int32_t mod_switch_to_single,
+                                         uint64_t *out) {
+    int32_t rc = check_args(h, k, m, vectors, batch, out);
+    if (rc || batch == 0) return rc;
+    WsGuard g(h);
+    if (!g.w) return fail(HECUDA_ERR_CUDA, "could not create a CUDA stream / workspace");
+    const Context &c = *h->ctx;
+    const size_t ct_words = (size_t)2 * c.L * c.n;
+    const size_t out_words = (size_t)2 * (mod_switch_to_single ? 1 : c.L) * c.n * m->result_count * batch;
+    cudaStream_t s = g.w->stream;
+    Tmp tmp(s);
+    u64 *d_in = nullptr, *d_out = nullptr;
+    CK(tmp.alloc(&d_in, ct_words * batch));
+    CK(tmp.alloc(&d_out, ct_words * m->result_count * batch));
+    CK(cudaMemcpyAsync(d_in, vectors, ct_words * batch * sizeof(u64), cudaMemcpyHostToDevice, s));
+    rc = mul_transpose_device(h, k, m, d_in, batch, mod_switch_to_single != 0, d_out, s);
+    if (rc) {
+        cudaStreamSynchronize(s);
+        return rc;
+    }
+    CK(cudaMemcpyAsync(out, d_out, out_words * sizeof(u64), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return HECUDA_OK;
+}
+
+}  // extern "C"
