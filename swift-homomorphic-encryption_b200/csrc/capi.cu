@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <new>
 #include <string>
@@ -173,17 +174,31 @@ template <class Body>
 int32_t host_pipeline(const hecuda_context *h, int64_t batch, int64_t chunk_hint, size_t scratch_words_per_item,
                       const std::vector<HostIo> &inputs, u64 *host_out, size_t out_words_per_item, Body body) {
     if (batch == 0) return HECUDA_OK;
-    WsGuard g0(h), g1(h);
-    if (!g0.w || !g1.w) return fail(HECUDA_ERR_CUDA, "could not create a CUDA stream / workspace");
-    Workspace *ws[2] = {g0.w, g1.w};
-    // at least ~8 stages so that H2D of stage k+1, the kernels of stage k and D2H of stage k-1 overlap
+    // `depth` stages in flight, each on its own stream: H2D of stage k+1.., kernels of stage k, D2H of stage k-1
+    static const int depth = [] {
+        const char *env = std::getenv("HECUDA_PIPELINE_DEPTH");
+        const int d = env ? std::atoi(env) : 3;
+        return d < 1 ? 1 : (d > 8 ? 8 : d);
+    }();
+    static const int64_t min_stages = [] {
+        const char *env = std::getenv("HECUDA_PIPELINE_STAGES");
+        const long long v = env ? std::atoll(env) : 16;
+        return (int64_t)(v < 1 ? 1 : v);
+    }();
+    std::vector<std::unique_ptr<WsGuard>> guards;
+    std::vector<Workspace *> ws;
+    for (int i = 0; i < depth; ++i) {
+        guards.emplace_back(new WsGuard(h));
+        if (!guards.back()->w) return fail(HECUDA_ERR_CUDA, "could not create a CUDA stream / workspace");
+        ws.push_back(guards.back()->w);
+    }
     int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(chunk_hint, batch));
-    if (batch >= 64) chunk = std::min<int64_t>(chunk, std::max<int64_t>(16, (batch + 7) / 8));
+    if (batch >= 64) chunk = std::min<int64_t>(chunk, std::max<int64_t>(16, (batch + min_stages - 1) / min_stages));
     int k = 0;
     for (int64_t done = 0; done < batch; done += chunk, ++k) {
-        Workspace &w = *ws[k & 1];
+        Workspace &w = *ws[k % depth];
         const int64_t items = std::min<int64_t>(chunk, batch - done);
-        // Work on one workspace is ordered by its stream; buffers only ever grow (first two iterations).
+        // Work on one workspace is ordered by its stream; buffers only ever grow (first `depth` iterations).
         // slot 0 = kernel scratch, slot 4 = staged inputs (back to back), slot 5 = staged output
         size_t in_words = 0;
         for (const HostIo &io : inputs) in_words += io.words_per_item * (size_t)items;
@@ -204,8 +219,7 @@ int32_t host_pipeline(const hecuda_context *h, int64_t batch, int64_t chunk_hint
         CK(cudaMemcpyAsync(host_out + out_words_per_item * (size_t)done, w.buf[5],
                            out_words_per_item * (size_t)items * sizeof(u64), cudaMemcpyDeviceToHost, w.stream));
     }
-    CK(cudaStreamSynchronize(ws[0]->stream));
-    CK(cudaStreamSynchronize(ws[1]->stream));
+    for (Workspace *w : ws) CK(cudaStreamSynchronize(w->stream));
     return HECUDA_OK;
 }
 

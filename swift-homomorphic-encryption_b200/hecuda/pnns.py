@@ -164,12 +164,21 @@ class SimdEncoder:
 class PlaintextMatrix:
     """PlaintextMatrix<Bfv<UInt64>, Eval> in .diagonal packing, resident in HBM."""
 
-    def __init__(self, context: Context, dimensions: MatrixDimensions, values, babyStepGiantStep: BabyStepGiantStep = None):
+    def __init__(self, context: Context, dimensions: MatrixDimensions, values, babyStepGiantStep: BabyStepGiantStep = None,
+                 plaintexts=None, evalFormat: bool = False):
+        """values: the matrix in row-major order (packed here), or plaintexts: the already packed diagonal plaintexts
+        (count x N coefficient rows, or count x L x N with evalFormat) as PlaintextMatrix.init(dimensions:packing:plaintexts:)."""
         self.context, self.dimensions = context, dimensions
         self.babyStepGiantStep = babyStepGiantStep or BabyStepGiantStep.forVectorDimension(dimensions.columnCount)
-        rows = PlaintextMatrix.diagonalPlaintexts(context, dimensions, self.babyStepGiantStep, values)
+        if plaintexts is None:
+            rows = PlaintextMatrix.diagonalPlaintexts(context, dimensions, self.babyStepGiantStep, values)
+        else:
+            rows = _host(plaintexts)
+            expected = self.babyStepGiantStep.vectorDimension * -(-dimensions.rowCount // context.degree)
+            if rows.size != expected * context.degree * (context.L if evalFormat else 1):
+                raise PnnsError(f"wrongPlaintextCount(got: {rows.size // context.degree}, expected: {expected})")
         h = C.c_void_p()
-        _check(load_library().hecuda_pnns_matrix_create(context._h, _ptr(rows), 0, dimensions.rowCount, dimensions.columnCount,
+        _check(load_library().hecuda_pnns_matrix_create(context._h, _ptr(rows), 1 if evalFormat else 0, dimensions.rowCount, dimensions.columnCount,
                                                        self.babyStepGiantStep.babyStep, self.babyStepGiantStep.giantStep,
                                                        C.byref(h)))
         self._h = h
