@@ -235,6 +235,24 @@ int32_t hecuda_pnns_mul_transpose_vector_device(const hecuda_context *ctx, const
                                                 const hecuda_pnns_matrix *matrix, const uint64_t *vectors, int64_t batch,
                                                 int32_t mod_switch_to_single, uint64_t *out, void *stream);
 
+/* PlaintextMatrix.mulTranspose(matrix:using:) -- MatrixMultiplication.swift:236-298: for every row of the dense-row
+ * packed query CiphertextMatrix (ciphertexts: ciphertext_count x 2 x L x N, Coeff) CiphertextMatrix.extractDenseRow
+ * (CiphertextMatrix.swift:245-352), the vector product above, then the dense-column packing of the result columns
+ * (rotateColumnsAndSum(by: rowCount) + swapRowsAndAdd, _HomomorphicEncryptionExtras/HeScheme.swift:113-151).
+ * The caller passes what extractDenseRow derives from the matrix shape for each query row -- the index of the
+ * ciphertext holding it, the SIMD-encoded plaintext mask (query_row_count x N coefficients, :300-320), the number of
+ * replication rotations (:331-336) -- with column_step = columnCount.nextPowerOfTwo, and the single rotation steps
+ * rotateColumnsMultiStep(by: rowCount) resolves to with the configured keys (GaloisElement._planMultiStep,
+ * PolyRq/Galois.swift:272-319; the reference iterates that plan in unspecified Dictionary order).  For
+ * query_row_count == 1 the row descriptors are ignored (extractDenseRow is the identity).
+ * out: *out_count ciphertexts of 2 x (1 or L) x N, the `.denseColumn` CiphertextMatrix; out_capacity in ciphertexts. */
+int32_t hecuda_pnns_mul_transpose_matrix(const hecuda_context *ctx, const hecuda_evk *evk, const hecuda_pnns_matrix *matrix,
+                                         const uint64_t *ciphertexts, int32_t ciphertext_count, int32_t query_row_count,
+                                         const int32_t *row_ciphertext_index, const uint64_t *row_masks,
+                                         const int32_t *row_rotate_count, int32_t column_step, const int32_t *pack_rotations,
+                                         int32_t pack_rotation_count, int32_t mod_switch_to_single, uint64_t *out,
+                                         int64_t out_capacity, int64_t *out_count);
+
 /* Bookkeeping for bench.py: number of kernel launches issued by this library in the calling process so far. */
 uint64_t hecuda_kernel_launch_count(void);
 

@@ -32,11 +32,17 @@ struct RowConsts {
 };
 
 // acc[item] (+)= src[item * src_stride]   over ciphertexts of 2 x rows x N
+// modes (optional, per item): 0 = leave acc alone, 1 = copy, 2 = add; without modes every item uses `add`
 __global__ void __launch_bounds__(256) accumulate_kernel(u64 *__restrict__ acc, const u64 *__restrict__ src,
                                                         int64_t src_item_stride, const __grid_constant__ RowConsts c,
-                                                        int n, int add) {
+                                                        int n, int add, const signed char *__restrict__ modes) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n) return;
+    if (modes) {
+        const int mode = modes[blockIdx.z];
+        if (mode == 0) return;
+        add = mode == 2;
+    }
     const int pr = blockIdx.y;
     const int64_t ct_words = (int64_t)2 * c.rows * n;
     const int64_t off = (int64_t)pr * n + e;
@@ -52,7 +58,7 @@ __global__ void __launch_bounds__(256) accumulate_kernel(u64 *__restrict__ acc, 
 }
 
 cudaError_t launch_accumulate(const Context &c, int l, u64 *acc, const u64 *src, int64_t src_item_stride, int64_t items,
-                              bool add, cudaStream_t s) {
+                              bool add, cudaStream_t s, const signed char *modes = nullptr) {
     RowConsts rc;
     const NttRowMap map = c.map_q(l);
     rc.rows = l;
@@ -64,7 +70,7 @@ cudaError_t launch_accumulate(const Context &c, int l, u64 *acc, const u64 *src,
         dim3 grid((unsigned)((c.n + threads - 1) / threads), (unsigned)(2 * l), (unsigned)chunk);
         ++g_kernel_launches;
         accumulate_kernel<<<grid, threads, 0, s>>>(acc + done * ct_words, src + done * src_item_stride, src_item_stride, rc,
-                                                   (int)c.n, add ? 1 : 0);
+                                                   (int)c.n, add ? 1 : 0, modes ? modes + done : nullptr);
         done += chunk;
     }
     return cudaGetLastError();
@@ -183,6 +189,166 @@ int32_t mul_transpose_device(const hecuda_context *h, const hecuda_evk *k, const
         if ((e = launch_mod_switch(c, src, l, dst, items * 2, s)) != cudaSuccess) return cuda_fail(e, "modSwitchDown");
         src = dst;
     }
+    return HECUDA_OK;
+}
+
+// batched applyGalois over `items` contiguous ciphertexts, chunked by the scratch size
+int32_t galois_batch(const Context &c, u64 *scratch, int64_t chunk, const u64 *key, unsigned element, const u64 *in, u64 *out,
+                     int64_t items, cudaStream_t s) {
+    const size_t ct_words = (size_t)2 * c.L * c.n;
+    for (int64_t done = 0; done < items; done += chunk) {
+        const int64_t part = std::min<int64_t>(chunk, items - done);
+        cudaError_t e = apply_galois_chunk(c, scratch, key, in + ct_words * done, c.L, element, out + ct_words * done, part, s);
+        if (e != cudaSuccess) return cuda_fail(e, "applyGalois");
+    }
+    return HECUDA_OK;
+}
+
+struct MatrixQuery {
+    int32_t rows;                      // ciphertextMatrix.rowCount
+    const int32_t *ciphertext_index;   // per row
+    const u64 *host_masks;             // rows x N coefficient plaintexts
+    const int32_t *rotate_count;       // per row
+    int32_t column_step;
+    const int32_t *pack_rotations;     // single rotations composing rotateColumnsMultiStep(by: matrix.rowCount)
+    int32_t pack_rotation_count;
+};
+
+// PlaintextMatrix.mulTranspose(matrix:using:) (MatrixMultiplication.swift:236-298) with CiphertextMatrix.extractDenseRow
+// (CiphertextMatrix.swift:245-352) batched over all query rows.
+int32_t mul_transpose_matrix_device(const hecuda_context *h, const hecuda_evk *k, const hecuda_pnns_matrix *m,
+                                    const u64 *d_cts, const MatrixQuery &q, bool to_single, u64 *d_out, int64_t out_capacity,
+                                    int64_t *out_count, cudaStream_t s) {
+    const Context &c = *h->ctx;
+    const int L = c.L;
+    const int64_t n = c.n, R = q.rows, results = m->result_count;
+    const size_t ct_words = (size_t)2 * L * n;
+    const int64_t per_simd_row = (n / 2) / m->row_count;
+    const int64_t S = per_simd_row, G = S > 0 ? (R + S - 1) / S : 0;
+    const int64_t outputs = S > 0 ? (G + 1) / 2 : R * results;
+    *out_count = outputs;
+    if (outputs > out_capacity) return fail(HECUDA_ERR_INVALID_ARGUMENT, "output buffer too small: needs " + std::to_string(outputs) + " ciphertexts");
+    Tmp tmp(s);
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(h->chunk, R));
+    u64 *x = nullptr, *y = nullptr, *z = nullptr, *scratch = nullptr, *inner = nullptr, *masks = nullptr, *mask_eval = nullptr;
+    signed char *d_modes = nullptr;
+    CK(tmp.alloc(&x, ct_words * R));
+    CK(tmp.alloc(&y, ct_words * R));
+    CK(tmp.alloc(&z, ct_words * R));
+    CK(tmp.alloc(&scratch, galois_scratch_words(c, L) * (size_t)chunk));
+    CK(tmp.alloc(&inner, ct_words * R * results));
+    const NttRowMap map = c.map_q(L);
+    const unsigned swap_element = (unsigned)(2 * n - 1);
+    cudaError_t e;
+    int32_t rc;
+    // mode tables: replication steps (extractDenseRow) then packing positions
+    int32_t max_rot = 0;
+    for (int64_t r = 0; r < R && R > 1; ++r) max_rot = std::max(max_rot, q.rotate_count[r]);
+    std::vector<signed char> modes;
+    for (int32_t t = 1; t <= max_rot; ++t)
+        for (int64_t r = 0; r < R; ++r) modes.push_back(t <= q.rotate_count[r] ? 2 : 0);
+    const size_t pack_modes_offset = modes.size();
+    const int64_t top = std::min<int64_t>(S, R) - 1;  // the longest group: positions above it hold nothing
+    for (int64_t p = top; p >= 0 && S > 0; --p)
+        for (int64_t g = 0; g < G; ++g) {
+            const int64_t size = std::min<int64_t>(S, R - g * S);
+            modes.push_back(p == size - 1 ? 1 : (p < size - 1 ? 2 : 0));
+        }
+    CK(cudaMallocAsync((void **)&d_modes, std::max<size_t>(modes.size(), 8), s));
+    tmp.ptrs.push_back(d_modes);
+    if (!modes.empty()) CK(cudaMemcpyAsync(d_modes, modes.data(), modes.size(), cudaMemcpyHostToDevice, s));
+    if (R == 1) {  // extractDenseRow is the identity for a single row (:263-265)
+        CK(cudaMemcpyAsync(y, d_cts, ct_words * sizeof(u64), cudaMemcpyDeviceToDevice, s));
+    } else {
+        const u64 *key_step = nullptr, *key_swap = nullptr;
+        const unsigned step_element = rotating_columns(q.column_step, n);
+        if (max_rot > 0 && (rc = find_key(k, step_element, &key_step))) return rc;
+        if ((rc = find_key(k, swap_element, &key_swap))) return rc;
+        CK(tmp.alloc(&masks, (size_t)n * R));
+        CK(tmp.alloc(&mask_eval, (size_t)L * n * R));
+        CK(cudaMemcpyAsync(masks, q.host_masks, (size_t)n * R * sizeof(u64), cudaMemcpyHostToDevice, s));
+        for (int64_t r = 0; r < R; ++r)
+            CK(cudaMemcpyAsync(x + ct_words * r, d_cts + ct_words * q.ciphertext_index[r], ct_words * sizeof(u64),
+                               cudaMemcpyDeviceToDevice, s));
+        // ciphertextEval *= plaintextMask (:322-324)
+        if ((e = launch_ntt_forward(c, map, x, x, R * 2 * L, s)) != cudaSuccess) return cuda_fail(e, "ntt");
+        if ((e = launch_plaintext_to_eval(c, masks, L, mask_eval, R, s)) != cudaSuccess) return cuda_fail(e, "plaintext_to_eval");
+        for (int64_t r = 0; r < R; ++r)
+            if ((e = launch_inner_product_plain(c, x + ct_words * r, 2, L, 1, mask_eval + (size_t)L * n * r, nullptr,
+                                                y + ct_words * r, 1, s)) != cudaSuccess)
+                return cuda_fail(e, "multiply by mask");
+        if ((e = launch_ntt_inverse(c, map, y, y, R * 2 * L, kScalePlain, s)) != cudaSuccess) return cuda_fail(e, "ntt");
+        // replicate across one SIMD row: rotate the copy, add where the row still needs copies (:331-336)
+        const u64 *copy = y;
+        u64 *ping[2] = {x, z};
+        for (int32_t t = 1; t <= max_rot; ++t) {
+            u64 *dst = ping[t & 1];
+            if ((rc = galois_batch(c, scratch, chunk, key_step, step_element, copy, dst, R, s))) return rc;
+            copy = dst;
+            if ((e = launch_accumulate(c, L, y, copy, (int64_t)ct_words, R, true, s, d_modes + (size_t)(t - 1) * R)) != cudaSuccess)
+                return cuda_fail(e, "sum");
+        }
+        // both SIMD rows: ciphertext += swapRows(ciphertext) (:342-345)
+        if ((rc = galois_batch(c, scratch, chunk, key_swap, swap_element, y, x, R, s))) return rc;
+        if ((e = launch_accumulate(c, L, y, x, (int64_t)ct_words, R, true, s)) != cudaSuccess) return cuda_fail(e, "sum");
+    }
+    if ((rc = mul_transpose_device(h, k, m, y, R, false, inner, s))) return rc;
+    u64 *final_cts = inner;
+    if (S > 0) {  // pack the result columns (:262-283); here results == 1
+        u64 *acc[2] = {x, y};
+        int cur = 0;
+        CK(cudaMemsetAsync(acc[0], 0, ct_words * G * sizeof(u64), s));
+        std::vector<std::pair<unsigned, const u64 *>> rotations;
+        for (int32_t i = 0; i < q.pack_rotation_count; ++i) {
+            const unsigned element = rotating_columns(q.pack_rotations[i], n);
+            const u64 *key = nullptr;
+            if (S > 1 && (rc = find_key(k, element, &key))) return rc;
+            rotations.push_back({element, key});
+        }
+        const int64_t gchunk = std::max<int64_t>(1, std::min<int64_t>(chunk, G));
+        size_t mode_row = pack_modes_offset;
+        for (int64_t p = top; p >= 0; --p, mode_row += (size_t)G) {
+            if (p < top)
+                for (const auto &rot : rotations) {  // rotateColumnsMultiStep(by: dimensions.rowCount)
+                    if ((rc = galois_batch(c, scratch, gchunk, rot.second, rot.first, acc[cur], acc[cur ^ 1], G, s))) return rc;
+                    cur ^= 1;
+                }
+            if ((e = launch_accumulate(c, L, acc[cur], inner + ct_words * p, (int64_t)ct_words * S, G, true, s,
+                                       d_modes + mode_row)) != cudaSuccess)
+                return cuda_fail(e, "sum");
+        }
+        // swapRowsAndAdd(swapping: packedRows[1], addingTo: packedRows[0]) for every full pair (:277-281)
+        const int64_t pairs = G / 2;
+        u64 *packed = z;
+        if ((e = launch_accumulate(c, L, packed, acc[cur], (int64_t)ct_words * 2, outputs, false, s)) != cudaSuccess)
+            return cuda_fail(e, "copy");
+        if (pairs > 0) {
+            const u64 *key_swap = nullptr;
+            if ((rc = find_key(k, swap_element, &key_swap))) return rc;
+            u64 *odd = acc[cur ^ 1];
+            if ((e = launch_accumulate(c, L, odd, acc[cur] + ct_words, (int64_t)ct_words * 2, pairs, false, s)) != cudaSuccess)
+                return cuda_fail(e, "copy");
+            if ((rc = galois_batch(c, scratch, std::max<int64_t>(1, std::min<int64_t>(chunk, pairs)), key_swap, swap_element, odd,
+                                   inner, pairs, s)))
+                return rc;
+            if ((e = launch_accumulate(c, L, packed, inner, (int64_t)ct_words, pairs, true, s)) != cudaSuccess) return cuda_fail(e, "sum");
+        }
+        final_cts = packed;
+    }
+    if (!to_single || L == 1) {
+        CK(cudaMemcpyAsync(d_out, final_cts, ct_words * outputs * sizeof(u64), cudaMemcpyDeviceToDevice, s));
+    } else {
+        const u64 *src = final_cts;
+        u64 *spare[2] = {final_cts == x ? y : x, final_cts == z ? y : z};
+        int which = 0;
+        for (int l = L; l > 1; --l) {
+            u64 *dst = l == 2 ? d_out : spare[which];
+            which ^= 1;
+            if ((e = launch_mod_switch(c, src, l, dst, outputs * 2, s)) != cudaSuccess) return cuda_fail(e, "modSwitchDown");
+            src = dst;
+        }
+    }
+    CK(cudaStreamSynchronize(s));  // `modes` and the caller's descriptor arrays are host temporaries
     return HECUDA_OK;
 }
 
@@ -311,6 +477,47 @@ int32_t hecuda_pnns_mul_transpose_vector(const hecuda_context *h, const hecuda_e
         cudaStreamSynchronize(s);
         return rc;
     }
+    CK(cudaMemcpyAsync(out, d_out, out_words * sizeof(u64), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return HECUDA_OK;
+}
+
+int32_t hecuda_pnns_mul_transpose_matrix(const hecuda_context *h, const hecuda_evk *k, const hecuda_pnns_matrix *m,
+                                         const uint64_t *ciphertexts, int32_t ciphertext_count, int32_t query_row_count,
+                                         const int32_t *row_ciphertext_index, const uint64_t *row_masks,
+                                         const int32_t *row_rotate_count, int32_t column_step, const int32_t *pack_rotations,
+                                         int32_t pack_rotation_count, int32_t mod_switch_to_single, uint64_t *out,
+                                         int64_t out_capacity, int64_t *out_count) {
+    int32_t rc = check_args(h, k, m, ciphertexts, ciphertext_count, out);
+    if (rc) return rc;
+    if (!out_count || ciphertext_count < 1 || query_row_count < 1 || pack_rotation_count < 0 ||
+        (pack_rotation_count && !pack_rotations))
+        return fail(HECUDA_ERR_INVALID_ARGUMENT, "invalidMatrixDimensions");
+    const Context &c = *h->ctx;
+    if (query_row_count > 1) {
+        if (!row_ciphertext_index || !row_masks || !row_rotate_count) return fail(HECUDA_ERR_INVALID_ARGUMENT, "null row descriptors");
+        if (column_step < 1 || column_step > c.n / 2) return fail(HECUDA_ERR_INVALID_ARGUMENT, "invalidMatrixDimensions");
+        for (int32_t r = 0; r < query_row_count; ++r)
+            if (row_ciphertext_index[r] < 0 || row_ciphertext_index[r] >= ciphertext_count || row_rotate_count[r] < 0)
+                return fail(HECUDA_ERR_INVALID_ARGUMENT, "wrongCiphertextCount: row descriptor out of range");
+    }
+    WsGuard g(h);
+    if (!g.w) return fail(HECUDA_ERR_CUDA, "could not create a CUDA stream / workspace");
+    const size_t ct_words = (size_t)2 * c.L * c.n;
+    cudaStream_t s = g.w->stream;
+    Tmp tmp(s);
+    u64 *d_in = nullptr, *d_out = nullptr;
+    CK(tmp.alloc(&d_in, ct_words * ciphertext_count));
+    CK(tmp.alloc(&d_out, ct_words * (size_t)std::max<int64_t>(out_capacity, 1)));
+    CK(cudaMemcpyAsync(d_in, ciphertexts, ct_words * ciphertext_count * sizeof(u64), cudaMemcpyHostToDevice, s));
+    const MatrixQuery q{query_row_count, row_ciphertext_index, (const u64 *)row_masks, row_rotate_count, column_step,
+                        pack_rotations, pack_rotation_count};
+    rc = mul_transpose_matrix_device(h, k, m, d_in, q, mod_switch_to_single != 0, d_out, out_capacity, out_count, s);
+    if (rc) {
+        cudaStreamSynchronize(s);
+        return rc;
+    }
+    const size_t out_words = (size_t)2 * (mod_switch_to_single ? 1 : c.L) * c.n * (size_t)*out_count;
     CK(cudaMemcpyAsync(out, d_out, out_words * sizeof(u64), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     return HECUDA_OK;

@@ -83,6 +83,9 @@ SYMBOLS = {
     "hecuda_pnns_matrix_result_count": (C.c_int32, [_VP, C.POINTER(C.c_int64)]),
     "hecuda_pnns_mul_transpose_vector": (C.c_int32, [_VP, _VP, _VP, _VP, C.c_int64, C.c_int32, _VP]),
     "hecuda_pnns_mul_transpose_vector_device": (C.c_int32, [_VP, _VP, _VP, _VP, C.c_int64, C.c_int32, _VP, _VP]),
+    "hecuda_pnns_mul_transpose_matrix": (C.c_int32, [_VP, _VP, _VP, _VP, C.c_int32, C.c_int32, C.POINTER(C.c_int32), _VP,
+                                                     C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.c_int32,
+                                                     _VP, C.c_int64, C.POINTER(C.c_int64)]),
     "hecuda_kernel_launch_count": (C.c_uint64, []),
 }
 
@@ -213,6 +216,7 @@ class EvaluationKey:
 
     def __init__(self, context: Context, relinearizationKey=None):
         self.context = context
+        self.galoisElements = []  # EvaluationKey.config.galoisElements
         h = C.c_void_p()
         if relinearizationKey is None:
             _check(load_library().hecuda_evk_create_empty(context._h, C.byref(h)))
@@ -230,6 +234,8 @@ class EvaluationKey:
         if k.size != self.context.L * 2 * (self.context.L + 1) * self.context.degree:
             raise HeError(-1, "invalidContext: Galois key must be L x 2 x (L+1) x N")
         _check(load_library().hecuda_evk_set_galois_key(self._h, element, _ptr(k)))
+        if element not in self.galoisElements:
+            self.galoisElements.append(int(element))
 
     def deviceBuffer(self):
         p, n = C.c_void_p(), C.c_uint64(0)

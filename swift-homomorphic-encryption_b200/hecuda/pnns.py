@@ -8,8 +8,8 @@
 
 The diagonal packing and the SIMD encoding of the database are host work in the reference too (offline
 preprocessing); conversion to Eval format, the rotations, inner products and modulus switching run on the device.
-`mulTranspose(matrix:)` (extractDenseRow + repacking of several result columns per ciphertext) is not mirrored yet:
-pass one dense-row ciphertext per query vector.
+`mulTransposeMatrix` runs the whole mulTranspose(matrix:) -- extractDenseRow, products, dense-column packing -- in one
+C-ABI call; the shape logic extractDenseRow derives per row (mask, ciphertext index, replication count) is computed here.
 """
 from __future__ import annotations
 
@@ -76,6 +76,100 @@ class GaloisElement:
     @staticmethod
     def swappingRows(degree: int) -> int:
         return 2 * degree - 1
+
+    @staticmethod
+    def stepsFor(elements, degree: int) -> dict:
+        """GaloisElement.stepsFor (PolyRq/Galois.swift:239-258): 3^k mod 2N  <->  rotation by N/2 - k."""
+        wanted, out, g = set(int(e) for e in elements), {}, 1
+        for k in range(degree // 2 + 1):
+            if g in wanted and g not in out:
+                out[g] = degree // 2 - k
+            g = g * 3 % (2 * degree)
+        return {e: out.get(e) for e in wanted}
+
+    @staticmethod
+    def planMultiStep(supportedSteps, step: int, degree: int):
+        """GaloisElement._planMultiStep (PolyRq/Galois.swift:272-319): greedy decomposition, by steps or by their
+        complements to N/2, whichever needs fewer rotations."""
+        if abs(step) >= degree:
+            raise HeError(-1, f"invalidRotationStep(step: {step}, degree: {degree})")
+        if step in supportedSteps:
+            return {step: 1}
+
+        def greedy(order, weight):
+            left, plan = weight(step), {}
+            for s in order:
+                w = weight(s)
+                if left // w:
+                    plan[s] = plan.get(s, 0) + left // w
+                left %= w
+            return plan if left == 0 else None
+
+        down = sorted(supportedSteps, reverse=True)
+        forward = greedy(down, lambda s: s)
+        backward = greedy(down[::-1], lambda s: (degree >> 1) - s)
+        if forward is None or backward is None:
+            return forward if backward is None else backward
+        return forward if sum(forward.values()) <= sum(backward.values()) else backward
+
+    @staticmethod
+    def rotationSequence(galoisElements, step: int, degree: int) -> list:
+        """The single rotations of rotateColumnsMultiStep(by: step) (_HomomorphicEncryptionExtras/HeScheme.swift:65-104),
+        larger steps first (the reference walks a Dictionary, i.e. in unspecified order)."""
+        if step == 0:
+            return []
+        if GaloisElement.rotatingColumns(step, degree) in galoisElements:
+            return [step]
+        steps = [s for s in GaloisElement.stepsFor(galoisElements, degree).values() if s is not None]
+        plan = GaloisElement.planMultiStep(steps, step + degree // 2 if step < 0 else step, degree)
+        if plan is None:
+            raise HeError(-1, f"invalidRotationStep(step: {step}, degree: {degree})")
+        return [s for s in sorted(plan, reverse=True) for _ in range(plan[s])]
+
+
+class CiphertextMatrix:
+    """The shape logic of CiphertextMatrix in `.denseRow` packing (CiphertextMatrix.swift, PlaintextMatrix.swift:262-268)."""
+
+    @staticmethod
+    def ciphertextCount(degree: int, dimensions: MatrixDimensions) -> int:
+        per_ciphertext = 2 * ((degree // 2) // _next_power_of_two(dimensions.columnCount))
+        return -(-dimensions.rowCount // per_ciphertext)
+
+    @staticmethod
+    def denseRowExtraction(degree: int, dimensions: MatrixDimensions, ciphertextCount: int, rowIndex: int):
+        """What extractDenseRow derives for one row (CiphertextMatrix.swift:254-320): (index of the ciphertext holding
+        the row, SIMD values of the plaintext mask, number of rotate-and-add replication steps)."""
+        columns = degree // 2
+        width = _next_power_of_two(dimensions.columnCount)
+        per_ciphertext = 2 * (columns // width)
+        ciphertext_index = rowIndex // per_ciphertext
+        is_last = ciphertext_index == ciphertextCount - 1
+
+        def slots(row):
+            lo = (row % per_ciphertext) * width
+            hi = lo + width
+            if lo <= columns < hi:                       # the batch would straddle the two SIMD rows
+                lo, hi = columns, columns + width
+            elif hi > columns:                           # second SIMD row: skip the first row's padding
+                lo, hi = lo + columns % width, hi + columns % width
+            if is_last:                                  # the last ciphertext repeats its rows to the end
+                hi = -(-hi // columns) * columns
+            return lo, hi
+
+        lo, hi = slots(rowIndex)
+        after = rowIndex + 1
+        while after < dimensions.rowCount and slots(after)[1] == hi:
+            after += 1
+        before = max(rowIndex - 1, 0)
+        while before > 0 and slots(before)[1] == hi:
+            before -= 1
+        period = _next_power_of_two(width * (after - before))
+        mask = [0] * lo
+        copies = 0
+        while len(mask) < hi:
+            mask += [1] * width + [0] * (period - width)
+            copies += 1
+        return ciphertext_index, mask[:degree], columns // (copies * width) - 1
 
 
 class SimdEncoder:
@@ -224,6 +318,45 @@ class PlaintextMatrix:
         _check(load_library().hecuda_pnns_mul_transpose_vector(ctx._h, evaluationKey._h, self._h, _ptr(cts), batch,
                                                               1 if modSwitchDownToSingle else 0, _ptr(out)))
         return out
+
+    def mulTransposeMatrix(self, ciphertexts, queryDimensions: MatrixDimensions, evaluationKey: EvaluationKey,
+                           modSwitchDownToSingle: bool = False) -> np.ndarray:
+        """mulTranspose(matrix:using:) (MatrixMultiplication.swift:236-298): `ciphertexts` is the dense-row packed query
+        CiphertextMatrix (count, 2, L, N); returns the dense-column packed result ciphertexts (count', 2, L or 1, N)."""
+        ctx = self.context
+        n = ctx.degree
+        if queryDimensions.columnCount != self.dimensions.columnCount:
+            raise PnnsError(f"invalidMatrixDimensions(rowCount: {queryDimensions.rowCount}, columnCount: {queryDimensions.columnCount})")
+        cts = _host(ciphertexts)
+        words = 2 * ctx.L * n
+        count = cts.size // words
+        rows = queryDimensions.rowCount
+        expected = CiphertextMatrix.ciphertextCount(n, queryDimensions)
+        if cts.size % words or count != expected:
+            raise PnnsError(f"wrongCiphertextCount(got: {count}, expected: {expected})")
+        index = (C.c_int32 * rows)()
+        rotate = (C.c_int32 * rows)()
+        masks = np.zeros((rows, n), dtype=np.uint64)
+        step = _next_power_of_two(queryDimensions.columnCount)
+        if rows > 1:
+            encoder = SimdEncoder(n, ctx.plaintextModulus)
+            values = np.zeros((rows, n), dtype=np.uint64)
+            for r in range(rows):
+                index[r], mask, rotate[r] = CiphertextMatrix.denseRowExtraction(n, queryDimensions, count, r)
+                values[r, : len(mask)] = mask
+            masks = encoder.encode(values)
+        per_simd_row = (n // 2) // self.dimensions.rowCount
+        sequence = []
+        if per_simd_row > 1 and rows > 1:
+            sequence = GaloisElement.rotationSequence(evaluationKey.galoisElements, self.dimensions.rowCount, n)
+        plan = (C.c_int32 * max(1, len(sequence)))(*sequence)
+        capacity = rows * self.resultCiphertextCount
+        out = np.empty((capacity, 2, 1 if modSwitchDownToSingle else ctx.L, n), dtype=np.uint64)
+        produced = C.c_int64(0)
+        _check(load_library().hecuda_pnns_mul_transpose_matrix(
+            ctx._h, evaluationKey._h, self._h, _ptr(cts), count, rows, index, _ptr(masks), rotate, step, plan, len(sequence),
+            1 if modSwitchDownToSingle else 0, _ptr(out), capacity, C.byref(produced)))
+        return out[: produced.value]
 
     def close(self):
         if getattr(self, "_h", None) is not None:

@@ -79,3 +79,45 @@ def test_pnns_errors():
     device_matrix.close()
     key.close()
     g.close()
+
+
+@pytest.mark.parametrize("n,t,bits,rows,cols,queries", [
+    (16, 1153, (55, 52, 62, 58), 4, 2, 3), (16, 1153, (55, 52, 62, 58), 3, 4, 5), (16, 1153, (55, 52, 62, 58), 8, 4, 2),
+    (16, 1153, (55, 52, 62, 58), 20, 3, 3), (64, 65537, (55, 55, 55), 10, 8, 9), (64, 65537, (55, 55, 55), 40, 12, 4),
+    (64, 65537, (55, 55, 55), 5, 32, 3), (64, 65537, (55, 55, 55), 10, 8, 1),
+    (4096, 65537, (36, 36, 37), 300, 128, 20), (8192, 65537, (55, 55, 55, 55), 5000, 384, 3)])
+def test_mul_transpose_matrix_matches_oracle_and_decrypts(n, t, bits, rows, cols, queries):
+    """PlaintextMatrix.mulTranspose(matrix:using:) incl. extractDenseRow and dense-column packing."""
+    moduli = orc.generate_primes(list(bits), False, n)
+    g, o = hecuda.Context(n, moduli, t), orc.Context(n, moduli, t)
+    rng = random.Random(rows * 131 + cols * 7 + queries)
+    matrix = [[rng.randrange(t) for _ in range(cols)] for _ in range(rows)]
+    query = [[rng.randrange(t) for _ in range(cols)] for _ in range(queries)]
+    sk, _ = o.keygen(9, relin=False)
+    key, okeys = hecuda.EvaluationKey(g, None), {}
+    for i, e in enumerate(opn.matrix_evaluation_key_elements(n, rows, cols, queries)):
+        okeys[e] = o.galois_keygen(70 + i, sk, e)
+        key.setGaloisKey(e, okeys[e])
+    flat = [v for row in matrix for v in row]
+    device_matrix = pnns.PlaintextMatrix(g, pnns.MatrixDimensions(rows, cols), flat)
+    bsgs = opn.BabyStepGiantStep.for_dimension(cols)
+    oplain = opn.diagonal_plaintexts(o, rows, cols, bsgs, flat)
+    query_plain = opn.dense_row_plaintexts(o, queries, cols, [v for row in query for v in row])
+    cts = [o.encrypt(200 + i, sk, p) for i, p in enumerate(query_plain)]
+    got = device_matrix.mulTransposeMatrix(np.stack(cts), pnns.MatrixDimensions(queries, cols), key)
+    expected = opn.mul_transpose_matrix(o, oplain, rows, cols, bsgs, cts, queries, okeys)
+    assert got.shape[0] == len(expected)
+    for i, ct in enumerate(expected):
+        assert np.array_equal(got[i], ct), i
+    single = device_matrix.mulTransposeMatrix(np.stack(cts), pnns.MatrixDimensions(queries, cols), key, modSwitchDownToSingle=True)
+    decoded = []
+    for i, ct in enumerate(expected):
+        assert np.array_equal(single[i], opn.mod_switch_down_to_single(o, ct)), i
+        decoded.append(opn.decode_simd(o, o.decrypt(sk, single[i])).tolist())
+    assert opn.unpack_dense_column(o, decoded, rows, queries) == \
+        [sum(a * b for a, b in zip(matrix[r], query[c])) % t for r in range(rows) for c in range(queries)]
+    with pytest.raises(pnns.PnnsError):   # PnnsError.invalidMatrixDimensions: column counts differ (:242-244)
+        device_matrix.mulTransposeMatrix(np.stack(cts), pnns.MatrixDimensions(queries, cols + 1), key)
+    device_matrix.close()
+    key.close()
+    g.close()

@@ -51,3 +51,24 @@ def test_diagonal_packing_and_dense_row_match_oracle(n, t, rows, cols):
         assert np.array_equal(got[i], row), i
     vector = values[:cols]
     assert np.array_equal(pnns.denseRowVector(host, vector), opn.dense_row_vector(octx, vector))
+
+
+def test_dense_row_extraction_and_rotation_plans_match_oracle():
+    rng = random.Random(5)
+    for _ in range(400):
+        n = rng.choice([16, 64, 4096])
+        cols = rng.randint(1, n // 2)
+        rows = rng.randint(2, 3 * n)
+        dims = pnns.MatrixDimensions(rows, cols)
+        count = pnns.CiphertextMatrix.ciphertextCount(n, dims)
+        for r in {0, rows - 1, rng.randrange(rows), rng.randrange(rows)}:
+            index, mask, rotations = pnns.CiphertextMatrix.denseRowExtraction(n, dims, count, r)
+            expected = opn.dense_row_extraction(n, rows, cols, count, r)
+            assert (index, mask, rotations) == (expected.ciphertext_index, expected.mask, expected.rotate_count)
+    for n in (16, 64, 8192):
+        elements = [orc.galois_element_rotating_columns(s, n) for s in (1, -1, 4)] + [2 * n - 1]
+        assert pnns.GaloisElement.stepsFor(elements, n) == opn.steps_for(elements, n)
+        for step in range(1, min(n // 2, 40)):
+            assert pnns.GaloisElement.rotationSequence(elements, step, n) == opn.rotation_sequence(elements, step, n)
+    assert pnns.GaloisElement.planMultiStep([1, 16, 256], 33, 8192) == {16: 2, 1: 1}
+    assert pnns.GaloisElement.planMultiStep([2, 4], 3, 64) is None
