@@ -339,7 +339,9 @@ int32_t mul_transpose_matrix_device(const hecuda_context *h, const hecuda_evk *k
         CK(cudaMemcpyAsync(d_out, final_cts, ct_words * outputs * sizeof(u64), cudaMemcpyDeviceToDevice, s));
     } else {
         const u64 *src = final_cts;
-        u64 *spare[2] = {final_cts == x ? y : x, final_cts == z ? y : z};
+        u64 *spare[2] = {nullptr, nullptr};  // sized for the outputs (more than R ciphertexts when rowCount > N)
+        CK(tmp.alloc(&spare[0], ct_words * outputs));
+        CK(tmp.alloc(&spare[1], ct_words * outputs));
         int which = 0;
         for (int l = L; l > 1; --l) {
             u64 *dst = l == 2 ? d_out : spare[which];
