@@ -253,6 +253,23 @@ int32_t hecuda_pnns_mul_transpose_matrix(const hecuda_context *ctx, const hecuda
                                          int32_t pack_rotation_count, int32_t mod_switch_to_single, uint64_t *out,
                                          int64_t out_capacity, int64_t *out_count);
 
+/* ---- wire format of RNS polynomials ----
+ * PolyRq.serialize(skipLSBs:) / PolyRq.load(from:skipLSBs:) -- PolyRq/PolyRq+Serialize.swift:28-84 over
+ * CoefficientPacking.coefficientsToBytes / bytesToCoefficients (CoefficientPacking.swift:59-217): row i is a big-endian
+ * bit stream of N fields of ceil(log2 q_i) - skip_lsbs bits padded to a byte, rows concatenated;
+ * hecuda_poly_serialized_byte_count = PolyContext.serializationByteCount.  in / out: poly_count x row_count x N words
+ * under `base`; serialized: poly_count x byte_count bytes.  Loading sets the skipped low bits to zero, as the reference. */
+int32_t hecuda_poly_serialized_byte_count(const hecuda_context *ctx, int32_t base, int32_t row_count, int32_t skip_lsbs,
+                                          uint64_t *bytes);
+int32_t hecuda_poly_serialize(const hecuda_context *ctx, int32_t base, const uint64_t *in, int32_t skip_lsbs,
+                              uint8_t *serialized, int32_t row_count, int64_t poly_count);
+int32_t hecuda_poly_load(const hecuda_context *ctx, int32_t base, const uint8_t *serialized, int32_t skip_lsbs, uint64_t *out,
+                         int32_t row_count, int64_t poly_count);
+int32_t hecuda_poly_serialize_device(const hecuda_context *ctx, int32_t base, const uint64_t *in, int32_t skip_lsbs,
+                                     uint8_t *serialized, int32_t row_count, int64_t poly_count, void *stream);
+int32_t hecuda_poly_load_device(const hecuda_context *ctx, int32_t base, const uint8_t *serialized, int32_t skip_lsbs,
+                                uint64_t *out, int32_t row_count, int64_t poly_count, void *stream);
+
 /* Bookkeeping for bench.py: number of kernel launches issued by this library in the calling process so far. */
 uint64_t hecuda_kernel_launch_count(void);
 

@@ -473,3 +473,28 @@ def decrypt_response(ctx, param: IndexPirParameter, response: list, indices: lis
             entry = entry[width:][:size]
         out.append(entry)
     return out
+
+
+# ------------------------------------------------------------------------------------------------ PolyRq wire format
+def serialization_byte_count(n: int, moduli, skip_lsbs: int = 0) -> int:
+    """PolyContext.serializationByteCount (PolyRq+Serialize.swift:86-96)."""
+    return sum(dividing_ceil(n * (ceil_log2(int(q)) - skip_lsbs), 8) for q in moduli)
+
+
+def serialize_poly(n: int, moduli, data, skip_lsbs: int = 0) -> bytes:
+    """PolyRq.serialize(skipLSBs:) (PolyRq+Serialize.swift:67-84): rows packed at ceilLog2(q_i) bits, concatenated."""
+    rows = np.asarray(data, dtype=np.uint64).reshape(len(moduli), n)
+    return b"".join(coefficients_to_bytes(rows[i], ceil_log2(int(q)), skip_lsbs) for i, q in enumerate(moduli))
+
+
+def load_poly(n: int, moduli, buffer: bytes, skip_lsbs: int = 0) -> np.ndarray:
+    """PolyRq.load(from:skipLSBs:) (PolyRq+Serialize.swift:28-61)."""
+    if len(buffer) != serialization_byte_count(n, moduli, skip_lsbs):
+        raise ValueError("serializedBufferSizeMismatch")
+    out, offset = np.zeros((len(moduli), n), dtype=np.uint64), 0
+    for i, q in enumerate(moduli):
+        bits = ceil_log2(int(q))
+        count = dividing_ceil(n * (bits - skip_lsbs), 8)
+        out[i] = bytes_to_coefficients(buffer[offset:offset + count], bits, decode=True, skip_lsbs=skip_lsbs)[:n]
+        offset += count
+    return out

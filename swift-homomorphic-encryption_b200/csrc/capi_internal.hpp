@@ -105,6 +105,7 @@ struct WsGuard {
 };
 
 int32_t check_ctx(const hecuda_context *h);
+bool make_map(const Context &c, int32_t base, int32_t rows, NttRowMap &map, std::string &err);
 
 // scratch words needed per ciphertext pair / ciphertext / group
 size_t multiply_scratch_words(const Context &c);

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <string>
 
 #include "context.hpp"
 
@@ -64,6 +65,15 @@ cudaError_t launch_inner_product_plain(const Context &ctx, const u64 *cts, int n
                                        const unsigned char *present, u64 *out, int64_t out_count, cudaStream_t stream);
 cudaError_t launch_plaintext_to_eval(const Context &ctx, const u64 *plain, int l, u64 *out, int64_t count,
                                      cudaStream_t stream);
+
+// ---- wire format (codec.cu): PolyRq.serialize / load, PolyRq+Serialize.swift:28-84
+struct CodecConsts;
+bool codec_consts(const Context &ctx, const NttRowMap &map, int skip, CodecConsts &c, std::string &err);
+long long serialized_poly_bytes(const CodecConsts &c);
+cudaError_t launch_poly_load(const Context &ctx, const CodecConsts &c, int skip, const unsigned char *bytes, u64 *out,
+                             int64_t polys, cudaStream_t stream);
+cudaError_t launch_poly_serialize(const Context &ctx, const CodecConsts &c, int skip, const u64 *in, unsigned char *bytes,
+                                  int64_t polys, cudaStream_t stream);
 
 // divideAndRoundQLast over polys x l x N -> polys x (l-1) x N
 cudaError_t launch_mod_switch(const Context &ctx, const u64 *in, int l, u64 *out, int64_t polys, cudaStream_t stream);

@@ -86,6 +86,11 @@ SYMBOLS = {
     "hecuda_pnns_mul_transpose_matrix": (C.c_int32, [_VP, _VP, _VP, _VP, C.c_int32, C.c_int32, C.POINTER(C.c_int32), _VP,
                                                      C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.c_int32,
                                                      _VP, C.c_int64, C.POINTER(C.c_int64)]),
+    "hecuda_poly_serialized_byte_count": (C.c_int32, [_VP, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_uint64)]),
+    "hecuda_poly_serialize": (C.c_int32, [_VP, C.c_int32, _VP, C.c_int32, _VP, C.c_int32, C.c_int64]),
+    "hecuda_poly_load": (C.c_int32, [_VP, C.c_int32, _VP, C.c_int32, _VP, C.c_int32, C.c_int64]),
+    "hecuda_poly_serialize_device": (C.c_int32, [_VP, C.c_int32, _VP, C.c_int32, _VP, C.c_int32, C.c_int64, _VP]),
+    "hecuda_poly_load_device": (C.c_int32, [_VP, C.c_int32, _VP, C.c_int32, _VP, C.c_int32, C.c_int64, _VP]),
     "hecuda_kernel_launch_count": (C.c_uint64, []),
 }
 
@@ -369,6 +374,36 @@ class Bfv:
         l = moduliCount or context.L
         out = np.empty((d.shape[0], l, context.degree), dtype=np.uint64)
         _check(load_library().hecuda_plaintext_to_eval(context._h, _ptr(d), l, _ptr(out), d.shape[0]))
+        return out
+
+    @staticmethod
+    def serializationByteCount(context: Context, rowCount: int, skipLSBs: int = 0, base: int = BASE_Q) -> int:
+        """PolyContext.serializationByteCount(skipLSBs:) (PolyRq+Serialize.swift:86-96)."""
+        n = C.c_uint64(0)
+        _check(load_library().hecuda_poly_serialized_byte_count(context._h, base, rowCount, skipLSBs, C.byref(n)))
+        return n.value
+
+    @staticmethod
+    def serialize(context: Context, polys, skipLSBs: int = 0, base: int = BASE_Q) -> np.ndarray:
+        """PolyRq.serialize(skipLSBs:) for polys of shape (..., rows, N) -> uint8 array (count, byteCount)."""
+        x = _host(polys)
+        rows = x.shape[-2]
+        count = x.size // (rows * context.degree)
+        size = Bfv.serializationByteCount(context, rows, skipLSBs, base)
+        out = np.empty((count, size), dtype=np.uint8)
+        _check(load_library().hecuda_poly_serialize(context._h, base, _ptr(x), skipLSBs, out.ctypes.data_as(C.c_void_p), rows, count))
+        return out
+
+    @staticmethod
+    def load(context: Context, serialized, rowCount: int, skipLSBs: int = 0, base: int = BASE_Q) -> np.ndarray:
+        """PolyRq.load(from:skipLSBs:): uint8 (count, byteCount) -> (count, rows, N) uint64."""
+        b = np.ascontiguousarray(np.asarray(serialized, dtype=np.uint8))
+        size = Bfv.serializationByteCount(context, rowCount, skipLSBs, base)
+        if b.size % size:
+            raise HeError(-1, f"serializedBufferSizeMismatch(actual: {b.size}, expected: a multiple of {size})")
+        count = b.size // size
+        out = np.empty((count, rowCount, context.degree), dtype=np.uint64)
+        _check(load_library().hecuda_poly_load(context._h, base, b.ctypes.data_as(C.c_void_p), skipLSBs, _ptr(out), rowCount, count))
         return out
 
     @staticmethod

@@ -195,3 +195,19 @@ def test_index_pir_end_to_end(cfg, encoding_entry_size):
         assert all(ct.shape == (2, 1, ctx.n) for r in response for ct in r)
         entries = pir.decrypt_response(ctx, param, response, indices, sk)
         assert entries == [database[i] for i in indices]
+
+
+# ------------------------------------------------------------------------------------------------------ wire format
+@pytest.mark.parametrize("poly,moduli,skip,expected", [
+    ([1, 2, 3, 4, 6, 7, 8, 9], [521, 541], 0, [1, 2, 3, 4, 6, 7, 8, 9]),
+    ([1, 2, 3, 4], [521], 1, [0, 2, 2, 4]),
+    ([1, 21, 302, 417], [521], 2, [0, 20, 300, 416]),
+])
+def test_poly_serialize_roundtrip_kats(poly, moduli, skip, expected):
+    """PolyRq+SerializeTests.roundtripKAT (PolyRq+SerializeTests.swift:61-104)."""
+    n = len(poly) // len(moduli)
+    data = pir.serialize_poly(n, moduli, poly, skip)
+    assert len(data) == pir.serialization_byte_count(n, moduli, skip)
+    assert pir.load_poly(n, moduli, data, skip).reshape(-1).tolist() == expected
+    with pytest.raises(ValueError):   # serializationErrOnWrongBuffer (:21-37)
+        pir.load_poly(n, moduli, data + b"\0", skip)
