@@ -126,6 +126,9 @@ int32_t hecuda_bfv_mod_switch_down_device(const hecuda_context *ctx, const uint6
  * Bfv+Keys.swift:42-49), same L x 2 x K x N Eval layout as the relinearization key.  Use hecuda_evk_create_empty for
  * an evaluation key that holds Galois keys only. */
 int32_t hecuda_evk_set_galois_key(hecuda_evk *evk, uint32_t element, const uint64_t *key);
+/* Device buffer of the key for `element` (allocated if absent), for multi-GPU setups that fill it with a collective
+ * the way hecuda_evk_device_buffer does for the relinearization key. */
+int32_t hecuda_evk_galois_device_buffer(hecuda_evk *evk, uint32_t element, void **device_ptr, uint64_t *bytes);
 /* Bfv.applyGalois(ciphertext:element:using:) -- Bfv/Bfv.swift:174-198 (rotateColumns / swapRows call this with
  * GaloisElement.rotatingColumns / swappingRows, HeScheme.swift:1463-1478).  ct, out: batch x 2 x l x N (Coeff). */
 int32_t hecuda_bfv_apply_galois(const hecuda_context *ctx, const hecuda_evk *evk, const uint64_t *ct,

@@ -612,6 +612,23 @@ int32_t hecuda_evk_set_galois_key(hecuda_evk *k, uint32_t element, const uint64_
     return HECUDA_OK;
 }
 
+int32_t hecuda_evk_galois_device_buffer(hecuda_evk *k, uint32_t element, void **device_ptr, uint64_t *bytes) {
+    if (!k || !device_ptr || !bytes) return fail(HECUDA_ERR_INVALID_ARGUMENT, "null argument");
+    int32_t rc = check_ctx(k->owner);
+    if (rc) return rc;
+    if (!valid_galois_element(element, k->owner->ctx->n)) return fail(HECUDA_ERR_INVALID_ARGUMENT, "invalid Galois element");
+    std::lock_guard<std::mutex> g(k->mu);
+    auto it = k->galois.find(element);
+    if (it == k->galois.end()) {  // the caller fills it (e.g. ncclBroadcast from the rank that holds the key)
+        u64 *d = nullptr;
+        CK(cudaMalloc(&d, k->words * sizeof(u64)));
+        it = k->galois.emplace(element, d).first;
+    }
+    *device_ptr = it->second;
+    *bytes = k->words * sizeof(u64);
+    return HECUDA_OK;
+}
+
 static int32_t check_galois(const hecuda_context *h, const hecuda_evk *k, const uint64_t *ct, int32_t l, uint32_t element,
                             uint64_t *out, int64_t batch, const u64 **key) {
     int32_t rc = check_ctx(h);

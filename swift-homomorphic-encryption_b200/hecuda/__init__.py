@@ -58,6 +58,7 @@ SYMBOLS = {
     "hecuda_bfv_mod_switch_down": (C.c_int32, [_VP, _VP, C.c_int32, C.c_int32, _VP, C.c_int64]),
     "hecuda_bfv_mod_switch_down_device": (C.c_int32, [_VP, _VP, C.c_int32, C.c_int32, _VP, C.c_int64, _VP]),
     "hecuda_evk_set_galois_key": (C.c_int32, [_VP, C.c_uint32, _VP]),
+    "hecuda_evk_galois_device_buffer": (C.c_int32, [_VP, C.c_uint32, C.POINTER(_VP), C.POINTER(C.c_uint64)]),
     "hecuda_bfv_apply_galois": (C.c_int32, [_VP, _VP, _VP, C.c_int32, C.c_uint32, _VP, C.c_int64]),
     "hecuda_bfv_apply_galois_device": (C.c_int32, [_VP, _VP, _VP, C.c_int32, C.c_uint32, _VP, C.c_int64, _VP]),
     "hecuda_poly_apply_galois": (C.c_int32, [_VP, C.c_int32, C.c_int32, _VP, _VP, C.c_int32, C.c_int64, C.c_uint32]),
@@ -245,6 +246,14 @@ class EvaluationKey:
     def deviceBuffer(self):
         p, n = C.c_void_p(), C.c_uint64(0)
         _check(load_library().hecuda_evk_device_buffer(self._h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def galoisDeviceBuffer(self, element: int):
+        """Device buffer of GaloisKey.keys[element], allocated if absent (filled by a collective on non-source ranks)."""
+        p, n = C.c_void_p(), C.c_uint64(0)
+        _check(load_library().hecuda_evk_galois_device_buffer(self._h, element, C.byref(p), C.byref(n)))
+        if element not in self.galoisElements:
+            self.galoisElements.append(int(element))
         return p.value, n.value
 
     def close(self):

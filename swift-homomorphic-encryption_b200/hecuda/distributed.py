@@ -33,11 +33,13 @@ class _CudaView:
         self.__cuda_array_interface__ = {"shape": (nbytes // 8,), "typestr": "<i8", "data": (ptr, False), "version": 2}
 
 
-def broadcast_evaluation_key(context, relin_key_host, src: int = 0):
+def broadcast_evaluation_key(context, relin_key_host, src: int = 0, galois_keys_host=None, galois_elements=None):
     """Creates the EvaluationKey on every rank; the key material comes from rank `src`.
 
     GPU ranks: the key is uploaded on `src` and broadcast device-to-device into each rank's key buffer (NCCL).
-    Returns a hecuda.EvaluationKey.  `relin_key_host` is only read on rank `src` (others may pass None)."""
+    Returns a hecuda.EvaluationKey.  `relin_key_host` and `galois_keys_host` ({element: key}) are only read on rank
+    `src` (others may pass None); `galois_elements` (the EvaluationKeyConfig, known to every rank) lists the Galois
+    keys to broadcast.  has_relin: pass relin_key_host=None on every rank for a Galois-only key."""
     import torch
     import torch.distributed as dist
 
@@ -45,15 +47,25 @@ def broadcast_evaluation_key(context, relin_key_host, src: int = 0):
 
     rank = dist.get_rank() if dist.is_initialized() else 0
     world = dist.get_world_size() if dist.is_initialized() else 1
+    elements = list(galois_elements if galois_elements is not None else (galois_keys_host or {}))
     if world == 1:
-        return hecuda.EvaluationKey(context, relin_key_host)
+        key = hecuda.EvaluationKey(context, relin_key_host)
+        for e in elements:
+            key.setGaloisKey(e, galois_keys_host[e])
+        return key
+    flag = torch.tensor([1 if (rank == src and relin_key_host is not None) else 0], device=torch.device("cuda", torch.cuda.current_device()))
+    dist.broadcast(flag, src=src)
+    has_relin = bool(flag.item())
     if rank == src:
         key = hecuda.EvaluationKey(context, relin_key_host)
+        for e in elements:
+            key.setGaloisKey(e, galois_keys_host[e])
     else:
-        key = hecuda.EvaluationKey(context, None)  # empty device buffer of the right size
-    ptr, nbytes = key.deviceBuffer()
-    view = torch.as_tensor(_CudaView(ptr, nbytes), device=torch.device("cuda", torch.cuda.current_device()))
-    dist.broadcast(view, src=src)
+        key = hecuda.EvaluationKey(context, None)  # empty device buffers of the right size
+    device = torch.device("cuda", torch.cuda.current_device())
+    buffers = ([key.deviceBuffer()] if has_relin else []) + [key.galoisDeviceBuffer(e) for e in elements]
+    for ptr, nbytes in buffers:
+        dist.broadcast(torch.as_tensor(_CudaView(ptr, nbytes), device=device), src=src)
     torch.cuda.synchronize()
     return key
 

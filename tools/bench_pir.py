@@ -40,9 +40,16 @@ def main():
     entry_size = int(sys.argv[2]) if len(sys.argv) > 2 else 64
     threads = int(sys.argv[3]) if len(sys.argv) > 3 else 8
     n, t = 4096, 17
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:  # one database shard per GPU (KeywordDatabase shards are independent): weak scaling, no data-path collective
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        hecuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        dist.init_process_group("nccl")
     ctx = hecuda.Context(n, PIR_MODULI, t)
     L = ctx.L
-    rng = np.random.default_rng(3)
+    rng = np.random.default_rng(3 + rank)
     config = pir.IndexPirConfig(entries, entry_size, 2, 1, True, "hybridCompression", False)
     param = pir.MulPir.generateParameter(config, ctx)
     chunk_count = -(-param.encodedEntrySize // pir.bytesPerPlaintext(ctx))
@@ -53,9 +60,16 @@ def main():
     process_s = time.time() - t0
     del rows
     server = pir.MulPirServer(param, ctx, [db])
-    key = hecuda.EvaluationKey(ctx, uniform(rng, PIR_MODULI, (L, 2), n))
-    for e in param.evaluationKeyConfig.galoisElements:
-        key.setGaloisKey(e, uniform(rng, PIR_MODULI, (L, 2), n))
+    elements = param.evaluationKeyConfig.galoisElements
+    if world > 1:  # the client's evaluation key reaches every shard by one NCCL broadcast
+        from hecuda.distributed import broadcast_evaluation_key
+        relin = uniform(rng, PIR_MODULI, (L, 2), n) if rank == 0 else None
+        gal = {e: uniform(rng, PIR_MODULI, (L, 2), n) for e in elements} if rank == 0 else None
+        key = broadcast_evaluation_key(ctx, relin, 0, gal, elements)
+    else:
+        key = hecuda.EvaluationKey(ctx, uniform(rng, PIR_MODULI, (L, 2), n))
+        for e in elements:
+            key.setGaloisKey(e, uniform(rng, PIR_MODULI, (L, 2), n))
     query_cts = -(-param.expandedQueryCount // n)
     query = uniform(rng, PIR_MODULI[:L], (query_cts, 2), n)
 
@@ -75,13 +89,22 @@ def main():
         for _ in range(per_thread):
             one()
     pool = [threading.Thread(target=worker) for _ in range(threads)]
+    if world > 1:
+        dist.barrier()
     t0 = time.perf_counter()
     for th in pool:
         th.start()
     for th in pool:
         th.join()
     concurrent_s = time.perf_counter() - t0
-    qps = threads * per_thread / concurrent_s
+    if world > 1:
+        worst = torch.tensor([concurrent_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+        concurrent_s = float(worst.item())
+    qps = world * threads * per_thread / concurrent_s
+    if rank != 0:
+        dist.destroy_process_group()
+        return
 
     db_bytes = count * L * n * 8
     out = {
@@ -89,11 +112,14 @@ def main():
         "config": {"workload": f"N={n}, q=27/28/28 bit, t={t}, entries={entries} x {entry_size} B, dims={param.dimensions}, "
                                f"chunks={chunk_count}, galois={param.evaluationKeyConfig.galoisElements}"},
         "database_plaintexts": count, "database_gb": round(db_bytes / 1e9, 3), "database_upload_s": round(process_s, 2),
-        "latency_ms": round(latency_ms, 3), "threads": threads, "value": round(qps, 1), "unit": "queries/s",
+        "latency_ms": round(latency_ms, 3), "threads": threads, "n_gpus": world, "scaling": "weak (one shard per GPU)",
+        "value": round(qps, 1), "unit": "queries/s",
         "db_scan_gbs_at_value": round(qps * db_bytes / 1e9, 1),
         "gpu_launches": hecuda.kernel_launch_count(),
     }
-    if os.environ.get("PIR_CPU", "1") == "1":
+    if world > 1:
+        dist.destroy_process_group()
+    if os.environ.get("PIR_CPU", "1") == "1" and world == 1:
         from oracle import oracle as orc
         from oracle import pir_oracle as opir
         o = orc.Context(n, PIR_MODULI, t)
