@@ -84,10 +84,17 @@ def main():
         one()
     latency_ms = (time.perf_counter() - t0) / reps * 1e3
 
-    per_thread = 10
-    def worker():
-        for _ in range(per_thread):
+    per_thread = 30
+    def worker(count=per_thread):
+        for _ in range(count):
             one()
+    # warm the per-thread streams and the stream-ordered memory pool at this concurrency (first use of a stream grows
+    # the pool, which synchronises the device) -- a server keeps them warm
+    pool = [threading.Thread(target=worker, args=(5,)) for _ in range(threads)]
+    for th in pool:
+        th.start()
+    for th in pool:
+        th.join()
     pool = [threading.Thread(target=worker) for _ in range(threads)]
     if world > 1:
         dist.barrier()
