@@ -273,6 +273,16 @@ int32_t hecuda_poly_serialize_device(const hecuda_context *ctx, int32_t base, co
 int32_t hecuda_poly_load_device(const hecuda_context *ctx, int32_t base, const uint8_t *serialized, int32_t skip_lsbs,
                                 uint64_t *out, int32_t row_count, int64_t poly_count, void *stream);
 
+/* Bfv.decryptCoeff -- Bfv/Bfv+Decrypt.swift:21-41 (dotProduct(ciphertext:with:) :188-204) with RnsTool.scaleAndRound
+ * (RnsTool.swift:272-302).  secret_key: SecretKey.poly, (L+1) x N in Eval format (only its first moduli_count rows are
+ * read); ciphertexts: batch x poly_count x moduli_count x N (Coeff, poly_count 2 or 3, any level); scaling_factor =
+ * correctionFactor^-1 mod t (1 for BFV ciphertexts produced here).  plaintexts: batch x N coefficients in [0, t).
+ * Client-side operation: provided so that responses can be checked where they are produced; the key copy on the device
+ * is zeroized before it is freed. */
+int32_t hecuda_bfv_decrypt(const hecuda_context *ctx, const uint64_t *secret_key, const uint64_t *ciphertexts,
+                           int32_t poly_count, int32_t moduli_count, uint64_t scaling_factor, uint64_t *plaintexts,
+                           int64_t batch);
+
 /* Bookkeeping for bench.py: number of kernel launches issued by this library in the calling process so far. */
 uint64_t hecuda_kernel_launch_count(void);
 

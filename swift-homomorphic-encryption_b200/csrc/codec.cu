@@ -7,6 +7,7 @@
 // bits to a whole byte; the rows follow each other.  Unpacking on the device lets query ciphertexts cross PCIe at
 // ceil(log2 q) bits per coefficient instead of 64, and responses leave the same way.
 #include <algorithm>
+#include <cstdint>
 
 #include "kernels.cuh"
 #include "modarith.cuh"
@@ -103,16 +104,52 @@ cudaError_t launch_poly_load(const Context &ctx, const CodecConsts &c, int skip,
     return cudaGetLastError();
 }
 
+// coefficients -> bytes, 8 output bytes per thread (rows whose byte count and offset are multiples of 8: N >= 64)
+__global__ void __launch_bounds__(256) poly_serialize_words_kernel(const u64 *__restrict__ in, unsigned char *__restrict__ bytes,
+                                                                  const __grid_constant__ CodecConsts c, int n, int skip) {
+    const int row = blockIdx.y;
+    const int64_t poly = blockIdx.z;
+    const long long row_words = (c.byte_offset[row + 1] - c.byte_offset[row]) >> 3;
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= row_words) return;
+    const int w = c.width[row];
+    const u64 mask = w >= 64 ? ~0ull : ((1ull << w) - 1);
+    const u64 *src = in + (poly * c.rows + row) * n;
+    const long long lo_bit = 64 * j, hi_bit = lo_bit + 64;
+    u64 value = 0;  // big-endian bit stream: stream bit lo_bit is the MSB of `value`
+    for (long long coeff = lo_bit / w; coeff < n && coeff * w < hi_bit; ++coeff) {
+        const long long begin = coeff * w, end = begin + w;
+        const long long lo = begin > lo_bit ? begin : lo_bit, hi = end < hi_bit ? end : hi_bit;
+        const int bits = (int)(hi - lo);
+        const u64 v = (src[coeff] >> skip) & mask;
+        const u64 field = (v >> (end - hi)) & (bits >= 64 ? ~0ull : ((1ull << bits) - 1));
+        value |= bits >= 64 ? field : field << (hi_bit - hi);
+    }
+    // store most significant byte first
+    const u64 swapped = __byte_perm((unsigned)(value >> 32), 0, 0x0123) | ((u64)__byte_perm((unsigned)value, 0, 0x0123) << 32);
+    *reinterpret_cast<u64 *>(bytes + poly * c.byte_offset[c.rows] + c.byte_offset[row] + 8 * j) = swapped;
+}
+
 cudaError_t launch_poly_serialize(const Context &ctx, const CodecConsts &c, int skip, const u64 *in, unsigned char *bytes,
                                   int64_t polys, cudaStream_t stream) {
     long long widest = 0;
-    for (int r = 0; r < c.rows; ++r) widest = std::max(widest, c.byte_offset[r + 1] - c.byte_offset[r]);
+    bool words = (reinterpret_cast<uintptr_t>(bytes) & 7) == 0 && (c.byte_offset[c.rows] & 7) == 0;
+    for (int r = 0; r < c.rows; ++r) {
+        widest = std::max(widest, c.byte_offset[r + 1] - c.byte_offset[r]);
+        words = words && (c.byte_offset[r] & 7) == 0 && (c.byte_offset[r + 1] & 7) == 0;
+    }
     for (int64_t done = 0; done < polys;) {
         const int64_t chunk = (polys - done) > 65535 ? 65535 : (polys - done);
-        dim3 grid((unsigned)((widest + 255) / 256), (unsigned)c.rows, (unsigned)chunk);
         ++g_kernel_launches;
-        poly_serialize_kernel<<<grid, 256, 0, stream>>>(in + done * c.rows * ctx.n, bytes + done * c.byte_offset[c.rows], c,
-                                                        (int)ctx.n, skip);
+        if (words) {
+            dim3 grid((unsigned)((widest / 8 + 255) / 256), (unsigned)c.rows, (unsigned)chunk);
+            poly_serialize_words_kernel<<<grid, 256, 0, stream>>>(in + done * c.rows * ctx.n, bytes + done * c.byte_offset[c.rows],
+                                                                  c, (int)ctx.n, skip);
+        } else {
+            dim3 grid((unsigned)((widest + 255) / 256), (unsigned)c.rows, (unsigned)chunk);
+            poly_serialize_kernel<<<grid, 256, 0, stream>>>(in + done * c.rows * ctx.n, bytes + done * c.byte_offset[c.rows], c,
+                                                            (int)ctx.n, skip);
+        }
         done += chunk;
     }
     return cudaGetLastError();

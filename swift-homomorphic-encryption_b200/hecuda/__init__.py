@@ -92,6 +92,7 @@ SYMBOLS = {
     "hecuda_poly_load": (C.c_int32, [_VP, C.c_int32, _VP, C.c_int32, _VP, C.c_int32, C.c_int64]),
     "hecuda_poly_serialize_device": (C.c_int32, [_VP, C.c_int32, _VP, C.c_int32, _VP, C.c_int32, C.c_int64, _VP]),
     "hecuda_poly_load_device": (C.c_int32, [_VP, C.c_int32, _VP, C.c_int32, _VP, C.c_int32, C.c_int64, _VP]),
+    "hecuda_bfv_decrypt": (C.c_int32, [_VP, _VP, _VP, C.c_int32, C.c_int32, C.c_uint64, _VP, C.c_int64]),
     "hecuda_kernel_launch_count": (C.c_uint64, []),
 }
 
@@ -383,6 +384,21 @@ class Bfv:
         l = moduliCount or context.L
         out = np.empty((d.shape[0], l, context.degree), dtype=np.uint64)
         _check(load_library().hecuda_plaintext_to_eval(context._h, _ptr(d), l, _ptr(out), d.shape[0]))
+        return out
+
+    @staticmethod
+    def decrypt(context: Context, ciphertexts, secretKey, scalingFactor: int = 1) -> np.ndarray:
+        """Bfv.decryptCoeff (Bfv+Decrypt.swift:21-41): (batch, polys, l, N) Coeff ciphertexts -> (batch, N) coefficients < t.
+        secretKey: SecretKey.poly, (L+1, N) in Eval format."""
+        cts = _host(ciphertexts)
+        if cts.ndim == 3:
+            cts = cts[None]
+        batch, polys, l, n = cts.shape
+        sk = _host(secretKey)
+        if sk.size < l * n:
+            raise HeError(-1, "invalidContext: secret key has too few rows")
+        out = np.empty((batch, n), dtype=np.uint64)
+        _check(load_library().hecuda_bfv_decrypt(context._h, _ptr(sk), _ptr(cts), polys, l, scalingFactor, _ptr(out), batch))
         return out
 
     @staticmethod
