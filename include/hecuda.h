@@ -256,6 +256,31 @@ int32_t hecuda_pnns_mul_transpose_matrix(const hecuda_context *ctx, const hecuda
                                          int32_t pack_rotation_count, int32_t mod_switch_to_single, uint64_t *out,
                                          int64_t out_capacity, int64_t *out_count);
 
+/* ---- coefficient-wise PolyRq arithmetic ----
+ * PolyRq += / -= (PolyRq/PolyRq.swift:147-174), *= in Eval format (:184-204, Modulus.multiplyMod Modulus.swift:89-94),
+ * negation (negateMod, ModularArithmetic/Scalar.swift:167-175) and *= [T] with one reduced scalar per RNS row
+ * (:232-245).  In place on lhs / data: poly_count x row_count x N under `base`; results canonical in [0, q_i).
+ * Ciphertext += Ciphertext, Ciphertext -= Ciphertext, Ciphertext *= Plaintext (Eval) are these on the polys. */
+int32_t hecuda_poly_add(const hecuda_context *ctx, int32_t base, uint64_t *lhs, const uint64_t *rhs, int32_t row_count,
+                        int64_t poly_count);
+int32_t hecuda_poly_sub(const hecuda_context *ctx, int32_t base, uint64_t *lhs, const uint64_t *rhs, int32_t row_count,
+                        int64_t poly_count);
+int32_t hecuda_poly_mul(const hecuda_context *ctx, int32_t base, uint64_t *lhs, const uint64_t *rhs, int32_t row_count,
+                        int64_t poly_count);
+int32_t hecuda_poly_neg(const hecuda_context *ctx, int32_t base, uint64_t *data, int32_t row_count, int64_t poly_count);
+int32_t hecuda_poly_mul_scalars(const hecuda_context *ctx, int32_t base, uint64_t *data, const uint64_t *scalars,
+                                int32_t row_count, int64_t poly_count);
+int32_t hecuda_poly_add_device(const hecuda_context *ctx, int32_t base, uint64_t *lhs, const uint64_t *rhs,
+                               int32_t row_count, int64_t poly_count, void *stream);
+int32_t hecuda_poly_sub_device(const hecuda_context *ctx, int32_t base, uint64_t *lhs, const uint64_t *rhs,
+                               int32_t row_count, int64_t poly_count, void *stream);
+int32_t hecuda_poly_mul_device(const hecuda_context *ctx, int32_t base, uint64_t *lhs, const uint64_t *rhs,
+                               int32_t row_count, int64_t poly_count, void *stream);
+int32_t hecuda_poly_neg_device(const hecuda_context *ctx, int32_t base, uint64_t *data, int32_t row_count,
+                               int64_t poly_count, void *stream);
+int32_t hecuda_poly_mul_scalars_device(const hecuda_context *ctx, int32_t base, uint64_t *data, const uint64_t *scalars,
+                                       int32_t row_count, int64_t poly_count, void *stream);
+
 /* ---- wire format of RNS polynomials ----
  * PolyRq.serialize(skipLSBs:) / PolyRq.load(from:skipLSBs:) -- PolyRq/PolyRq+Serialize.swift:28-84 over
  * CoefficientPacking.coefficientsToBytes / bytesToCoefficients (CoefficientPacking.swift:59-217): row i is a big-endian

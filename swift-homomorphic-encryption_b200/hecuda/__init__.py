@@ -93,6 +93,16 @@ SYMBOLS = {
     "hecuda_poly_serialize_device": (C.c_int32, [_VP, C.c_int32, _VP, C.c_int32, _VP, C.c_int32, C.c_int64, _VP]),
     "hecuda_poly_load_device": (C.c_int32, [_VP, C.c_int32, _VP, C.c_int32, _VP, C.c_int32, C.c_int64, _VP]),
     "hecuda_bfv_decrypt": (C.c_int32, [_VP, _VP, _VP, C.c_int32, C.c_int32, C.c_uint64, _VP, C.c_int64]),
+    "hecuda_poly_add": (C.c_int32, [_VP, C.c_int32, _VP, _VP, C.c_int32, C.c_int64]),
+    "hecuda_poly_add_device": (C.c_int32, [_VP, C.c_int32, _VP, _VP, C.c_int32, C.c_int64, _VP]),
+    "hecuda_poly_sub": (C.c_int32, [_VP, C.c_int32, _VP, _VP, C.c_int32, C.c_int64]),
+    "hecuda_poly_sub_device": (C.c_int32, [_VP, C.c_int32, _VP, _VP, C.c_int32, C.c_int64, _VP]),
+    "hecuda_poly_mul": (C.c_int32, [_VP, C.c_int32, _VP, _VP, C.c_int32, C.c_int64]),
+    "hecuda_poly_mul_device": (C.c_int32, [_VP, C.c_int32, _VP, _VP, C.c_int32, C.c_int64, _VP]),
+    "hecuda_poly_neg": (C.c_int32, [_VP, C.c_int32, _VP, C.c_int32, C.c_int64]),
+    "hecuda_poly_neg_device": (C.c_int32, [_VP, C.c_int32, _VP, C.c_int32, C.c_int64, _VP]),
+    "hecuda_poly_mul_scalars": (C.c_int32, [_VP, C.c_int32, _VP, _VP, C.c_int32, C.c_int64]),
+    "hecuda_poly_mul_scalars_device": (C.c_int32, [_VP, C.c_int32, _VP, _VP, C.c_int32, C.c_int64, _VP]),
     "hecuda_kernel_launch_count": (C.c_uint64, []),
 }
 
@@ -385,6 +395,44 @@ class Bfv:
         out = np.empty((d.shape[0], l, context.degree), dtype=np.uint64)
         _check(load_library().hecuda_plaintext_to_eval(context._h, _ptr(d), l, _ptr(out), d.shape[0]))
         return out
+
+    @staticmethod
+    def _elementwise(name: str, context: Context, lhs, rhs, base: int):
+        a = _host(lhs).copy()
+        rows = a.shape[-2]
+        count = a.size // (rows * context.degree)
+        fn = getattr(load_library(), "hecuda_poly_" + name)
+        if rhs is None:
+            _check(fn(context._h, base, _ptr(a), rows, count))
+        else:
+            b = _host(rhs)
+            if name != "mul_scalars" and b.shape != a.shape:
+                raise HeError(-1, "invalidPolyContext: operand shapes differ")
+            _check(fn(context._h, base, _ptr(a), _ptr(b), rows, count))
+        return a
+
+    @staticmethod
+    def polyAdd(context: Context, lhs, rhs, base: int = BASE_Q):
+        """PolyRq + PolyRq (PolyRq.swift:147-157) on (..., rows, N) arrays."""
+        return Bfv._elementwise("add", context, lhs, rhs, base)
+
+    @staticmethod
+    def polySub(context: Context, lhs, rhs, base: int = BASE_Q):
+        return Bfv._elementwise("sub", context, lhs, rhs, base)
+
+    @staticmethod
+    def polyMul(context: Context, lhs, rhs, base: int = BASE_Q):
+        """PolyRq<Eval> * PolyRq<Eval> (PolyRq.swift:184-204)."""
+        return Bfv._elementwise("mul", context, lhs, rhs, base)
+
+    @staticmethod
+    def polyNeg(context: Context, poly, base: int = BASE_Q):
+        return Bfv._elementwise("neg", context, poly, None, base)
+
+    @staticmethod
+    def polyMulScalars(context: Context, poly, scalars, base: int = BASE_Q):
+        """PolyRq *= [T] (PolyRq.swift:232-245): one reduced scalar per RNS row."""
+        return Bfv._elementwise("mul_scalars", context, poly, np.asarray(scalars, dtype=np.uint64), base)
 
     @staticmethod
     def decrypt(context: Context, ciphertexts, secretKey, scalingFactor: int = 1) -> np.ndarray:
