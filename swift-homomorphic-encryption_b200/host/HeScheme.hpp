@@ -28,14 +28,15 @@ namespace he {
 class HeError : public std::runtime_error {
    public:
     enum Kind { invalidCiphertext, incompatibleCiphertexts, invalidPolyContext, invalidContext, unsupportedHeOperation,
-                missingRelinearizationKey, invalidEncryptionParameters, deviceError };
+                missingRelinearizationKey, missingGaloisKey, invalidEncryptionParameters, deviceError };
     HeError(Kind k, const std::string &m) : std::runtime_error(m), kind(k) {}
     Kind kind;
     static HeError fromStatus(int32_t rc) {
         const std::string msg = hecuda_last_error() ? hecuda_last_error() : "";
         switch (rc) {
             case HECUDA_ERR_UNSUPPORTED: return HeError(unsupportedHeOperation, msg);
-            case HECUDA_ERR_MISSING_KEY: return HeError(missingRelinearizationKey, msg);
+            case HECUDA_ERR_MISSING_KEY:
+                return HeError(msg.find("Galois") != std::string::npos ? missingGaloisKey : missingRelinearizationKey, msg);
             case HECUDA_ERR_INVALID_ARGUMENT: return HeError(invalidCiphertext, msg);
             default: return HeError(deviceError, msg);
         }
@@ -103,6 +104,17 @@ class EvaluationKey {
         if (relinearizationKey.size() != L * 2 * (L + 1) * (size_t)context->degree)
             throw HeError(HeError::invalidContext, "relinearization key must be L x 2 x (L+1) x N");
         check(hecuda_evk_create(context->handle(), relinearizationKey.data(), &handle_));
+    }
+    // an evaluation key without a relinearization key (EvaluationKeyConfig.hasRelinearizationKey == false)
+    explicit EvaluationKey(std::shared_ptr<const Context> c) : context(std::move(c)) {
+        check(hecuda_evk_create_empty(context->handle(), &handle_));
+    }
+    // GaloisKey.keys[element] (Keys.swift:150-163): L ciphertexts x 2 polys x (L+1) x N, Eval format
+    void setGaloisKey(uint32_t element, const std::vector<uint64_t> &key) {
+        const size_t L = context->ciphertextModuliCount();
+        if (key.size() != L * 2 * (L + 1) * (size_t)context->degree)
+            throw HeError(HeError::invalidContext, "Galois key must be L x 2 x (L+1) x N");
+        check(hecuda_evk_set_galois_key(handle_, element, key.data()));
     }
     ~EvaluationKey() { hecuda_evk_destroy(handle_); }
     EvaluationKey(const EvaluationKey &) = delete;
@@ -174,6 +186,83 @@ struct Bfv {
         Ciphertext out(ct.context, ct.polyCount, ct.moduliCount - 1);
         check(hecuda_bfv_mod_switch_down(ct.context->handle(), ct.data.data(), ct.polyCount, ct.moduliCount, out.data.data(), 1));
         ct = std::move(out);
+    }
+
+    // Bfv.modSwitchDownToSingle (HeScheme.swift:1481-1485)
+    static void modSwitchDownToSingle(Ciphertext &ct) {
+        while (ct.moduliCount > 1) modSwitchDown(ct);
+    }
+
+    // validateEquality for the coefficient-wise ciphertext operations (HeScheme.swift:1326-1340)
+    static void validateSameShape(const Ciphertext &lhs, const Ciphertext &rhs) {
+        if (!lhs.context || !rhs.context || !(*lhs.context == *rhs.context))
+            throw HeError(HeError::invalidContext, "ciphertexts have different contexts");
+        if (lhs.polyCount != rhs.polyCount || lhs.moduliCount != rhs.moduliCount || lhs.correctionFactor != rhs.correctionFactor)
+            throw HeError(HeError::incompatibleCiphertexts, "ciphertexts have different shapes");
+    }
+    // Bfv.addAssign / subAssign / negAssign on canonical ciphertexts (Bfv.swift:61-125): coefficient-wise on the polys
+    static void addAssign(Ciphertext &lhs, const Ciphertext &rhs) {
+        validateSameShape(lhs, rhs);
+        check(hecuda_poly_add(lhs.context->handle(), HECUDA_BASE_Q, lhs.data.data(), rhs.data.data(), lhs.moduliCount, lhs.polyCount));
+    }
+    static void subAssign(Ciphertext &lhs, const Ciphertext &rhs) {
+        validateSameShape(lhs, rhs);
+        check(hecuda_poly_sub(lhs.context->handle(), HECUDA_BASE_Q, lhs.data.data(), rhs.data.data(), lhs.moduliCount, lhs.polyCount));
+    }
+    static void negAssign(Ciphertext &ct) {
+        check(hecuda_poly_neg(ct.context->handle(), HECUDA_BASE_Q, ct.data.data(), ct.moduliCount, ct.polyCount));
+    }
+
+    // Bfv.applyGalois (Bfv.swift:174-198); rotateColumns / swapRows (HeScheme.swift:1463-1478) are applyGalois with
+    // GaloisElement.rotatingColumns / swappingRows (PolyRq/Galois.swift:174-212)
+    static void applyGalois(Ciphertext &ct, uint32_t element, const EvaluationKey &key) {
+        if (ct.correctionFactor != 1) throw HeError(HeError::invalidCiphertext, "correction factor must be 1");
+        if (ct.polyCount != freshCiphertextPolyCount) throw HeError(HeError::invalidCiphertext, "ciphertext must have two polys");
+        if (!(*ct.context == *key.context)) throw HeError(HeError::invalidContext, "key belongs to another context");
+        Ciphertext out(ct.context, 2, ct.moduliCount);
+        check(hecuda_bfv_apply_galois(ct.context->handle(), key.handle(), ct.data.data(), ct.moduliCount, element, out.data.data(), 1));
+        ct = std::move(out);
+    }
+    static uint32_t rotatingColumnsElement(int step, int64_t degree) {
+        uint64_t positive = (uint64_t)(step < 0 ? -step : step);
+        if (positive == 0 || positive >= (uint64_t)(degree >> 1)) throw HeError(HeError::invalidCiphertext, "invalidRotationStep");
+        if (step > 0) positive = (uint64_t)(degree >> 1) - positive;
+        uint64_t g = 1, base = 3, mod = 2 * (uint64_t)degree;
+        for (uint64_t e = positive; e; e >>= 1) {
+            if (e & 1) g = g * base % mod;
+            base = base * base % mod;
+        }
+        return (uint32_t)g;
+    }
+    static void rotateColumns(Ciphertext &ct, int step, const EvaluationKey &key) {
+        applyGalois(ct, rotatingColumnsElement(step, ct.context->degree), key);
+    }
+    static void swapRows(Ciphertext &ct, const EvaluationKey &key) {
+        applyGalois(ct, (uint32_t)(2 * ct.context->degree - 1), key);
+    }
+
+    // Bfv.innerProduct(ciphertexts:plaintexts:) (Bfv.swift:476-505): Eval ciphertexts x optional Eval plaintexts
+    static Ciphertext innerProduct(const std::vector<Ciphertext> &ciphertexts, const std::vector<const PolyRq *> &plaintexts) {
+        if (ciphertexts.empty()) throw HeError(HeError::invalidCiphertext, "Empty ciphertexts");
+        if (ciphertexts.size() != plaintexts.size()) throw HeError(HeError::incompatibleCiphertexts, "counts differ");
+        const Ciphertext &first = ciphertexts[0];
+        const size_t ctWords = (size_t)first.polyCount * first.polyWords(), ptWords = first.polyWords();
+        std::vector<uint64_t> cts(ctWords * ciphertexts.size()), pts(ptWords * ciphertexts.size(), 0);
+        std::vector<uint8_t> present(ciphertexts.size(), 0);
+        for (size_t k = 0; k < ciphertexts.size(); ++k) {
+            if (ciphertexts[k].polyCount != first.polyCount || ciphertexts[k].moduliCount != first.moduliCount)
+                throw HeError(HeError::incompatibleCiphertexts, "ciphertexts have different shapes");
+            std::copy(ciphertexts[k].data.begin(), ciphertexts[k].data.end(), cts.begin() + k * ctWords);
+            if (plaintexts[k]) {
+                if (plaintexts[k]->moduliCount != first.moduliCount) throw HeError(HeError::invalidPolyContext, "plaintext moduli count");
+                std::copy(plaintexts[k]->data.begin(), plaintexts[k]->data.end(), pts.begin() + k * ptWords);
+                present[k] = 1;
+            }
+        }
+        Ciphertext out(first.context, first.polyCount, first.moduliCount);
+        check(hecuda_bfv_inner_product_plaintexts(first.context->handle(), cts.data(), first.polyCount, first.moduliCount,
+                                                  (int64_t)ciphertexts.size(), pts.data(), present.data(), out.data.data(), 1));
+        return out;
     }
 
     // PolyRq.forwardNtt / inverseNtt (in place; the reference consumes `self` and returns the other format)

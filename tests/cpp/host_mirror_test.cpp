@@ -62,6 +62,49 @@ int main(int argc, char **argv) {
     he::Bfv::forwardNtt(poly);
     he::Bfv::inverseNtt(poly);
     failures += std::memcmp(poly.data.data(), a.data(), pw * 8) != 0;
+    // optional second case: Galois / coefficient-wise / inner-product surface
+    if (argc >= 3) {
+        std::ifstream f2(argv[2], std::ios::binary);
+        if (!f2) return 4;
+        auto h2 = read_vec(f2);  // element, rotation step, terms
+        auto ct = read_vec(f2), other = read_vec(f2), gkey = read_vec(f2), rkey = read_vec(f2);
+        auto sum = read_vec(f2), diff = read_vec(f2), neg = read_vec(f2), galois = read_vec(f2), rotated = read_vec(f2);
+        auto single = read_vec(f2), ipCts = read_vec(f2), ipPts = read_vec(f2), ipPresent = read_vec(f2), ipOut = read_vec(f2);
+        he::EvaluationKey gal(ctx);
+        gal.setGaloisKey((uint32_t)h2[0], gkey);
+        gal.setGaloisKey(he::Bfv::rotatingColumnsElement((int)(int64_t)h2[1], n), rkey);
+        auto load = [&](const std::vector<uint64_t> &v, int polys, int rows) {
+            he::Ciphertext c(ctx, polys, rows);
+            std::copy(v.begin(), v.begin() + c.data.size(), c.data.begin());
+            return c;
+        };
+        auto same = [&](const he::Ciphertext &c, const std::vector<uint64_t> &v) {
+            return c.data.size() == v.size() && std::memcmp(c.data.data(), v.data(), v.size() * 8) == 0;
+        };
+        he::Ciphertext x = load(ct, 2, L), y = load(other, 2, L);
+        he::Ciphertext t1 = x; he::Bfv::addAssign(t1, y); failures += !same(t1, sum);
+        he::Ciphertext t2 = x; he::Bfv::subAssign(t2, y); failures += !same(t2, diff);
+        he::Ciphertext t3 = x; he::Bfv::negAssign(t3); failures += !same(t3, neg);
+        he::Ciphertext t4 = x; he::Bfv::applyGalois(t4, (uint32_t)h2[0], gal); failures += !same(t4, galois);
+        he::Ciphertext t5 = x; he::Bfv::rotateColumns(t5, (int)(int64_t)h2[1], gal); failures += !same(t5, rotated);
+        he::Ciphertext t6 = x; he::Bfv::modSwitchDownToSingle(t6); failures += t6.moduliCount != 1 || !same(t6, single);
+        const int terms = (int)h2[2];
+        std::vector<he::Ciphertext> cts;
+        std::vector<he::PolyRq> pts;
+        std::vector<const he::PolyRq *> ptrs;
+        for (int k = 0; k < terms; ++k) {
+            he::Ciphertext c(ctx, 2, L);
+            std::copy(ipCts.begin() + k * 2 * pw, ipCts.begin() + (k + 1) * 2 * pw, c.data.begin());
+            cts.push_back(c);
+            he::PolyRq p(ctx, L);
+            std::copy(ipPts.begin() + k * pw, ipPts.begin() + (k + 1) * pw, p.data.begin());
+            pts.push_back(p);
+        }
+        for (int k = 0; k < terms; ++k) ptrs.push_back(ipPresent[k] ? &pts[k] : nullptr);
+        failures += !same(he::Bfv::innerProduct(cts, ptrs), ipOut);
+        try { he::Bfv::applyGalois(x, 5, gal); ++failures; } catch (const he::HeError &e) { failures += e.kind != he::HeError::missingGaloisKey; }
+        try { he::Ciphertext three(ctx, 3, L); he::Bfv::addAssign(three, x); ++failures; } catch (const he::HeError &e) { failures += e.kind != he::HeError::incompatibleCiphertexts; }
+    }
     std::printf("host mirror: %d failure(s)\n", failures);
     return failures ? 1 : 0;
 }
