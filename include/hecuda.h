@@ -298,6 +298,18 @@ int32_t hecuda_poly_serialize_device(const hecuda_context *ctx, int32_t base, co
 int32_t hecuda_poly_load_device(const hecuda_context *ctx, int32_t base, const uint8_t *serialized, int32_t skip_lsbs,
                                 uint64_t *out, int32_t row_count, int64_t poly_count, void *stream);
 
+/* Seeded ciphertexts.  hecuda_poly_random_from_seed = PolyRq.random(context:using:) with NistAes128Ctr(seed:)
+ * (PolyRq/PolyRq+Randomize.swift:29-81; Random/NistAes128Ctr.swift, NistCtrDrbg.swift: NIST SP 800-90A CTR_DRBG over
+ * AES-128 without derivation function, 4096-byte buffered): seeds batch x 32 bytes -> out batch x moduli_count x N
+ * residues, coefficient k of row r = the (r N + k)-th little-endian 128-bit word of the stream mod q_r.
+ * hecuda_ciphertext_expand_seeded = Ciphertext(deserialize: .seeded(poly0:seed:)) (SerializedCiphertext.swift:41-60):
+ * poly0 batch x serialized bytes (hecuda_poly_serialized_byte_count, skipLSBs 0) and the seeds -> batch x 2 x
+ * moduli_count x N Coeff ciphertexts (poly1 = the random polynomial, sampled in Eval format, converted to Coeff). */
+int32_t hecuda_poly_random_from_seed(const hecuda_context *ctx, const uint8_t *seeds, int32_t moduli_count, uint64_t *out,
+                                     int64_t batch);
+int32_t hecuda_ciphertext_expand_seeded(const hecuda_context *ctx, const uint8_t *poly0, const uint8_t *seeds,
+                                        int32_t moduli_count, uint64_t *out, int64_t batch);
+
 /* Bfv.decryptCoeff -- Bfv/Bfv+Decrypt.swift:21-41 (dotProduct(ciphertext:with:) :188-204) with RnsTool.scaleAndRound
  * (RnsTool.swift:272-302).  secret_key: SecretKey.poly, (L+1) x N in Eval format (only its first moduli_count rows are
  * read); ciphertexts: batch x poly_count x moduli_count x N (Coeff, poly_count 2 or 3, any level); scaling_factor =

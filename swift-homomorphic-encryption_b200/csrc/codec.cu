@@ -14,11 +14,6 @@
 
 namespace hecuda {
 
-struct CodecConsts {
-    int rows;
-    int width[kMaxRows];             // serialized bits per coefficient of each row
-    long long byte_offset[kMaxRows + 1];  // of each row inside one serialized polynomial
-};
 
 // bytes -> coefficients: one thread per coefficient
 __global__ void __launch_bounds__(256) poly_load_kernel(const unsigned char *__restrict__ bytes, u64 *__restrict__ out,

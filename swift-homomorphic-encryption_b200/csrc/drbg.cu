@@ -1,0 +1,197 @@
+// drbg.cu -- seeded-ciphertext expansion on the device.
+//
+//   NistCtrDrbg (CTR_DRBG, AES-128, no derivation function)   Random/NistCtrDrbg.swift:25-84  (NIST SP 800-90A)
+//   NistAes128Ctr = BufferedRng<NistCtrDrbg>, 4096-byte buffer Random/NistAes128Ctr.swift:17-40, BufferedRng.swift:17-67
+//   PolyRq.randomizeUniform(using:)                            PolyRq/PolyRq+Randomize.swift:49-81
+//   Ciphertext(deserialize: .seeded(poly0:seed:))              SerializedCiphertext.swift:41-60
+//
+// The byte stream a seed produces is a chain of 4096-byte segments: segment s is AES-128-CTR under (key_s, V_s), and
+// (key_{s+1}, V_{s+1}) come from two more blocks of the same keystream.  One thread per seed walks that chain (it is
+// inherently sequential, 2 block encryptions + 1 key schedule per segment) and leaves the expanded round keys; then
+// every 16-byte block of every segment is independent: one CTA per segment, one thread per block = per coefficient
+// (a coefficient consumes exactly one little-endian 128-bit word, reduced modulo its row modulus).
+// AES is FIPS-197 written from the specification (S-box, ShiftRows, MixColumns over GF(2^8)); the reference gets it
+// from swift-crypto.  Pinned by the reference's NIST vectors through the oracle (tests/test_oracle_drbg.py).
+#include <algorithm>
+
+#include "capi_internal.hpp"
+#include "drbg.cuh"
+#include "modarith.cuh"
+
+using namespace hecuda;
+using namespace hecuda::api;
+using namespace hecuda::drbg;
+
+namespace {
+
+__constant__ unsigned char c_sbox[256];
+
+// one thread per seed: the (round keys, V) of every 4096-byte segment of its stream
+__global__ void drbg_chain_kernel(const unsigned char *__restrict__ seeds, unsigned char *__restrict__ round_keys,
+                                  u64 *__restrict__ counters, int segments, long long batch) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+    unsigned char key[16], rk[kRoundKeyBytes];
+    for (int i = 0; i < 16; ++i) key[i] = 0;
+    u64 hi = 0, lo = 0;
+    expand_key(key, rk, c_sbox);
+    drbg_update(key, hi, lo, rk, seeds + 32 * b, c_sbox);  // init(entropy:) (:52-59)
+    for (int s = 0; s < segments; ++s) {
+        expand_key(key, rk, c_sbox);
+        unsigned char *dst = round_keys + ((size_t)b * segments + s) * kRoundKeyBytes;
+        for (int i = 0; i < kRoundKeyBytes; ++i) dst[i] = rk[i];
+        counters[2 * ((size_t)b * segments + s)] = hi;
+        counters[2 * ((size_t)b * segments + s) + 1] = lo;
+        // ctrDrbgGenerate(count: 4096) (:71-84): V += 256 blocks, then update with zero additional input
+        const u64 l = lo + kSegmentBlocks;
+        hi += l < lo ? 1 : 0;
+        lo = l;
+        drbg_update(key, hi, lo, rk, nullptr, c_sbox);
+    }
+}
+
+struct FillConsts {
+    int rows;
+    u64 p[kMaxRows];
+};
+
+// one CTA per segment, one thread per 16-byte block = per coefficient (randomizeUniform, PolyRq+Randomize.swift:58-80)
+__global__ void __launch_bounds__(kSegmentBlocks) drbg_fill_kernel(const unsigned char *__restrict__ round_keys,
+                                                                   const u64 *__restrict__ counters, u64 *__restrict__ out,
+                                                                   const __grid_constant__ FillConsts c, int n, int segments) {
+    __shared__ unsigned char sbox[256];
+    __shared__ unsigned char rk[kRoundKeyBytes];
+    const long long b = blockIdx.y;
+    const int s = blockIdx.x;
+    sbox[threadIdx.x] = c_sbox[threadIdx.x];
+    if (threadIdx.x < kRoundKeyBytes) rk[threadIdx.x] = round_keys[((size_t)b * segments + s) * kRoundKeyBytes + threadIdx.x];
+    __syncthreads();
+    const long long k = (long long)s * kSegmentBlocks + threadIdx.x;
+    if (k >= (long long)c.rows * n) return;
+    unsigned char block[16];
+    counter_block(counters[2 * ((size_t)b * segments + s)], counters[2 * ((size_t)b * segments + s) + 1], 1 + threadIdx.x, block);
+    encrypt_block(block, rk, sbox);
+    u64 lo = 0, hi = 0;  // UInt128(littleEndianBytes:)
+#pragma unroll
+    for (int i = 7; i >= 0; --i) {
+        lo = (lo << 8) | block[i];
+        hi = (hi << 8) | block[8 + i];
+    }
+    const int row = (int)(k / n);
+    out[(size_t)b * c.rows * n + k] = (u64)((((u128)hi << 64) | lo) % c.p[row]);
+}
+
+cudaError_t random_polys_device(const Context &c, int l, const unsigned char *d_seeds, u64 *d_out, int64_t batch,
+                                cudaStream_t s) {
+    int device = 0;
+    cudaGetDevice(&device);
+    unsigned char sbox[256];
+    make_sbox(sbox);
+    cudaError_t e = cudaMemcpyToSymbolAsync(c_sbox, sbox, 256, 0, cudaMemcpyHostToDevice, s);  // per device, cheap
+    if (e != cudaSuccess) return e;
+    e = cudaStreamSynchronize(s);  // `sbox` lives on this stack frame
+    if (e != cudaSuccess) return e;
+    const int segments = (int)(((size_t)l * c.n * 16 + kSegmentBytes - 1) / kSegmentBytes);
+    unsigned char *d_rk = nullptr;
+    u64 *d_ctr = nullptr;
+    e = cudaMallocAsync((void **)&d_rk, (size_t)batch * segments * kRoundKeyBytes, s);
+    if (e == cudaSuccess) e = cudaMallocAsync((void **)&d_ctr, (size_t)batch * segments * 2 * sizeof(u64), s);
+    if (e == cudaSuccess) {
+        ++g_kernel_launches;
+        drbg_chain_kernel<<<(unsigned)((batch + 31) / 32), 32, 0, s>>>(d_seeds, d_rk, d_ctr, segments, batch);
+        e = cudaGetLastError();
+    }
+    FillConsts fc;
+    fc.rows = l;
+    for (int r = 0; r < l; ++r) fc.p[r] = c.slots[c.slot_q(r)].dev.p;
+    for (int64_t done = 0; e == cudaSuccess && done < batch;) {
+        const int64_t part = std::min<int64_t>(batch - done, 65535);
+        ++g_kernel_launches;
+        drbg_fill_kernel<<<dim3((unsigned)segments, (unsigned)part), kSegmentBlocks, 0, s>>>(
+            d_rk + (size_t)done * segments * kRoundKeyBytes, d_ctr + (size_t)done * segments * 2, d_out + (size_t)done * l * c.n, fc,
+            (int)c.n, segments);
+        e = cudaGetLastError();
+        done += part;
+    }
+    if (d_rk) {
+        cudaMemsetAsync(d_rk, 0, (size_t)batch * segments * kRoundKeyBytes, s);  // key material
+        cudaFreeAsync(d_rk, s);
+    }
+    if (d_ctr) cudaFreeAsync(d_ctr, s);
+    return e;
+}
+
+int32_t check(const hecuda_context *h, const void *seeds, int32_t l, const void *out, int64_t batch) {
+    int32_t rc = check_ctx(h);
+    if (rc) return rc;
+    if (l < 1 || l > h->ctx->L) return fail(HECUDA_ERR_INVALID_ARGUMENT, "invalidPolyContext: moduli_count out of range");
+    if (batch < 0 || (batch && (!seeds || !out))) return fail(HECUDA_ERR_INVALID_ARGUMENT, "null buffer");
+    return HECUDA_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t hecuda_poly_random_from_seed(const hecuda_context *h, const uint8_t *seeds, int32_t l, uint64_t *out, int64_t batch) {
+    int32_t rc = check(h, seeds, l, out, batch);
+    if (rc || batch == 0) return rc;
+    const Context &c = *h->ctx;
+    WsGuard g(h);
+    if (!g.w) return fail(HECUDA_ERR_CUDA, "could not create a CUDA stream / workspace");
+    cudaStream_t s = g.w->stream;
+    unsigned char *d_seeds = nullptr;
+    u64 *d_out = nullptr;
+    const size_t words = (size_t)l * c.n * batch;
+    CK(cudaMallocAsync((void **)&d_seeds, (size_t)32 * batch, s));
+    CK(cudaMallocAsync((void **)&d_out, words * sizeof(u64), s));
+    cudaError_t e = cudaMemcpyAsync(d_seeds, seeds, (size_t)32 * batch, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = random_polys_device(c, l, d_seeds, d_out, batch, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, words * sizeof(u64), cudaMemcpyDeviceToHost, s);
+    cudaFreeAsync(d_seeds, s);
+    cudaFreeAsync(d_out, s);
+    cudaError_t e2 = cudaStreamSynchronize(s);
+    if (e == cudaSuccess) e = e2;
+    return e == cudaSuccess ? HECUDA_OK : cuda_fail(e, "poly_random_from_seed");
+}
+
+int32_t hecuda_ciphertext_expand_seeded(const hecuda_context *h, const uint8_t *poly0, const uint8_t *seeds, int32_t l,
+                                        uint64_t *out, int64_t batch) {
+    int32_t rc = check(h, seeds, l, out, batch);
+    if (rc) return rc;
+    if (batch && !poly0) return fail(HECUDA_ERR_INVALID_ARGUMENT, "null buffer");
+    if (batch == 0) return HECUDA_OK;
+    const Context &c = *h->ctx;
+    const NttRowMap map = c.map_q(l);
+    CodecConsts cc;
+    std::string err;
+    if (!codec_consts(c, map, 0, cc, err)) return fail(HECUDA_ERR_INVALID_ARGUMENT, err);
+    const size_t poly_bytes = (size_t)serialized_poly_bytes(cc), poly_words = (size_t)l * c.n;
+    WsGuard g(h);
+    if (!g.w) return fail(HECUDA_ERR_CUDA, "could not create a CUDA stream / workspace");
+    cudaStream_t s = g.w->stream;
+    unsigned char *d_seeds = nullptr, *d_poly0 = nullptr;
+    u64 *d_a = nullptr, *d_p0 = nullptr, *d_out = nullptr;
+    cudaError_t e = cudaMallocAsync((void **)&d_seeds, (size_t)32 * batch, s);
+    if (e == cudaSuccess) e = cudaMallocAsync((void **)&d_poly0, poly_bytes * batch, s);
+    if (e == cudaSuccess) e = cudaMallocAsync((void **)&d_a, poly_words * batch * sizeof(u64), s);
+    if (e == cudaSuccess) e = cudaMallocAsync((void **)&d_p0, poly_words * batch * sizeof(u64), s);
+    if (e == cudaSuccess) e = cudaMallocAsync((void **)&d_out, 2 * poly_words * batch * sizeof(u64), s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_seeds, seeds, (size_t)32 * batch, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_poly0, poly0, poly_bytes * batch, cudaMemcpyHostToDevice, s);
+    // poly0: PolyRq(deserialize:) ; poly1: random Eval polynomial converted to Coeff (SerializedCiphertext.swift:44-49)
+    if (e == cudaSuccess) e = launch_poly_load(c, cc, 0, d_poly0, d_p0, batch, s);
+    if (e == cudaSuccess) e = random_polys_device(c, l, d_seeds, d_a, batch, s);
+    if (e == cudaSuccess) e = launch_ntt_inverse(c, map, d_a, d_a, batch * l, kScalePlain, s);
+    const size_t pw = poly_words * sizeof(u64);
+    if (e == cudaSuccess) e = cudaMemcpy2DAsync(d_out, 2 * pw, d_p0, pw, pw, (size_t)batch, cudaMemcpyDeviceToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpy2DAsync(d_out + poly_words, 2 * pw, d_a, pw, pw, (size_t)batch, cudaMemcpyDeviceToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, 2 * pw * batch, cudaMemcpyDeviceToHost, s);
+    for (void *p : {(void *)d_seeds, (void *)d_poly0, (void *)d_a, (void *)d_p0, (void *)d_out})
+        if (p) cudaFreeAsync(p, s);
+    cudaError_t e2 = cudaStreamSynchronize(s);
+    if (e == cudaSuccess) e = e2;
+    return e == cudaSuccess ? HECUDA_OK : cuda_fail(e, "expand_seeded");
+}
+
+}  // extern "C"

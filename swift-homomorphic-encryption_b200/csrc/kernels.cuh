@@ -67,7 +67,11 @@ cudaError_t launch_plaintext_to_eval(const Context &ctx, const u64 *plain, int l
                                      cudaStream_t stream);
 
 // ---- wire format (codec.cu): PolyRq.serialize / load, PolyRq+Serialize.swift:28-84
-struct CodecConsts;
+struct CodecConsts {
+    int rows;
+    int width[kMaxRows];                  // serialized bits per coefficient of each row
+    long long byte_offset[kMaxRows + 1];  // of each row inside one serialized polynomial
+};
 bool codec_consts(const Context &ctx, const NttRowMap &map, int skip, CodecConsts &c, std::string &err);
 long long serialized_poly_bytes(const CodecConsts &c);
 cudaError_t launch_poly_load(const Context &ctx, const CodecConsts &c, int skip, const unsigned char *bytes, u64 *out,

@@ -92,6 +92,8 @@ SYMBOLS = {
     "hecuda_poly_load": (C.c_int32, [_VP, C.c_int32, _VP, C.c_int32, _VP, C.c_int32, C.c_int64]),
     "hecuda_poly_serialize_device": (C.c_int32, [_VP, C.c_int32, _VP, C.c_int32, _VP, C.c_int32, C.c_int64, _VP]),
     "hecuda_poly_load_device": (C.c_int32, [_VP, C.c_int32, _VP, C.c_int32, _VP, C.c_int32, C.c_int64, _VP]),
+    "hecuda_poly_random_from_seed": (C.c_int32, [_VP, _VP, C.c_int32, _VP, C.c_int64]),
+    "hecuda_ciphertext_expand_seeded": (C.c_int32, [_VP, _VP, _VP, C.c_int32, _VP, C.c_int64]),
     "hecuda_bfv_decrypt": (C.c_int32, [_VP, _VP, _VP, C.c_int32, C.c_int32, C.c_uint64, _VP, C.c_int64]),
     "hecuda_poly_add": (C.c_int32, [_VP, C.c_int32, _VP, _VP, C.c_int32, C.c_int64]),
     "hecuda_poly_add_device": (C.c_int32, [_VP, C.c_int32, _VP, _VP, C.c_int32, C.c_int64, _VP]),
@@ -394,6 +396,29 @@ class Bfv:
         l = moduliCount or context.L
         out = np.empty((d.shape[0], l, context.degree), dtype=np.uint64)
         _check(load_library().hecuda_plaintext_to_eval(context._h, _ptr(d), l, _ptr(out), d.shape[0]))
+        return out
+
+    @staticmethod
+    def randomPolys(context: Context, seeds, moduliCount: int = 0) -> np.ndarray:
+        """PolyRq.random(context:using: NistAes128Ctr(seed:)) for (batch, 32) uint8 seeds -> (batch, l, N)."""
+        sd = np.ascontiguousarray(np.asarray(seeds, dtype=np.uint8)).reshape(-1, 32)
+        l = moduliCount or context.L
+        out = np.empty((sd.shape[0], l, context.degree), dtype=np.uint64)
+        _check(load_library().hecuda_poly_random_from_seed(context._h, sd.ctypes.data_as(C.c_void_p), l, _ptr(out), sd.shape[0]))
+        return out
+
+    @staticmethod
+    def expandSeeded(context: Context, poly0, seeds, moduliCount: int = 0) -> np.ndarray:
+        """Ciphertext(deserialize: .seeded(poly0:seed:)) (SerializedCiphertext.swift:41-60) -> (batch, 2, l, N) Coeff."""
+        sd = np.ascontiguousarray(np.asarray(seeds, dtype=np.uint8)).reshape(-1, 32)
+        l = moduliCount or context.L
+        size = Bfv.serializationByteCount(context, l)
+        p0 = np.ascontiguousarray(np.asarray(poly0, dtype=np.uint8)).reshape(-1)
+        if p0.size != size * sd.shape[0]:
+            raise HeError(-1, f"serializedBufferSizeMismatch(actual: {p0.size}, expected: {size * sd.shape[0]})")
+        out = np.empty((sd.shape[0], 2, l, context.degree), dtype=np.uint64)
+        _check(load_library().hecuda_ciphertext_expand_seeded(context._h, p0.ctypes.data_as(C.c_void_p),
+                                                              sd.ctypes.data_as(C.c_void_p), l, _ptr(out), sd.shape[0]))
         return out
 
     @staticmethod
