@@ -213,6 +213,19 @@ int32_t hecuda_mulpir_compute_response_device(const hecuda_context *ctx, const h
                                               const uint64_t *query, int32_t query_ciphertext_count,
                                               int32_t indices_count, uint64_t *out, void *stream);
 
+/* The same, bytes in / bytes out: the query ciphertexts as they travel (SerializedCiphertext.seeded: poly0 serialized with
+ * skipLSBs 0 over all L rows, plus the 32-byte seed; SerializedCiphertext.swift:41-49,150-154) and the reply ciphertexts as
+ * they leave (SerializedCiphertext.full with Bfv.skipLSBsForDecryption, Bfv+Decrypt.swift:51-110: single modulus, poly 0 and
+ * poly 1 packed with skip_lsbs_poly0 / skip_lsbs_poly1 dropped bits).  out: indices_count x chunk_count x
+ * (byteCount(1 row, skip0) + byteCount(1 row, skip1)) bytes.  Expansion of the seeds, the whole response computation and
+ * the packing run on the device; PCIe carries ceil(log2 q) bits per coefficient in and (ceil(log2 q_0) - skip) out. */
+int32_t hecuda_mulpir_compute_response_wire(const hecuda_context *ctx, const hecuda_evk *evk,
+                                            const hecuda_pir_database *const *databases, int32_t database_count,
+                                            const int32_t *dimensions, int32_t dimension_count, int32_t chunk_count,
+                                            const uint8_t *query_poly0, const uint8_t *query_seeds,
+                                            int32_t query_ciphertext_count, int32_t indices_count, int32_t skip_lsbs_poly0,
+                                            int32_t skip_lsbs_poly1, uint8_t *out);
+
 /* ---- PNNS server: encrypted vector x plaintext matrix ----
  * Device-resident PlaintextMatrix in `.diagonal(babyStepGiantStep:)` packing (PrivateNearestNeighborSearch/
  * PlaintextMatrix.swift:417-482): nextPowerOfTwo(column_count) * ceil(row_count / N) plaintexts in the order the

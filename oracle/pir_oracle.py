@@ -498,3 +498,14 @@ def load_poly(n: int, moduli, buffer: bytes, skip_lsbs: int = 0) -> np.ndarray:
         out[i] = bytes_to_coefficients(buffer[offset:offset + count], bits, decode=True, skip_lsbs=skip_lsbs)[:n]
         offset += count
     return out
+
+
+def skip_lsbs_for_decryption(n: int, q0: int, t: int) -> list:
+    """Bfv.skipLSBsForDecryption(for:) of a single-modulus ciphertext (Bfv+Decrypt.swift:51-110)."""
+    l_prime = log2(q0 // t) - 3 if q0 >= 2 * t else 0
+    tmp = int(8.0 * math.sqrt(2.0 * n / 9.0))
+    poly0 = max(l_prime, 0)
+    poly1 = l_prime - (0 if tmp == 0 else ceil_log2(tmp))
+    if poly1 <= 1:
+        poly0, poly1 = max(l_prime + 1, 0), 0
+    return [poly0, poly1]

@@ -122,6 +122,8 @@ cudaError_t relinearize_chunk(const Context &c, u64 *scratch, const u64 *key, co
                               int64_t items, cudaStream_t s);
 cudaError_t apply_galois_chunk(const Context &c, u64 *scratch, const u64 *key, const u64 *ct, int l, unsigned element,
                                u64 *out, int64_t items, cudaStream_t s);
+cudaError_t expand_seeded_device(const Context &c, int l, const unsigned char *d_poly0, const unsigned char *d_seeds, u64 *d_out,
+                                 int64_t batch, cudaStream_t s);
 cudaError_t inner_product_chunk(const Context &c, u64 *scratch, const u64 *lhs, const u64 *rhs, int64_t pairs, u64 *out,
                                 int64_t groups, cudaStream_t s);
 

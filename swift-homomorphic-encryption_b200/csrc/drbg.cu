@@ -131,6 +131,34 @@ int32_t check(const hecuda_context *h, const void *seeds, int32_t l, const void 
 
 }  // namespace
 
+namespace hecuda {
+namespace api {
+
+// Ciphertext(deserialize: .seeded) for `batch` ciphertexts, all buffers on the device; d_out: batch x 2 x l x N (Coeff)
+cudaError_t expand_seeded_device(const Context &c, int l, const unsigned char *d_poly0, const unsigned char *d_seeds, u64 *d_out,
+                                 int64_t batch, cudaStream_t s) {
+    const NttRowMap map = c.map_q(l);
+    CodecConsts cc;
+    std::string err;
+    if (!codec_consts(c, map, 0, cc, err)) return cudaErrorInvalidValue;
+    const size_t poly_words = (size_t)l * c.n, pw = poly_words * sizeof(u64);
+    u64 *d_a = nullptr, *d_p0 = nullptr;
+    cudaError_t e = cudaMallocAsync((void **)&d_a, pw * batch, s);
+    if (e == cudaSuccess) e = cudaMallocAsync((void **)&d_p0, pw * batch, s);
+    // poly0: PolyRq(deserialize:) ; poly1: random Eval polynomial converted to Coeff (SerializedCiphertext.swift:44-49)
+    if (e == cudaSuccess) e = launch_poly_load(c, cc, 0, d_poly0, d_p0, batch, s);
+    if (e == cudaSuccess) e = random_polys_device(c, l, d_seeds, d_a, batch, s);
+    if (e == cudaSuccess) e = launch_ntt_inverse(c, map, d_a, d_a, batch * l, kScalePlain, s);
+    if (e == cudaSuccess) e = cudaMemcpy2DAsync(d_out, 2 * pw, d_p0, pw, pw, (size_t)batch, cudaMemcpyDeviceToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpy2DAsync(d_out + poly_words, 2 * pw, d_a, pw, pw, (size_t)batch, cudaMemcpyDeviceToDevice, s);
+    if (d_a) cudaFreeAsync(d_a, s);
+    if (d_p0) cudaFreeAsync(d_p0, s);
+    return e;
+}
+
+}  // namespace api
+}  // namespace hecuda
+
 extern "C" {
 
 int32_t hecuda_poly_random_from_seed(const hecuda_context *h, const uint8_t *seeds, int32_t l, uint64_t *out, int64_t batch) {
@@ -171,23 +199,15 @@ int32_t hecuda_ciphertext_expand_seeded(const hecuda_context *h, const uint8_t *
     if (!g.w) return fail(HECUDA_ERR_CUDA, "could not create a CUDA stream / workspace");
     cudaStream_t s = g.w->stream;
     unsigned char *d_seeds = nullptr, *d_poly0 = nullptr;
-    u64 *d_a = nullptr, *d_p0 = nullptr, *d_out = nullptr;
+    u64 *d_out = nullptr;
     cudaError_t e = cudaMallocAsync((void **)&d_seeds, (size_t)32 * batch, s);
     if (e == cudaSuccess) e = cudaMallocAsync((void **)&d_poly0, poly_bytes * batch, s);
-    if (e == cudaSuccess) e = cudaMallocAsync((void **)&d_a, poly_words * batch * sizeof(u64), s);
-    if (e == cudaSuccess) e = cudaMallocAsync((void **)&d_p0, poly_words * batch * sizeof(u64), s);
     if (e == cudaSuccess) e = cudaMallocAsync((void **)&d_out, 2 * poly_words * batch * sizeof(u64), s);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_seeds, seeds, (size_t)32 * batch, cudaMemcpyHostToDevice, s);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_poly0, poly0, poly_bytes * batch, cudaMemcpyHostToDevice, s);
-    // poly0: PolyRq(deserialize:) ; poly1: random Eval polynomial converted to Coeff (SerializedCiphertext.swift:44-49)
-    if (e == cudaSuccess) e = launch_poly_load(c, cc, 0, d_poly0, d_p0, batch, s);
-    if (e == cudaSuccess) e = random_polys_device(c, l, d_seeds, d_a, batch, s);
-    if (e == cudaSuccess) e = launch_ntt_inverse(c, map, d_a, d_a, batch * l, kScalePlain, s);
-    const size_t pw = poly_words * sizeof(u64);
-    if (e == cudaSuccess) e = cudaMemcpy2DAsync(d_out, 2 * pw, d_p0, pw, pw, (size_t)batch, cudaMemcpyDeviceToDevice, s);
-    if (e == cudaSuccess) e = cudaMemcpy2DAsync(d_out + poly_words, 2 * pw, d_a, pw, pw, (size_t)batch, cudaMemcpyDeviceToDevice, s);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, 2 * pw * batch, cudaMemcpyDeviceToHost, s);
-    for (void *p : {(void *)d_seeds, (void *)d_poly0, (void *)d_a, (void *)d_p0, (void *)d_out})
+    if (e == cudaSuccess) e = expand_seeded_device(c, l, d_poly0, d_seeds, d_out, batch, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, 2 * poly_words * sizeof(u64) * batch, cudaMemcpyDeviceToHost, s);
+    for (void *p : {(void *)d_seeds, (void *)d_poly0, (void *)d_out})
         if (p) cudaFreeAsync(p, s);
     cudaError_t e2 = cudaStreamSynchronize(s);
     if (e == cudaSuccess) e = e2;

@@ -526,4 +526,64 @@ int32_t hecuda_mulpir_compute_response(const hecuda_context *h, const hecuda_evk
     return HECUDA_OK;
 }
 
+int32_t hecuda_mulpir_compute_response_wire(const hecuda_context *h, const hecuda_evk *k, const hecuda_pir_database *const *dbs,
+                                            int32_t db_count, const int32_t *dims, int32_t dim_count, int32_t chunk_count,
+                                            const uint8_t *query_poly0, const uint8_t *query_seeds, int32_t query_ct_count,
+                                            int32_t indices_count, int32_t skip_lsbs_poly0, int32_t skip_lsbs_poly1,
+                                            uint8_t *out) {
+    ResponseShape shape;
+    int32_t rc = check_response_args(h, k, dbs, db_count, dims, dim_count, chunk_count, (const uint64_t *)query_poly0,
+                                     query_ct_count, indices_count, out, shape);
+    if (rc) return rc;
+    if (!query_seeds) return fail(HECUDA_ERR_INVALID_ARGUMENT, "null argument");
+    const Context &c = *h->ctx;
+    CodecConsts in_codec, out_codec[2];
+    std::string err;
+    if (!codec_consts(c, c.map_q(c.L), 0, in_codec, err) || !codec_consts(c, c.map_q(1), skip_lsbs_poly0, out_codec[0], err) ||
+        !codec_consts(c, c.map_q(1), skip_lsbs_poly1, out_codec[1], err))
+        return fail(HECUDA_ERR_INVALID_ARGUMENT, err);
+    WsGuard g(h);
+    if (!g.w) return fail(HECUDA_ERR_CUDA, "could not create a CUDA stream / workspace");
+    cudaStream_t s = g.w->stream;
+    StreamBuffers tmp(s);
+    const size_t ct_words = (size_t)2 * c.L * c.n, in_bytes = (size_t)serialized_poly_bytes(in_codec);
+    const int64_t replies = (int64_t)indices_count * chunk_count;
+    const size_t b0 = (size_t)serialized_poly_bytes(out_codec[0]), b1 = (size_t)serialized_poly_bytes(out_codec[1]);
+    unsigned char *d_poly0 = nullptr, *d_seeds = nullptr, *d_bytes[2] = {nullptr, nullptr}, *d_reply = nullptr;
+    u64 *d_query = nullptr, *d_resp = nullptr, *d_polys = nullptr;
+    CK(tmp.alloc_bytes((void **)&d_poly0, in_bytes * query_ct_count));
+    CK(tmp.alloc_bytes((void **)&d_seeds, (size_t)32 * query_ct_count));
+    CK(tmp.alloc(&d_query, ct_words * query_ct_count));
+    CK(tmp.alloc(&d_resp, (size_t)2 * c.n * replies));
+    CK(tmp.alloc(&d_polys, (size_t)2 * c.n * replies));
+    CK(tmp.alloc_bytes((void **)&d_bytes[0], ((b0 + 7) & ~(size_t)7) * replies + 8));
+    CK(tmp.alloc_bytes((void **)&d_bytes[1], ((b1 + 7) & ~(size_t)7) * replies + 8));
+    CK(tmp.alloc_bytes((void **)&d_reply, (b0 + b1) * replies));
+    CK(cudaMemcpyAsync(d_poly0, query_poly0, in_bytes * query_ct_count, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d_seeds, query_seeds, (size_t)32 * query_ct_count, cudaMemcpyHostToDevice, s));
+    // Query.ciphertexts arrive as SerializedCiphertext.seeded (SerializedCiphertext.swift:41-49)
+    cudaError_t e = expand_seeded_device(c, c.L, d_poly0, d_seeds, d_query, query_ct_count, s);
+    if (e != cudaSuccess) return cuda_fail(e, "expand seeded query");
+    rc = compute_response_device(h, k, dbs, db_count, shape, d_query, query_ct_count, indices_count, d_resp, s);
+    if (rc) {
+        cudaStreamSynchronize(s);
+        return rc;
+    }
+    // Response ciphertexts leave as .full(polys:skipLSBs:) with Bfv.skipLSBsForDecryption (Bfv+Decrypt.swift:51-110):
+    // poly 0 and poly 1 are packed with different numbers of dropped low bits
+    const size_t pw = (size_t)c.n * sizeof(u64);
+    for (int p = 0; p < 2; ++p) {
+        const size_t bytes = p ? b1 : b0;
+        CK(cudaMemcpy2DAsync(d_polys + (size_t)p * c.n * replies, pw, d_resp + (size_t)p * c.n, 2 * pw, pw, (size_t)replies,
+                             cudaMemcpyDeviceToDevice, s));
+        if ((e = launch_poly_serialize(c, out_codec[p], p ? skip_lsbs_poly1 : skip_lsbs_poly0, d_polys + (size_t)p * c.n * replies,
+                                       d_bytes[p], replies, s)) != cudaSuccess)
+            return cuda_fail(e, "serialize response");
+        CK(cudaMemcpy2DAsync(d_reply + (p ? b0 : 0), b0 + b1, d_bytes[p], bytes, bytes, (size_t)replies, cudaMemcpyDeviceToDevice, s));
+    }
+    CK(cudaMemcpyAsync(out, d_reply, (b0 + b1) * replies, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return HECUDA_OK;
+}
+
 }  // extern "C"

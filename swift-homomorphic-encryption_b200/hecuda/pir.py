@@ -222,6 +222,18 @@ class MulPir:
                                  config.encodingEntrySize)
 
 
+def skipLSBsForDecryption(context) -> List[int]:
+    """Bfv.skipLSBsForDecryption(for:) of a single-modulus ciphertext (Bfv+Decrypt.swift:51-110): how many low bits of
+    poly 0 / poly 1 a reply may drop.  `context` needs degree, plaintextModulus, coefficientModuli."""
+    q0, t = int(context.coefficientModuli[0]), int(context.plaintextModulus)
+    l_prime = (q0 // t).bit_length() - 1 - 3 if q0 >= 2 * t else 0
+    spread = int(8.0 * (2.0 * context.degree / 9.0) ** 0.5)
+    poly0, poly1 = max(l_prime, 0), l_prime - (_ceil_log2(spread) if spread else 0)
+    if poly1 <= 1:
+        poly0, poly1 = max(l_prime + 1, 0), 0
+    return [poly0, poly1]
+
+
 class ProcessedDatabase:
     """ProcessedDatabase<Bfv<UInt64>> resident in HBM (IndexPirDatabase.swift): `count` optional Eval plaintexts."""
 
@@ -253,6 +265,32 @@ class ProcessedDatabase:
             self.close()
         except Exception:
             pass
+
+
+class PirWire:
+    """Request / reply bytes of the index-PIR server (the payloads of the reference's protobuf messages)."""
+
+    @staticmethod
+    def computeResponse(server: "MulPirServer", queryPoly0, querySeeds, evaluationKey: EvaluationKey, indicesCount: int = 1):
+        """Serialized seeded query ciphertexts in, serialized (skipLSBsForDecryption) reply ciphertexts out, one C-ABI call.
+        queryPoly0: (count, byteCount(L rows)) uint8; querySeeds: (count, 32) uint8.  Returns (replies, skipLSBs) with
+        replies of shape (indicesCount, chunkCount, bytes(poly0) + bytes(poly1))."""
+        from . import Bfv
+        ctx = server.context
+        seeds = np.ascontiguousarray(np.asarray(querySeeds, dtype=np.uint8)).reshape(-1, 32)
+        poly0 = np.ascontiguousarray(np.asarray(queryPoly0, dtype=np.uint8)).reshape(seeds.shape[0], -1)
+        if poly0.shape[1] != Bfv.serializationByteCount(ctx, ctx.L):
+            raise HeError(-1, "serializedBufferSizeMismatch")
+        skips = skipLSBsForDecryption(ctx)
+        sizes = [Bfv.serializationByteCount(ctx, 1, s) for s in skips]
+        out = np.empty((indicesCount, server.chunkCount, sum(sizes)), dtype=np.uint8)
+        handles = (C.c_void_p * len(server.databases))(*[db._h for db in server.databases])
+        dims = (C.c_int32 * len(server.parameter.dimensions))(*server.parameter.dimensions)
+        _check(load_library().hecuda_mulpir_compute_response_wire(
+            ctx._h, evaluationKey._h, handles, len(server.databases), dims, len(server.parameter.dimensions), server.chunkCount,
+            poly0.ctypes.data_as(C.c_void_p), seeds.ctypes.data_as(C.c_void_p), seeds.shape[0], indicesCount, skips[0], skips[1],
+            out.ctypes.data_as(C.c_void_p)))
+        return out, skips
 
 
 class PirUtil:

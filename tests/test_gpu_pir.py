@@ -175,3 +175,50 @@ def test_index_pir_production_sizes(n, bits, t, entries, entry_size, compression
         assert np.array_equal(got[0, c], expected[0][c])
     key.close()
     g.close()
+
+
+@pytest.mark.parametrize("n,bits,t,entries,entry_size", [(16, TEST_MODULI_BITS, 1153, 60, 7), (4096, [27, 28, 28], 17, 20000, 3),
+                                                         (4096, [27, 28, 28], 17, 200, 3000)])
+def test_wire_level_response_matches_oracle_and_decrypts(n, bits, t, entries, entry_size):
+    """Serialized seeded query in, serialized skipLSBs reply out (one C-ABI call) == oracle composition; the reply still
+    decrypts to the database entry after the dropped bits come back as zeros (Bfv+Decrypt.swift:51-110)."""
+    from oracle import drbg_oracle as drbg
+    g, o = contexts(n, bits, t)
+    rng = random.Random(entries)
+    config = pir.IndexPirConfig(entries, entry_size, 2, 1, True, "hybridCompression", False)
+    param = pir.MulPir.generateParameter(config, g)
+    oparam = opir.generate_parameter(opir.IndexPirConfig(entries, entry_size, 2, 1, True, "hybridCompression", False), n, t)
+    database = [bytes(rng.randrange(256) for _ in range(entry_size)) for _ in range(entries)]
+    sk, relin = o.keygen(13)
+    key, okeys = load_keys(g, o, sk, relin, param.evaluationKeyConfig.galoisElements)
+    server = pir.MulPirServer(param, g, [pir.MulPirServer.process(database, g, param)])
+    index = rng.randrange(entries)
+    # a seeded query: c1 comes from the seed, c0 = Delta m + e - c1 s is built with the oracle's secret key
+    query = opir.generate_query(o, oparam, [index], sk, 900)
+    seeds = np.random.default_rng(5).integers(0, 256, size=(len(query), 32), dtype=np.uint8)
+    seeded = []
+    for ct, seed in zip(query, seeds):
+        a_eval = drbg.random_poly(n, o.q, seed.tobytes())
+        c1 = orc.ntt_inverse(n, o.q, a_eval)
+        # keep the encrypted message: c0' = c0 + (c1 - c1') s, computed in Eval format with the secret key
+        s_eval = np.asarray(sk, dtype=np.uint64)[: o.L]
+        delta = orc.poly_op("sub", n, o.q, orc.ntt_forward(n, o.q, ct[1]), a_eval)
+        c0 = orc.poly_op("add", n, o.q, ct[0], orc.ntt_inverse(n, o.q, orc.poly_op("mul", n, o.q, delta, s_eval)))
+        seeded.append((np.frombuffer(opir.serialize_poly(n, o.q, c0), dtype=np.uint8), seed, np.stack([c0, c1])))
+    poly0 = np.stack([s[0] for s in seeded])
+    replies, skips = pir.PirWire.computeResponse(server, poly0, seeds, key)
+    assert skips == opir.skip_lsbs_for_decryption(n, o.q[0], t)
+    expanded = [drbg.expand_seeded_ciphertext(o, s[0].tobytes(), s[1].tobytes()) for s in seeded]
+    for e, s in zip(expanded, seeded):
+        assert np.array_equal(e, s[2])
+    expected = opir.compute_response(o, expanded, 1, okeys, relin, [opir.process_database(o, oparam, database)], oparam)
+    recovered = []
+    for chunk in range(server.chunkCount):
+        ct = expected[0][chunk]
+        want = opir.serialize_poly(n, o.q[:1], ct[0], skips[0]) + opir.serialize_poly(n, o.q[:1], ct[1], skips[1])
+        assert replies[0, chunk].tobytes() == want, chunk
+        half = len(opir.serialize_poly(n, o.q[:1], ct[0], skips[0]))
+        recovered.append(np.stack([opir.load_poly(n, o.q[:1], want[:half], skips[0]), opir.load_poly(n, o.q[:1], want[half:], skips[1])]))
+    assert opir.decrypt_response(o, oparam, [recovered], [index], sk) == [database[index]]
+    key.close()
+    g.close()

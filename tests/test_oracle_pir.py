@@ -211,3 +211,13 @@ def test_poly_serialize_roundtrip_kats(poly, moduli, skip, expected):
     assert pir.load_poly(n, moduli, data, skip).reshape(-1).tolist() == expected
     with pytest.raises(ValueError):   # serializationErrOnWrongBuffer (:21-37)
         pir.load_poly(n, moduli, data + b"\0", skip)
+
+
+@pytest.mark.parametrize("n,q0,t,expected", [
+    (4096, (1 << 27) - 40959, 17, [19, 11]),                    # n_4096_logq_27_28_28_logt_5
+    (8192, (1 << 55) - 311295, (1 << 23) + 16385, [28, 19]),    # n_8192_logq_3x55_logt_24
+])
+def test_skip_lsbs_for_decryption_kats(n, q0, t, expected):
+    """EncryptionParametersTests.predefined KAT column skipLSBs (EncryptionParametersTests.swift:218-252) for the two
+    parameter sets whose moduli are written out in EncryptionParameters.swift:357-367,401-411."""
+    assert pir.skip_lsbs_for_decryption(n, q0, t) == expected

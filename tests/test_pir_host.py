@@ -88,3 +88,16 @@ def test_plaintext_rows_agree_with_oracle(entry_size, dimension_count, encoding)
             assert np.array_equal(octx.plaintext_to_eval(rows[i]), odb.plaintexts[i])
         else:
             assert not rows[i].any()
+
+
+def test_skip_lsbs_for_decryption_matches_oracle_and_kats():
+    cases = [(4096, (1 << 27) - 40959, 17, [19, 11]), (8192, (1 << 55) - 311295, (1 << 23) + 16385, [28, 19])]
+    for n, q0, t, expected in cases:
+        assert pir.skipLSBsForDecryption(SimpleNamespace(degree=n, plaintextModulus=t, coefficientModuli=[q0])) == expected
+    rng = random.Random(2)
+    for _ in range(300):
+        n = 1 << rng.randint(3, 15)
+        q0 = rng.randrange(1 << 10, 1 << 62)
+        t = rng.randrange(2, q0)
+        got = pir.skipLSBsForDecryption(SimpleNamespace(degree=n, plaintextModulus=t, coefficientModuli=[q0]))
+        assert got == opir.skip_lsbs_for_decryption(n, q0, t)
