@@ -84,6 +84,16 @@ def main():
         one()
     latency_ms = (time.perf_counter() - t0) / reps * 1e3
 
+    # the same query as bytes: seeded serialized ciphertexts in, skipLSBs-packed reply out (hecuda_mulpir_compute_response_wire)
+    packed = hecuda.Bfv.serialize(ctx, query[:, 0])
+    seeds = rng.integers(0, 256, size=(query_cts, 32), dtype=np.uint8)
+    for _ in range(3):
+        pir.PirWire.computeResponse(server, packed, seeds, key)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        wire_reply, wire_skips = pir.PirWire.computeResponse(server, packed, seeds, key)
+    wire_latency_ms = (time.perf_counter() - t0) / reps * 1e3
+
     per_thread = 30
     def worker(count=per_thread):
         for _ in range(count):
@@ -119,7 +129,11 @@ def main():
         "config": {"workload": f"N={n}, q=27/28/28 bit, t={t}, entries={entries} x {entry_size} B, dims={param.dimensions}, "
                                f"chunks={chunk_count}, galois={param.evaluationKeyConfig.galoisElements}"},
         "database_plaintexts": count, "database_gb": round(db_bytes / 1e9, 3), "database_upload_s": round(process_s, 2),
-        "latency_ms": round(latency_ms, 3), "threads": threads, "n_gpus": world, "scaling": "weak (one shard per GPU)",
+        "latency_ms": round(latency_ms, 3),
+        "wire": {"latency_ms": round(wire_latency_ms, 3), "request_bytes": int(packed.nbytes + seeds.nbytes),
+                 "reply_bytes": int(wire_reply.nbytes), "skip_lsbs": wire_skips,
+                 "unpacked_request_bytes": int(query.nbytes), "unpacked_reply_bytes": int(2 * n * 8 * chunk_count)},
+        "threads": threads, "n_gpus": world, "scaling": "weak (one shard per GPU)",
         "value": round(qps, 1), "unit": "queries/s",
         "db_scan_gbs_at_value": round(qps * db_bytes / 1e9, 1),
         "gpu_launches": hecuda.kernel_launch_count(),
