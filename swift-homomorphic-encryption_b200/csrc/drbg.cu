@@ -25,28 +25,53 @@ using namespace hecuda::drbg;
 namespace {
 
 __constant__ unsigned char c_sbox[256];
+__constant__ u32w c_te0[256];
 
-// one thread per seed: the (round keys, V) of every 4096-byte segment of its stream
-__global__ void drbg_chain_kernel(const unsigned char *__restrict__ seeds, unsigned char *__restrict__ round_keys,
-                                  u64 *__restrict__ counters, int segments, long long batch) {
-    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= batch) return;
-    unsigned char key[16], rk[kRoundKeyBytes];
-    for (int i = 0; i < 16; ++i) key[i] = 0;
+__device__ __forceinline__ void load_tables(unsigned char *sbox, u32w *te0) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+        sbox[i] = c_sbox[i];
+        te0[i] = c_te0[i];
+    }
+    __syncthreads();
+}
+
+// two lanes per seed walk its chain of segments: both expand the current key, lane p encrypts counter block V + 1 + p,
+// the pair exchanges the blocks by shuffle and absorbs them (ctrDrbgUpdate); lane 0 leaves (round keys, V) of each segment
+__global__ void __launch_bounds__(64) drbg_chain_kernel(const unsigned char *__restrict__ seeds, u32w *__restrict__ round_keys,
+                                                        u64 *__restrict__ counters, int segments, long long batch) {
+    __shared__ unsigned char sbox[256];
+    __shared__ u32w te0[256];
+    load_tables(sbox, te0);
+    const long long b = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 1;
+    const int lane = threadIdx.x & 1;
+    const bool live = b < batch;  // dead pairs still take part in the shuffles
+    const long long seed = live ? b : 0;
+    u32w key[4] = {0, 0, 0, 0}, rk[kRoundKeyWords], blk[4], b0[4], b1[4], provided[8];
     u64 hi = 0, lo = 0;
-    expand_key(key, rk, c_sbox);
-    drbg_update(key, hi, lo, rk, seeds + 32 * b, c_sbox);  // init(entropy:) (:52-59)
-    for (int s = 0; s < segments; ++s) {
-        expand_key(key, rk, c_sbox);
-        unsigned char *dst = round_keys + ((size_t)b * segments + s) * kRoundKeyBytes;
-        for (int i = 0; i < kRoundKeyBytes; ++i) dst[i] = rk[i];
-        counters[2 * ((size_t)b * segments + s)] = hi;
-        counters[2 * ((size_t)b * segments + s) + 1] = lo;
-        // ctrDrbgGenerate(count: 4096) (:71-84): V += 256 blocks, then update with zero additional input
-        const u64 l = lo + kSegmentBlocks;
-        hi += l < lo ? 1 : 0;
-        lo = l;
-        drbg_update(key, hi, lo, rk, nullptr, c_sbox);
+    for (int i = 0; i < 8; ++i) {
+        const unsigned char *p = seeds + 32 * seed + 4 * i;
+        provided[i] = ((u32w)p[0] << 24) | ((u32w)p[1] << 16) | ((u32w)p[2] << 8) | p[3];
+    }
+    for (int s = -1; s < segments; ++s) {  // s = -1: init(entropy:) (NistCtrDrbg.swift:52-59)
+        expand_key(key, rk, sbox);
+        if (s >= 0) {
+            if (live && lane == 0) {
+                u32w *dst = round_keys + ((size_t)b * segments + s) * kRoundKeyWords;
+                for (int i = 0; i < kRoundKeyWords; ++i) dst[i] = rk[i];
+                counters[2 * ((size_t)b * segments + s)] = hi;
+                counters[2 * ((size_t)b * segments + s) + 1] = lo;
+            }
+            const u64 l = lo + kSegmentBlocks;  // ctrDrbgGenerate(count: 4096) advances V by 256 blocks (:71-84)
+            hi += l < lo ? 1 : 0;
+            lo = l;
+        }
+        counter_block(hi, lo, 1 + (u64)lane, blk);
+        encrypt_block(blk, rk, te0, sbox);
+        for (int i = 0; i < 4; ++i) {
+            b0[i] = __shfl_sync(0xffffffffu, blk[i], (threadIdx.x & 30), 32);
+            b1[i] = __shfl_sync(0xffffffffu, blk[i], (threadIdx.x & 30) | 1, 32);
+        }
+        drbg_absorb(key, hi, lo, b0, b1, s < 0 ? provided : nullptr);
     }
 }
 
@@ -56,27 +81,24 @@ struct FillConsts {
 };
 
 // one CTA per segment, one thread per 16-byte block = per coefficient (randomizeUniform, PolyRq+Randomize.swift:58-80)
-__global__ void __launch_bounds__(kSegmentBlocks) drbg_fill_kernel(const unsigned char *__restrict__ round_keys,
+__global__ void __launch_bounds__(kSegmentBlocks) drbg_fill_kernel(const u32w *__restrict__ round_keys,
                                                                    const u64 *__restrict__ counters, u64 *__restrict__ out,
                                                                    const __grid_constant__ FillConsts c, int n, int segments) {
     __shared__ unsigned char sbox[256];
-    __shared__ unsigned char rk[kRoundKeyBytes];
+    __shared__ u32w te0[256];
+    __shared__ u32w rk[kRoundKeyWords];
     const long long b = blockIdx.y;
     const int s = blockIdx.x;
-    sbox[threadIdx.x] = c_sbox[threadIdx.x];
-    if (threadIdx.x < kRoundKeyBytes) rk[threadIdx.x] = round_keys[((size_t)b * segments + s) * kRoundKeyBytes + threadIdx.x];
-    __syncthreads();
+    if (threadIdx.x < kRoundKeyWords) rk[threadIdx.x] = round_keys[((size_t)b * segments + s) * kRoundKeyWords + threadIdx.x];
+    load_tables(sbox, te0);
     const long long k = (long long)s * kSegmentBlocks + threadIdx.x;
     if (k >= (long long)c.rows * n) return;
-    unsigned char block[16];
-    counter_block(counters[2 * ((size_t)b * segments + s)], counters[2 * ((size_t)b * segments + s) + 1], 1 + threadIdx.x, block);
-    encrypt_block(block, rk, sbox);
-    u64 lo = 0, hi = 0;  // UInt128(littleEndianBytes:)
-#pragma unroll
-    for (int i = 7; i >= 0; --i) {
-        lo = (lo << 8) | block[i];
-        hi = (hi << 8) | block[8 + i];
-    }
+    u32w blk[4];
+    counter_block(counters[2 * ((size_t)b * segments + s)], counters[2 * ((size_t)b * segments + s) + 1], 1 + (u64)threadIdx.x, blk);
+    encrypt_block(blk, rk, te0, sbox);
+    // UInt128(littleEndianBytes:) of the 16 output bytes: byte i of the block is bits 8i.. of the value
+    const u64 lo = (u64)__byte_perm(blk[0], 0, 0x0123) | ((u64)__byte_perm(blk[1], 0, 0x0123) << 32);
+    const u64 hi = (u64)__byte_perm(blk[2], 0, 0x0123) | ((u64)__byte_perm(blk[3], 0, 0x0123) << 32);
     const int row = (int)(k / n);
     out[(size_t)b * c.rows * n + k] = (u64)((((u128)hi << 64) | lo) % c.p[row]);
 }
@@ -86,19 +108,21 @@ cudaError_t random_polys_device(const Context &c, int l, const unsigned char *d_
     int device = 0;
     cudaGetDevice(&device);
     unsigned char sbox[256];
-    make_sbox(sbox);
-    cudaError_t e = cudaMemcpyToSymbolAsync(c_sbox, sbox, 256, 0, cudaMemcpyHostToDevice, s);  // per device, cheap
+    u32w te0[256];
+    make_tables(sbox, te0);
+    cudaError_t e = cudaMemcpyToSymbolAsync(c_sbox, sbox, sizeof(sbox), 0, cudaMemcpyHostToDevice, s);  // per device, cheap
+    if (e == cudaSuccess) e = cudaMemcpyToSymbolAsync(c_te0, te0, sizeof(te0), 0, cudaMemcpyHostToDevice, s);
     if (e != cudaSuccess) return e;
-    e = cudaStreamSynchronize(s);  // `sbox` lives on this stack frame
+    e = cudaStreamSynchronize(s);  // the tables live on this stack frame
     if (e != cudaSuccess) return e;
     const int segments = (int)(((size_t)l * c.n * 16 + kSegmentBytes - 1) / kSegmentBytes);
-    unsigned char *d_rk = nullptr;
+    u32w *d_rk = nullptr;
     u64 *d_ctr = nullptr;
-    e = cudaMallocAsync((void **)&d_rk, (size_t)batch * segments * kRoundKeyBytes, s);
+    e = cudaMallocAsync((void **)&d_rk, (size_t)batch * segments * kRoundKeyWords * sizeof(u32w), s);
     if (e == cudaSuccess) e = cudaMallocAsync((void **)&d_ctr, (size_t)batch * segments * 2 * sizeof(u64), s);
     if (e == cudaSuccess) {
         ++g_kernel_launches;
-        drbg_chain_kernel<<<(unsigned)((batch + 31) / 32), 32, 0, s>>>(d_seeds, d_rk, d_ctr, segments, batch);
+        drbg_chain_kernel<<<(unsigned)((batch + 31) / 32), 64, 0, s>>>(d_seeds, d_rk, d_ctr, segments, batch);
         e = cudaGetLastError();
     }
     FillConsts fc;
@@ -108,13 +132,13 @@ cudaError_t random_polys_device(const Context &c, int l, const unsigned char *d_
         const int64_t part = std::min<int64_t>(batch - done, 65535);
         ++g_kernel_launches;
         drbg_fill_kernel<<<dim3((unsigned)segments, (unsigned)part), kSegmentBlocks, 0, s>>>(
-            d_rk + (size_t)done * segments * kRoundKeyBytes, d_ctr + (size_t)done * segments * 2, d_out + (size_t)done * l * c.n, fc,
+            d_rk + (size_t)done * segments * kRoundKeyWords, d_ctr + (size_t)done * segments * 2, d_out + (size_t)done * l * c.n, fc,
             (int)c.n, segments);
         e = cudaGetLastError();
         done += part;
     }
     if (d_rk) {
-        cudaMemsetAsync(d_rk, 0, (size_t)batch * segments * kRoundKeyBytes, s);  // key material
+        cudaMemsetAsync(d_rk, 0, (size_t)batch * segments * kRoundKeyWords * sizeof(u32w), s);  // key material
         cudaFreeAsync(d_rk, s);
     }
     if (d_ctr) cudaFreeAsync(d_ctr, s);

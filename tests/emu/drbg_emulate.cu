@@ -14,30 +14,38 @@ using namespace hecuda::drbg;
 int main(int argc, char **argv) {
     if (argc < 3 || std::strlen(argv[1]) != 64) return 2;
     unsigned char seed[32], sbox[256];
+    u32w te0[256];
     for (int i = 0; i < 32; ++i) {
         unsigned v = 0;
         std::sscanf(argv[1] + 2 * i, "%2x", &v);
         seed[i] = (unsigned char)v;
     }
     const long count = std::atol(argv[2]);
-    make_sbox(sbox);
-    unsigned char key[16] = {0}, rk[kRoundKeyBytes];
+    make_tables(sbox, te0);
+    u32w key[4] = {0, 0, 0, 0}, rk[kRoundKeyWords], provided[8], b0[4], b1[4];
+    for (int i = 0; i < 8; ++i)
+        provided[i] = ((u32w)seed[4 * i] << 24) | ((u32w)seed[4 * i + 1] << 16) | ((u32w)seed[4 * i + 2] << 8) | seed[4 * i + 3];
     u64 hi = 0, lo = 0;
-    expand_key(key, rk, sbox);
-    drbg_update(key, hi, lo, rk, seed, sbox);
     std::vector<unsigned char> out;
-    while ((long)out.size() < count) {  // one 4096-byte segment per iteration, exactly like the two kernels
+    for (int s = -1; (long)out.size() < count; ++s) {  // the same loop as drbg_chain_kernel, both lanes in turn
         expand_key(key, rk, sbox);
-        for (int i = 0; i < kSegmentBlocks; ++i) {
-            unsigned char block[16];
-            counter_block(hi, lo, 1 + (u64)i, block);
-            encrypt_block(block, rk, sbox);
-            out.insert(out.end(), block, block + 16);
+        if (s >= 0) {
+            for (int i = 0; i < kSegmentBlocks; ++i) {  // drbg_fill_kernel
+                u32w blk[4];
+                counter_block(hi, lo, 1 + (u64)i, blk);
+                encrypt_block(blk, rk, te0, sbox);
+                for (int w = 0; w < 4; ++w)
+                    for (int k = 3; k >= 0; --k) out.push_back((unsigned char)(blk[w] >> (8 * k)));
+            }
+            const u64 l = lo + kSegmentBlocks;
+            hi += l < lo ? 1 : 0;
+            lo = l;
         }
-        const u64 l = lo + kSegmentBlocks;
-        hi += l < lo ? 1 : 0;
-        lo = l;
-        drbg_update(key, hi, lo, rk, nullptr, sbox);
+        counter_block(hi, lo, 1, b0);
+        counter_block(hi, lo, 2, b1);
+        encrypt_block(b0, rk, te0, sbox);
+        encrypt_block(b1, rk, te0, sbox);
+        drbg_absorb(key, hi, lo, b0, b1, s < 0 ? provided : nullptr);
     }
     for (long i = 0; i < count; ++i) std::printf("%02x", out[i]);
     std::printf("\n");
