@@ -215,14 +215,15 @@ int32_t hecuda_poly_load(const hecuda_context *h, int32_t base, const uint8_t *s
     cudaStream_t s = g.w->stream;
     unsigned char *d_in = nullptr;
     u64 *d_out = nullptr;
-    CK(cudaMallocAsync((void **)&d_in, in_bytes, s));
-    CK(cudaMallocAsync((void **)&d_out, out_words * sizeof(u64), s));
-    cudaError_t e = cudaMemcpyAsync(d_in, serialized, in_bytes, cudaMemcpyHostToDevice, s);
+    cudaError_t e = cudaMallocAsync((void **)&d_in, in_bytes, s);
+    if (e == cudaSuccess) e = cudaMallocAsync((void **)&d_out, out_words * sizeof(u64), s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_in, serialized, in_bytes, cudaMemcpyHostToDevice, s);
     if (e == cudaSuccess) e = launch_poly_load(*h->ctx, c, skip_lsbs, d_in, d_out, polys, s);
     if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, out_words * sizeof(u64), cudaMemcpyDeviceToHost, s);
-    cudaFreeAsync(d_in, s);
-    cudaFreeAsync(d_out, s);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (d_in) cudaFreeAsync(d_in, s);
+    if (d_out) cudaFreeAsync(d_out, s);
+    const cudaError_t e2 = cudaStreamSynchronize(s);
+    if (e == cudaSuccess) e = e2;
     return e == cudaSuccess ? HECUDA_OK : cuda_fail(e, "poly_load");
 }
 
@@ -237,14 +238,15 @@ int32_t hecuda_poly_serialize(const hecuda_context *h, int32_t base, const uint6
     cudaStream_t s = g.w->stream;
     unsigned char *d_out = nullptr;
     u64 *d_in = nullptr;
-    CK(cudaMallocAsync((void **)&d_in, in_words * sizeof(u64), s));
-    CK(cudaMallocAsync((void **)&d_out, out_bytes, s));
-    cudaError_t e = cudaMemcpyAsync(d_in, in, in_words * sizeof(u64), cudaMemcpyHostToDevice, s);
+    cudaError_t e = cudaMallocAsync((void **)&d_in, in_words * sizeof(u64), s);
+    if (e == cudaSuccess) e = cudaMallocAsync((void **)&d_out, out_bytes, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_in, in, in_words * sizeof(u64), cudaMemcpyHostToDevice, s);
     if (e == cudaSuccess) e = launch_poly_serialize(*h->ctx, c, skip_lsbs, d_in, d_out, polys, s);
     if (e == cudaSuccess) e = cudaMemcpyAsync(serialized, d_out, out_bytes, cudaMemcpyDeviceToHost, s);
-    cudaFreeAsync(d_in, s);
-    cudaFreeAsync(d_out, s);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (d_in) cudaFreeAsync(d_in, s);
+    if (d_out) cudaFreeAsync(d_out, s);
+    const cudaError_t e2 = cudaStreamSynchronize(s);
+    if (e == cudaSuccess) e = e2;
     return e == cudaSuccess ? HECUDA_OK : cuda_fail(e, "poly_serialize");
 }
 

@@ -195,13 +195,13 @@ int32_t hecuda_poly_random_from_seed(const hecuda_context *h, const uint8_t *see
     unsigned char *d_seeds = nullptr;
     u64 *d_out = nullptr;
     const size_t words = (size_t)l * c.n * batch;
-    CK(cudaMallocAsync((void **)&d_seeds, (size_t)32 * batch, s));
-    CK(cudaMallocAsync((void **)&d_out, words * sizeof(u64), s));
-    cudaError_t e = cudaMemcpyAsync(d_seeds, seeds, (size_t)32 * batch, cudaMemcpyHostToDevice, s);
+    cudaError_t e = cudaMallocAsync((void **)&d_seeds, (size_t)32 * batch, s);
+    if (e == cudaSuccess) e = cudaMallocAsync((void **)&d_out, words * sizeof(u64), s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_seeds, seeds, (size_t)32 * batch, cudaMemcpyHostToDevice, s);
     if (e == cudaSuccess) e = random_polys_device(c, l, d_seeds, d_out, batch, s);
     if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, words * sizeof(u64), cudaMemcpyDeviceToHost, s);
-    cudaFreeAsync(d_seeds, s);
-    cudaFreeAsync(d_out, s);
+    if (d_seeds) cudaFreeAsync(d_seeds, s);
+    if (d_out) cudaFreeAsync(d_out, s);
     cudaError_t e2 = cudaStreamSynchronize(s);
     if (e == cudaSuccess) e = e2;
     return e == cudaSuccess ? HECUDA_OK : cuda_fail(e, "poly_random_from_seed");
