@@ -47,6 +47,25 @@ using namespace hecuda::api;
 namespace hecuda {
 namespace api {
 
+cudaError_t wait_stream(cudaStream_t s) {
+    static const bool blocking = [] {
+        const char *env = std::getenv("HECUDA_BLOCKING_SYNC");
+        return env && env[0] == '1';
+    }();
+    if (!blocking) return cudaStreamSynchronize(s);
+    thread_local cudaEvent_t event = nullptr;
+    thread_local int event_device = -1;
+    int device = 0;
+    cudaError_t e = cudaGetDevice(&device);
+    if (e != cudaSuccess) return e;
+    if (!event || event_device != device) {
+        if ((e = cudaEventCreateWithFlags(&event, cudaEventBlockingSync | cudaEventDisableTiming)) != cudaSuccess) return e;
+        event_device = device;
+    }
+    if ((e = cudaEventRecord(event, s)) != cudaSuccess) return e;
+    return cudaEventSynchronize(event);
+}
+
 int32_t check_ctx(const hecuda_context *h) {
     if (!h || !h->ctx) return fail(HECUDA_ERR_INVALID_ARGUMENT, "invalidContext: null context");
     int dev = -1;

@@ -224,7 +224,7 @@ int32_t expand_device(const hecuda_context *h, const hecuda_evk *k, const u64 *d
     CK(tmp.alloc(&scratch, galois_scratch_words(c, l) * (size_t)chunk));
     CK(tmp.alloc_bytes((void **)&d_steps, plan.steps.size() * sizeof(ExpandStep)));
     CK(cudaMemcpyAsync(d_steps, plan.steps.data(), plan.steps.size() * sizeof(ExpandStep), cudaMemcpyHostToDevice, s));
-    CK(cudaStreamSynchronize(s));  // plan.steps is a pageable temporary
+    CK(wait_stream(s));  // plan.steps is a pageable temporary
     const RowConsts rc = row_consts(c, l);
     const int threads = n >= 256 ? 256 : (n < 32 ? 32 : (int)n);
     const u64 *cur = d_in;  // the active roots are a prefix of the input (only the last one can be a single output)
@@ -478,11 +478,11 @@ int32_t hecuda_mulpir_expand(const hecuda_context *h, const hecuda_evk *k, const
     CK(cudaMemcpyAsync(d_in, cts, ct_words * ct_count * sizeof(u64), cudaMemcpyHostToDevice, s));
     rc = expand_device(h, k, d_in, ct_count, output_count, d_out, s);
     if (rc) {
-        cudaStreamSynchronize(s);
+        wait_stream(s);
         return rc;
     }
     CK(cudaMemcpyAsync(out, d_out, ct_words * output_count * sizeof(u64), cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
+    CK(wait_stream(s));
     return HECUDA_OK;
 }
 
@@ -518,11 +518,11 @@ int32_t hecuda_mulpir_compute_response(const hecuda_context *h, const hecuda_evk
     CK(cudaMemcpyAsync(d_query, query, ct_words * query_ct_count * sizeof(u64), cudaMemcpyHostToDevice, s));
     rc = compute_response_device(h, k, dbs, db_count, shape, d_query, query_ct_count, indices_count, d_out, s);
     if (rc) {
-        cudaStreamSynchronize(s);
+        wait_stream(s);
         return rc;
     }
     CK(cudaMemcpyAsync(out, d_out, out_words * sizeof(u64), cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
+    CK(wait_stream(s));
     return HECUDA_OK;
 }
 
@@ -566,7 +566,7 @@ int32_t hecuda_mulpir_compute_response_wire(const hecuda_context *h, const hecud
     if (e != cudaSuccess) return cuda_fail(e, "expand seeded query");
     rc = compute_response_device(h, k, dbs, db_count, shape, d_query, query_ct_count, indices_count, d_resp, s);
     if (rc) {
-        cudaStreamSynchronize(s);
+        wait_stream(s);
         return rc;
     }
     // Response ciphertexts leave as .full(polys:skipLSBs:) with Bfv.skipLSBsForDecryption (Bfv+Decrypt.swift:51-110):
@@ -582,7 +582,7 @@ int32_t hecuda_mulpir_compute_response_wire(const hecuda_context *h, const hecud
         CK(cudaMemcpy2DAsync(d_reply + (p ? b0 : 0), b0 + b1, d_bytes[p], bytes, bytes, (size_t)replies, cudaMemcpyDeviceToDevice, s));
     }
     CK(cudaMemcpyAsync(out, d_reply, (b0 + b1) * replies, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
+    CK(wait_stream(s));
     return HECUDA_OK;
 }
 

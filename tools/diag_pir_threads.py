@@ -48,7 +48,8 @@ for e in param.evaluationKeyConfig.galoisElements:
 query = uniform(MOD[:L], (1, 2))
 for _ in range(3):
     server.computeResponse(query, key)
-for threads in (1, 2, 4, 8):
+only = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+for threads in ((1, 2, 4, 8) if not only else (only, only, 4, only)):
     def worker():
         for _ in range(10):
             server.computeResponse(query, key)
