@@ -1,5 +1,5 @@
 #!/bin/bash
-# two processes, one per GPU, concurrently: plain vs blocking waits, 4 vs 8 threads
+# two PIR server processes, one per GPU, at once (run with gpurun --gpus 2): spinning vs blocking waits
 mkdir -p gpurun_out
 run2() { # label env threads
   ( env $2 timeout 120 python tools/diag_pir_threads.py plain 0 $3 2>&1 | sed "s/^/[$1 gpu0] /" ) &
@@ -8,6 +8,6 @@ run2() { # label env threads
 {
 run2 spin X=1 8
 run2 block HECUDA_BLOCKING_SYNC=1 8
-nproc; cat /sys/fs/cgroup/cpu.max 2>/dev/null; python -c "import os;print(len(os.sched_getaffinity(0)))"
+nproc; cat /sys/fs/cgroup/cpu.max 2>/dev/null
 } > gpurun_out/diag_pir_2proc.log 2>&1
 grep -v Warning gpurun_out/diag_pir_2proc.log
