@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Diagnostic: concurrent MulPir queries/s of this process under different process set-ups (see tools/gpu_run15.sh)."""
+"""Diagnostic: concurrent MulPir queries/s of this process under different process set-ups (see tools/gpu_two_process_pir.sh): plain / after importing torch / with an NCCL group; optional thread count."""
 import os
 import sys
 import threading
