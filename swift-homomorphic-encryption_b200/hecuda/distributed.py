@@ -85,6 +85,20 @@ def broadcast_key_bytes(relin_key_host, shape, src: int = 0) -> np.ndarray:
     return t.numpy().view(np.uint64)
 
 
+def broadcast_galois_keys_bytes(galois_keys_host, elements, shape, src: int = 0) -> dict:
+    """Host-side (gloo) variant for the Galois keys of an evaluation key: `elements` (the EvaluationKeyConfig) is known on
+    every rank, the key material only on rank `src`.  Returns {element: key} on every rank."""
+    return {int(e): broadcast_key_bytes(None if galois_keys_host is None else galois_keys_host[e], shape, src=src)
+            for e in elements}
+
+
+def shard_databases(entry_count: int, rank: int, world: int) -> Tuple[int, int]:
+    """The entries [lo, hi) of an index-PIR database that rank `rank` serves: one contiguous shard per GPU, like the
+    reference's offline KeywordDatabase sharding (KeywordDatabase.swift:56-110); a query for entry i goes to the rank
+    whose range contains it and is answered there without any exchange."""
+    return shard_range(entry_count, rank, world)
+
+
 def sharded_apply(fn: Callable[..., np.ndarray], *batched_inputs: np.ndarray, gather: bool = True):
     """Runs `fn` on this rank's contiguous slice of every batched input; optionally all-gathers the outputs.
 

@@ -58,6 +58,26 @@ def _worker(rank, world, port, out_dir):
     rk = hd.broadcast_key_bytes(rk, shape, src=0).reshape(shape)
     prod = hd.sharded_apply(lambda x, y: ctx.mul(x, y, threads=1), a, b)
     relin = hd.sharded_apply(lambda x: ctx.relinearize(x, rk, threads=1), prod)
+    # PIR: one database shard per rank, the client's Galois keys broadcast once, every query answered on its shard
+    from oracle import pir_oracle as opir
+    entries, entry_size = 90, 3
+    lo, hi = hd.shard_databases(entries, rank, world)
+    pctx = orc.Context(16, orc.generate_primes([55, 52, 62, 58], False, 16), 1153)
+    oparam = opir.generate_parameter(opir.IndexPirConfig(hi - lo, entry_size, 2, 1, False, "noCompression", False), 16, 1153)
+    database = [bytes([(7 * i + k) % 256 for k in range(entry_size)]) for i in range(entries)]
+    sk, prk = pctx.keygen(9)
+    gshape = (pctx.L, 2, pctx.L + 1, 16)
+    gkeys = {e: pctx.galois_keygen(40 + e, sk, e) for e in oparam.galois_elements} if rank == 0 else None
+    gkeys = {e: k.reshape(gshape) for e, k in hd.broadcast_galois_keys_bytes(gkeys, oparam.galois_elements, gshape, 0).items()}
+    prk = hd.broadcast_key_bytes(prk if rank == 0 else None, gshape, src=0).reshape(gshape)
+    shard = opir.process_database(pctx, oparam, database[lo:hi])
+    answers = {}
+    for index in (3, 44, 45, 89):
+        if lo <= index < hi:
+            query = opir.generate_query(pctx, oparam, [index - lo], sk, 300 + index)
+            reply = opir.compute_response(pctx, query, 1, gkeys, prk, [shard], oparam)
+            answers[index] = opir.decrypt_response(pctx, oparam, reply, [index - lo], sk)[0]
+    np.save(os.path.join(out_dir, f"pir_{rank}.npy"), np.array([[i] + list(v) for i, v in answers.items()], dtype=np.int64))
     np.save(os.path.join(out_dir, f"relin_{rank}.npy"), relin)
     np.save(os.path.join(out_dir, f"key_{rank}.npy"), rk)
     dist.barrier()
@@ -78,6 +98,11 @@ def test_two_rank_gloo_pipeline(tmp_path):
     b = orc.fill_uniform(2, ctx.q, n, 7 * 2 * L).reshape(7, 2, L, n)
     rk = ctx.keygen(5)[1]
     expect = ctx.relinearize(ctx.mul(a, b), rk)
+    served = {}
+    for r in range(world):
+        for row in np.load(tmp_path / f"pir_{r}.npy"):
+            served[int(row[0])] = bytes(int(v) for v in row[1:])
+    assert served == {i: bytes([(7 * i + k) % 256 for k in range(3)]) for i in (3, 44, 45, 89)}
     for r in range(world):
         assert np.array_equal(np.load(tmp_path / f"key_{r}.npy"), rk)
         assert np.array_equal(np.load(tmp_path / f"relin_{r}.npy"), expect)
