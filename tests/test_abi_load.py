@@ -59,3 +59,33 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h", ".cpp")):
                 src = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "he_oracle" not in src and "from oracle" not in src and "import oracle" not in src, f
+
+
+def _build_c_example(tmp_path):
+    import shutil
+    import subprocess
+    gcc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else shutil.which("gcc")
+    libdir = os.path.join(ROOT, "swift-homomorphic-encryption_b200")
+    out = str(tmp_path / "multiply_relinearize")
+    subprocess.check_call([gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-O1", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "multiply_relinearize.c"), "-L" + libdir, "-lhecuda",
+                           "-Wl,-rpath," + libdir, "-o", out])
+    return out
+
+
+def test_header_is_valid_c99_and_example_links(tmp_path):
+    """include/hecuda.h is a C header (the reference's FFI is C: Sources/CUtil): a strict C99 client compiles and links."""
+    import subprocess
+    exe = _build_c_example(tmp_path)
+    import torch
+    if not torch.cuda.is_available():
+        run = subprocess.run([exe], capture_output=True, text=True)
+        assert run.returncode != 0 and "no CUDA device" in run.stderr   # fails loudly: no CPU fallback
+
+
+@pytest.mark.gpu
+def test_c_example_runs_on_gpu(tmp_path):
+    import subprocess
+    run = subprocess.run([_build_c_example(tmp_path)], capture_output=True, text=True)
+    assert run.returncode == 0, run.stderr
+    assert "16 products" in run.stdout
