@@ -103,13 +103,25 @@ def host_threads():
         return max(1, os.cpu_count() or 1)
 
 
+def cpu_quota():
+    """CPU bandwidth limit of this container in cores (cgroup v2 cpu.max), or None when unlimited / unknown."""
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        return None if quota == "max" else max(1, -(-int(quota) // int(period)))
+    except Exception:
+        return None
+
+
 def best_thread_count(ctx, n, L):
-    """All logical CPUs or half of them (one per physical core), whichever runs the oracle faster on a short probe --
-    the CPU baseline should get its best configuration."""
+    """All logical CPUs, half of them (one per physical core) or the container's CPU quota, whichever runs the oracle
+    fastest on a short probe -- the CPU baseline should get its best configuration."""
     from oracle import oracle as orc
 
     full = host_threads()
-    candidates = sorted({full, max(1, full // 2)}, reverse=True)
+    candidates = {full, max(1, full // 2)}
+    if cpu_quota():
+        candidates.add(min(full, cpu_quota()))
+    candidates = sorted(candidates, reverse=True)
     best, best_rate = full, 0.0
     for c in candidates:
         k = 2 * c
@@ -175,7 +187,7 @@ def run_reference(args):
         "dtype": "u64", "data": "synthetic",
         "config": {"workload": f"{args.workload}: Bfv<UInt64> ct*ct multiply N={n}, {len(moduli)} coefficient moduli "
                                f"(L={L}), CPU sample of {sample} ciphertext pairs per step"},
-        "cpu_baseline": {"value": value, "unit": "mult/s", "cores": cores, "kind": "port",
+        "cpu_baseline": {"value": value, "unit": "mult/s", "cores": cores, "kind": "port", "cpu_quota_cores": cpu_quota(),
                          "sample": f"{sample} pairs/step x {args.steps} steps, OpenMP over pairs, C restatement of the "
                                    "Swift reference (no Swift toolchain on this box)"},
         "e2e": {"value": value, "unit": "mult/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -422,7 +434,7 @@ def main():
         cpu = None
         if not args.no_cpu_baseline:
             v, cores, sample, dt = cpu_reference_throughput(n, moduli, t)
-            cpu = {"value": v, "unit": "mult/s", "cores": cores, "kind": "port",
+            cpu = {"value": v, "unit": "mult/s", "cores": cores, "kind": "port", "cpu_quota_cores": cpu_quota(),
                    "sample": f"{sample} ciphertext pairs of the same workload in {dt:.1f} s, OpenMP over pairs "
                              "(C restatement of the Swift reference; no Swift toolchain on this box)"}
         line = {
