@@ -6,6 +6,7 @@
 #include <cstring>
 
 #include "hostmath.hpp"
+#include "ntt_fast.cuh"
 
 namespace hecuda {
 using namespace host;
@@ -36,8 +37,8 @@ static bool build_slot(HostSlot &hs, u64 p, int64_t n, int logn, u64 t, std::vec
     d.bits = bit_length(p);
     d.s_prod = d.bits - 2;
     d.mu_prod = (u64)(((u128)1 << (d.bits + 62)) / p);
-    d.red_shift = d.bits > 7 ? d.bits - 7 : 0;
-    d.red_recip = (u32)((((u128)1) << (d.red_shift + 18)) / p);
+    d.red_shift = d.bits > 12 ? d.bits - 12 : 0;
+    d.red_recip = (u32)((((u128)1) << (d.red_shift + 32)) / p);
     const u64 psi = min_primitive_root(2 * (u64)n, p);
     const u64 psi_inv = invmod(psi, p);
     hs.roots.assign(n, 1);
@@ -108,6 +109,8 @@ Context *Context::create(int64_t n, const u64 *coeff_moduli, int nmod, u64 t, st
     c->L = nmod - 1;
     c->t = t;
     cudaGetDevice(&c->device);
+    c->sm_count = 1;
+    cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device);
     const int L = c->L;
     c->q.assign(coeff_moduli, coeff_moduli + L);
     c->q_ks = coeff_moduli[L];
@@ -128,16 +131,31 @@ Context *Context::create(int64_t n, const u64 *coeff_moduli, int nmod, u64 t, st
     for (int j = 0; j <= L; ++j) slot_mod[c->slot_bsk(j)] = c->bsk[j];
     slot_mod[c->slot_ks()] = c->q_ks;
     const size_t table_bytes = sizeof(ulonglong2) * (size_t)n;
-    if (cudaMalloc(&c->d_pool, table_bytes * 2 * nslots) != cudaSuccess) { err = "cudaMalloc failed for twiddle tables"; delete c; return nullptr; }
-    std::vector<ulonglong2> tw, itw;
+    const bool fast = c->logn >= fast::kMinLogN && c->logn <= fast::kMaxLogN;
+    const int threads = (int)(n / 16);
+    const size_t tr_bytes = fast ? sizeof(ulonglong2) * (size_t)15 * threads : 0;  // transposed line-owning-pass tables
+    const size_t slot_bytes = 2 * (table_bytes + tr_bytes);
+    if (cudaMalloc(&c->d_pool, slot_bytes * nslots) != cudaSuccess) { err = "cudaMalloc failed for twiddle tables"; delete c; return nullptr; }
+    std::vector<ulonglong2> tw, itw, tr(15 * (size_t)threads), itr(15 * (size_t)threads);
     std::vector<ModSlot> dev_slots(nslots);
     for (int s = 0; s < nslots; ++s) {
         if (!build_slot(c->slots[s], slot_mod[s], n, c->logn, t, tw, itw, err)) { delete c; return nullptr; }
-        char *base = (char *)c->d_pool + table_bytes * 2 * s;
+        char *base = (char *)c->d_pool + slot_bytes * s;
         cudaMemcpy(base, tw.data(), table_bytes, cudaMemcpyHostToDevice);
         cudaMemcpy(base + table_bytes, itw.data(), table_bytes, cudaMemcpyHostToDevice);
         c->slots[s].dev.tw = (const ulonglong2 *)base;
         c->slots[s].dev.itw = (const ulonglong2 *)(base + table_bytes);
+        if (fast) {
+            for (int k = 0; k < 15; ++k)
+                for (int tau = 0; tau < threads; ++tau) {
+                    tr[(size_t)k * threads + tau] = tw[fast::fwd_last_source(c->logn, k, tau)];
+                    itr[(size_t)k * threads + tau] = itw[fast::inv_first_source(c->logn, k, tau)];
+                }
+            cudaMemcpy(base + 2 * table_bytes, tr.data(), tr_bytes, cudaMemcpyHostToDevice);
+            cudaMemcpy(base + 2 * table_bytes + tr_bytes, itr.data(), tr_bytes, cudaMemcpyHostToDevice);
+            c->slots[s].dev.tw_t = (const ulonglong2 *)(base + 2 * table_bytes);
+            c->slots[s].dev.itw_t = (const ulonglong2 *)(base + 2 * table_bytes + tr_bytes);
+        }
         dev_slots[s] = c->slots[s].dev;
     }
     if (cudaMalloc(&c->d_slots, sizeof(ModSlot) * nslots) != cudaSuccess) { err = "cudaMalloc failed"; delete c; return nullptr; }

@@ -27,8 +27,8 @@ struct ModSlot {
     u64 mu_prod;      // floor(2^(bits+62) / p)
     int s_prod;       // bits - 2
     int bits;
-    int red_shift;    // bits - 7                      } small-quotient reduction of lazy NTT values (< 512 p),
-    u32 red_recip;    // floor(2^(red_shift+18) / p)   } ntt_fast.cuh::reduce_small
+    int red_shift;    // max(bits - 12, 0)             } small-quotient reduction of lazy NTT values (< 512 p),
+    u32 red_recip;    // floor(2^(red_shift+32) / p)   } ntt_fast.cuh::reduce_small
     u64 ninv;         // -p^-1 mod 2^64 (Montgomery)
     u64 r64;          // 2^64 mod p
     // Last inverse-NTT stage: x' = (x + y) c0, y' = (x - y) c1 with c0 = s N^-1, c1 = s N^-1 psi^-(N/2)
@@ -39,6 +39,10 @@ struct ModSlot {
     struct InvScale { u64 c0, c0p, c1, c1p; } inv_scale[3];
     const ulonglong2 *tw;     // forward twiddles  [N]
     const ulonglong2 *itw;    // inverse twiddles  [N]  (itw[m+i] = tw[m+i]^-1)
+    // transposed copies for the register-tiled kernels' line-owning pass (ntt_fast.cuh): entry k (< 15) of thread
+    // tau (< N/16) at [k * N/16 + tau]; null when N is outside the fast kernels' range
+    const ulonglong2 *tw_t;
+    const ulonglong2 *itw_t;
 };
 
 enum { kScalePlain = 0, kScaleTMont = 1, kScaleMont = 2 };
@@ -111,6 +115,7 @@ class Context {
     int L;           // ciphertext moduli
     u64 t;
     int device;
+    int sm_count;
     std::vector<u64> q;    // q_0..q_{L-1}
     u64 q_ks;
     std::vector<u64> bsk;  // L+1 primes

@@ -1,7 +1,22 @@
 // ntt_fast.cu -- sm_100a kernels of the register-tiled NTT (see ntt_fast.cuh for the pass structure).
-// One CTA per row, N/16 threads, row staged in padded shared memory between passes, 16-byte coalesced global
-// accesses on the contiguous side.  Rows are dispatched per modulus class (NARROW / WIDE) so each launch runs
-// one specialised instruction stream.
+//
+// Persistent CTAs: each CTA (T = N/16 threads, as many CTAs per SM as 64-register threads allow) walks over rows
+// task = blockIdx.x, blockIdx.x + gridDim.x, ...  For every row
+//   1. TMA in: one thread issues bulk-tensor copies (cp.async.bulk.tensor.2d, 256 lines = 32 KB each, 128-byte
+//      swizzle) that land the row in shared memory and complete on an mbarrier; it also prefetches the CTA's next row
+//      into L2 (cp.async.bulk.prefetch.tensor) and, when the row's modulus differs from the previous row's, bulk-copies
+//      the first N/16 twiddles (all the LB > 0 passes need) into the CTA's shared-memory twiddle cache;
+//   2. 3-4 register passes over the row in shared memory (ntt_fast.cuh), one __syncthreads between passes;
+//   3. TMA out: bulk-tensor copies shared -> global of the finished row (same swizzle, undone by the copy engine);
+//      the next row's TMA-in is issued by the same thread once the copy engine has read the buffer.
+// NARROW / MID / WIDE rows (different lazy-reduction schedules) are mixed in one launch: the row's class selects the
+// instruction stream, rows are ordered class-major so all CTAs walk the classes in step, and there is one tail per
+// NTT call instead of one per class.
+#include <cuda.h>
+
+#include <mutex>
+
+#include <algorithm>
 #include "kernels.cuh"
 #include "ntt_fast.cuh"
 
@@ -14,184 +29,302 @@ struct RowList {          // rows (within a polynomial) that one launch handles
     int count;
     unsigned short row[kMaxRowList];
     unsigned char slot[kMaxRowList];
-    // input side (forward only): source row and whether it must be re-reduced into this row's modulus
-    unsigned char src_row[kMaxRowList];
-    unsigned char reduce[kMaxRowList];
-    long long src_poly_stride;  // words between consecutive input polynomials
+    // 2 bits class | bit 2: re-reduce the gathered input into this row's modulus (forward only)
+    unsigned char flags[kMaxRowList];
+    unsigned char src_row[kMaxRowList];  // input side (forward only): source row
+    long long src_poly_stride;           // words between consecutive input polynomials
 };
 
-template <int LOGN, bool NARROW>
-__global__ void __launch_bounds__((1 << LOGN) / 16, (1024 / ((1 << LOGN) / 16))) ntt_fwd_fast_kernel(const u64 *__restrict__ in, u64 *__restrict__ out,
-                                                                       const ModSlot *__restrict__ slots,
-                                                                       const __grid_constant__ RowList rl) {
-    extern __shared__ u64 sm[];
-    constexpr int P = plan_passes(LOGN);
-    const int tau = threadIdx.x;
-    const int64_t poly = blockIdx.x / rl.count;
-    const int which = blockIdx.x - poly * rl.count;
-    const int64_t row = poly * rl.rows_per_poly + rl.row[which];
-    const ModSlot &S = slots[rl.slot[which]];
-    RowMod m;
-    m.p = S.p;
-    m.two_p = 2 * S.p;
-    m.mu1 = S.mu1;
-    m.np = 0 - S.p;
-    m.four_p = 4 * S.p;
-    m.red_shift = S.red_shift;
-    m.red_recip = S.red_recip;
-    m.tw = S.tw;
-    const u64 *src = in + poly * rl.src_poly_stride + ((int64_t)rl.src_row[which] << LOGN);
-    u64 *dst = out + (row << LOGN);
-    u64 x[16];
-    {
-        constexpr int C = fwd_c(LOGN, 0), LB = fwd_lb(LOGN, 0);
-        load_global<LOGN, LB, C>(x, src, tau);
-        if (rl.reduce[which]) {  // gathered key-switch digit whose source modulus is too large for the lazy range
+// ------------------------------------------------------------------------------------------------ TMA / mbarrier
+__device__ __forceinline__ u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64 *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(u64 *bar, u32 bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity) {
+    asm volatile(
+        "{\n\t.reg .pred done;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 done, [%0], %1;\n\t"
+        "@!done bra WAIT_%=;\n\t}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// 1-D bulk copy global -> shared (twiddle cache), completes `bytes` on the mbarrier
+__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src, u32 bytes, u64 *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// one box (16 words x kBoxLines lines) of the 2-D view {word in line, line} of a buffer, global -> shared
+__device__ __forceinline__ void tma_load_box(void *smem_dst, const CUtensorMap *map, int line, u64 *bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(map), "r"(0), "r"(line), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_box(const CUtensorMap *map, int line, const void *smem_src) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(0), "r"(line),
+                 "r"(smem_u32(smem_src))
+                 : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_box(const CUtensorMap *map, int line) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(0), "r"(line) : "memory");
+}
+__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------------ row bodies
+template <int LOGN, int CLS, int K>
+__device__ __forceinline__ void fwd_row_pass(u64 (&x)[16], u64 *sm, int tau, const RowMod &m, bool reduce_in) {
+    constexpr int P = plan_passes(LOGN), C = fwd_c(LOGN, K), LB = fwd_lb(LOGN, K);
+    load_smem<LOGN, LB, C>(x, sm, tau);
+    if (K == 0 && reduce_in) {  // gathered key-switch digit whose source modulus is too large for the lazy range
 #pragma unroll
-            for (int r = 0; r < 16; ++r) x[r] = barrett64(x[r], m.p, m.mu1);
-        }
-        fwd_pass<LOGN, LB, C, NARROW>(x, tau, m);
-        store_smem<LOGN, LB, C>(x, sm, tau);
+        for (int r = 0; r < 16; ++r) x[r] = barrett64(x[r], 0 - m.np, m.slot->mu1);
     }
+    fwd_pass<LOGN, LB, C, CLS>(x, tau, m);
+    if (K == P - 1) fwd_finish<CLS>(x, m);
+    store_smem<LOGN, LB, C>(x, sm, tau);
+}
+template <int LOGN, int CLS>
+__device__ __forceinline__ void fwd_row(u64 *sm, int tau, const RowMod &m, bool reduce_in) {
+    constexpr int P = plan_passes(LOGN);
+    u64 x[16];
+    fwd_row_pass<LOGN, CLS, 0>(x, sm, tau, m, reduce_in);
     __syncthreads();
-    {
-        constexpr int C = fwd_c(LOGN, 1), LB = fwd_lb(LOGN, 1);
-        load_smem<LOGN, LB, C>(x, sm, tau);
-        fwd_pass<LOGN, LB, C, NARROW>(x, tau, m);
-        store_smem<LOGN, LB, C>(x, sm, tau);
-    }
+    fwd_row_pass<LOGN, CLS, 1>(x, sm, tau, m, false);
     __syncthreads();
     if (P == 4) {
-        constexpr int C = fwd_c(LOGN, 2), LB = fwd_lb(LOGN, 2);
-        load_smem<LOGN, LB, C>(x, sm, tau);
-        fwd_pass<LOGN, LB, C, NARROW>(x, tau, m);
-        store_smem<LOGN, LB, C>(x, sm, tau);
+        fwd_row_pass<LOGN, CLS, (P == 4 ? 2 : 1)>(x, sm, tau, m, false);
         __syncthreads();
     }
-    {
-        constexpr int C = fwd_c(LOGN, P - 1), LB = fwd_lb(LOGN, P - 1);
-        load_smem<LOGN, LB, C>(x, sm, tau);
-        fwd_pass<LOGN, LB, C, NARROW>(x, tau, m);
-        fwd_finish<LOGN, NARROW>(x, m);
-        store_global<LOGN, LB, C>(x, dst, tau);
-    }
+    fwd_row_pass<LOGN, CLS, P - 1>(x, sm, tau, m, false);
 }
 
-template <int LOGN, bool NARROW>
-__global__ void __launch_bounds__((1 << LOGN) / 16, (1024 / ((1 << LOGN) / 16))) ntt_inv_fast_kernel(const u64 *__restrict__ in, u64 *__restrict__ out,
-                                                                       const ModSlot *__restrict__ slots,
-                                                                       const __grid_constant__ RowList rl, int scale_mode) {
-    extern __shared__ u64 sm[];
+template <int LOGN, int CLS, int K>
+__device__ __forceinline__ void inv_row_pass(u64 (&x)[16], u64 *sm, int tau, const RowMod &m) {
+    constexpr int C = inv_c(LOGN, K), LB = inv_lb(LOGN, K);
+    load_smem<LOGN, LB, C>(x, sm, tau);
+    if (CLS == kNarrow && K > 0 && inv_reduce_at(LOGN, K)) inv_reduce(x, m);
+    inv_pass<LOGN, LB, C, CLS, inv_bound_in(LOGN, K)>(x, tau, m);
+    store_smem<LOGN, LB, C>(x, sm, tau);
+}
+template <int LOGN, int CLS>
+__device__ __forceinline__ void inv_row(u64 *sm, int tau, const RowMod &m) {
     constexpr int P = plan_passes(LOGN);
-    const int tau = threadIdx.x;
-    const int64_t poly = blockIdx.x / rl.count;
-    const int which = blockIdx.x - poly * rl.count;
-    const int64_t row = poly * rl.rows_per_poly + rl.row[which];
-    const ModSlot &S = slots[rl.slot[which]];
-    RowMod m;
-    m.p = S.p;
-    m.two_p = 2 * S.p;
-    m.mu1 = S.mu1;
-    m.np = 0 - S.p;
-    m.four_p = 4 * S.p;
-    m.red_shift = S.red_shift;
-    m.red_recip = S.red_recip;
-    m.tw = S.itw;
-    m.c0 = S.inv_scale[scale_mode].c0;
-    m.c0p = S.inv_scale[scale_mode].c0p;
-    m.c1 = S.inv_scale[scale_mode].c1;
-    m.c1p = S.inv_scale[scale_mode].c1p;
-    const u64 *src = in + (row << LOGN);
-    u64 *dst = out + (row << LOGN);
     u64 x[16];
-    {
-        constexpr int C = inv_c(LOGN, 0), LB = inv_lb(LOGN, 0);
-        load_global<LOGN, LB, C>(x, src, tau);
-        inv_pass<LOGN, LB, C, NARROW, inv_bound_in(LOGN, 0)>(x, tau, m);
-        store_smem<LOGN, LB, C>(x, sm, tau);
-    }
+    inv_row_pass<LOGN, CLS, 0>(x, sm, tau, m);
     __syncthreads();
-    {
-        constexpr int C = inv_c(LOGN, 1), LB = inv_lb(LOGN, 1);
-        load_smem<LOGN, LB, C>(x, sm, tau);
-        if (NARROW && inv_reduce_at(LOGN, 1)) inv_reduce<0>(x, m);
-        inv_pass<LOGN, LB, C, NARROW, inv_bound_in(LOGN, 1)>(x, tau, m);
-        store_smem<LOGN, LB, C>(x, sm, tau);
-    }
+    inv_row_pass<LOGN, CLS, 1>(x, sm, tau, m);
     __syncthreads();
     if (P == 4) {
-        constexpr int C = inv_c(LOGN, 2), LB = inv_lb(LOGN, 2);
-        load_smem<LOGN, LB, C>(x, sm, tau);
-        if (NARROW && inv_reduce_at(LOGN, 2)) inv_reduce<0>(x, m);
-        inv_pass<LOGN, LB, C, NARROW, inv_bound_in(LOGN, 2)>(x, tau, m);
-        store_smem<LOGN, LB, C>(x, sm, tau);
+        inv_row_pass<LOGN, CLS, (P == 4 ? 2 : 1)>(x, sm, tau, m);
         __syncthreads();
     }
-    {
-        constexpr int C = inv_c(LOGN, P - 1), LB = inv_lb(LOGN, P - 1);
-        load_smem<LOGN, LB, C>(x, sm, tau);
-        if (NARROW && inv_reduce_at(LOGN, P - 1)) inv_reduce<0>(x, m);
-        inv_pass<LOGN, LB, C, NARROW, inv_bound_in(LOGN, P - 1)>(x, tau, m);
-        store_global<LOGN, LB, C>(x, dst, tau);
+    inv_row_pass<LOGN, CLS, P - 1>(x, sm, tau, m);
+}
+
+// Shared memory of a CTA: [row: N words][twiddle cache: N/16 entries][2 mbarriers].
+template <int LOGN>
+constexpr size_t ntt_smem_bytes() {
+    return sizeof(u64) * ((size_t)1 << LOGN) + sizeof(ulonglong2) * ((size_t)1 << (LOGN - 4)) + 16;
+}
+
+template <int LOGN, bool INVERSE>
+__global__ void __launch_bounds__((1 << LOGN) / 16, (1024 / ((1 << LOGN) / 16)))
+    ntt_rows_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_out,
+                    const ModSlot *__restrict__ slots, const __grid_constant__ RowList rl, const int polys,
+                    const int scale_mode) {
+    extern __shared__ __align__(1024) u64 sm[];  // row first: the 128-byte swizzle wants it 1024-byte aligned
+    constexpr int kLines = (1 << LOGN) / kLineWords;
+    constexpr int kBoxes = kLines > kBoxLines ? kLines / kBoxLines : 1;
+    constexpr int kLinesPerBox = kLines / kBoxes;
+    constexpr u32 kRowBytes = (u32)sizeof(u64) << LOGN, kTwBytes = (u32)sizeof(ulonglong2) << (LOGN - 4);
+    ulonglong2 *tw_cache = reinterpret_cast<ulonglong2 *>(sm + (1 << LOGN));
+    u64 *bar_row = reinterpret_cast<u64 *>(tw_cache + (1 << (LOGN - 4)));
+    u64 *bar_tw = bar_row + 1;
+    const int tau = threadIdx.x;
+    const int tasks = polys * rl.count;  // < 2^31 (checked by the launcher)
+    if (tau == 0) {
+        if (smem_u32(sm) & 1023) __trap();  // dynamic shared memory starts at the window base when there is no static part
+        mbar_init(bar_row, 1);
+        mbar_init(bar_tw, 1);
     }
+    __syncthreads();
+    u32 phase_row = 0, phase_tw = 0;
+    int cached_slot = -1;
+    for (int task = blockIdx.x; task < tasks; task += gridDim.x) {
+        const int which = task / polys;
+        const int poly = task - which * polys;
+        const int flags = rl.flags[which];
+        const int slot = rl.slot[which];
+        const ModSlot &S = slots[slot];
+        // line index (16-word lines) of the row inside the buffer each tensor map describes
+        const int64_t out_word = ((int64_t)poly * rl.rows_per_poly + rl.row[which]) << LOGN;
+        const int64_t in_word = INVERSE ? out_word : (int64_t)poly * rl.src_poly_stride + ((int64_t)rl.src_row[which] << LOGN);
+        const bool new_slot = slot != cached_slot;  // uniform over the CTA
+        cached_slot = slot;
+        if (tau == 0) {
+            // the previous row's TMA-out has finished reading the buffer (wait_group.read below, same thread), and every
+            // thread has passed the barrier that follows its last use of the twiddle cache
+            if (new_slot) {
+                mbar_arrive_expect_tx(bar_tw, kTwBytes);
+                tma_load_1d(tw_cache, INVERSE ? S.itw : S.tw, kTwBytes, bar_tw);
+            }
+            mbar_arrive_expect_tx(bar_row, kRowBytes);
+            const int line = (int)(in_word >> 4);
+#pragma unroll
+            for (int b = 0; b < kBoxes; ++b) tma_load_box(sm + b * kLinesPerBox * kLineWords, &map_in, line + b * kLinesPerBox, bar_row);
+            const int next = task + gridDim.x;
+            if (next < tasks) {
+                const int nw = next / polys;
+                const int np_ = next - nw * polys;
+                const int64_t nword = INVERSE ? ((int64_t)np_ * rl.rows_per_poly + rl.row[nw]) << LOGN
+                                              : (int64_t)np_ * rl.src_poly_stride + ((int64_t)rl.src_row[nw] << LOGN);
+#pragma unroll
+                for (int b = 0; b < kBoxes; ++b) tma_prefetch_box(&map_in, (int)(nword >> 4) + b * kLinesPerBox);
+            }
+        }
+        const int cls = flags & 3;
+        RowMod m;
+        m.np = 0 - S.p;
+        m.kp = cls == kWide ? 2 * S.p : 4 * S.p;
+        m.tw = nullptr;
+        m.tw_s = smem_u32(tw_cache);
+        m.slot = &S;
+        m.scale_mode = INVERSE ? scale_mode : -1;
+        if (new_slot) {
+            mbar_wait(bar_tw, phase_tw);
+            phase_tw ^= 1;
+        }
+        mbar_wait(bar_row, phase_row);
+        phase_row ^= 1;
+#ifndef HE_EXPERIMENT_ONLY_CLASS
+        if (INVERSE) {
+            if (cls == kNarrow) inv_row<LOGN, kNarrow>(sm, tau, m);
+            else if (cls == kMid) inv_row<LOGN, kMid>(sm, tau, m);
+            else inv_row<LOGN, kWide>(sm, tau, m);
+        } else {
+            const bool reduce_in = (flags & 4) != 0;
+            if (cls == kNarrow) fwd_row<LOGN, kNarrow>(sm, tau, m, reduce_in);
+            else if (cls == kMid) fwd_row<LOGN, kMid>(sm, tau, m, reduce_in);
+            else fwd_row<LOGN, kWide>(sm, tau, m, reduce_in);
+        }
+#else  // register-pressure experiments: one class only
+        if (INVERSE) inv_row<LOGN, HE_EXPERIMENT_ONLY_CLASS>(sm, tau, m);
+        else fwd_row<LOGN, HE_EXPERIMENT_ONLY_CLASS>(sm, tau, m, (flags & 4) != 0);
+#endif
+        // ---- TMA out: every thread makes its generic-proxy writes visible to the async proxy, then one thread copies
+        fence_proxy_async_smem();
+        __syncthreads();
+        if (tau == 0) {
+            const int line = (int)(out_word >> 4);
+#pragma unroll
+            for (int b = 0; b < kBoxes; ++b) tma_store_box(&map_out, line + b * kLinesPerBox, sm + b * kLinesPerBox * kLineWords);
+            tma_commit();
+            tma_store_wait_read();  // the buffer may be refilled once the copy engine has read it
+        }
+    }
+    if (tau == 0) tma_store_wait_all();
 }
 
 // ---------------------------------------------------------------------------------------------- launch
-static void build_row_lists(const Context &ctx, const NttRowMap &map, RowList &narrow, RowList &wide) {
-    narrow.rows_per_poly = wide.rows_per_poly = map.rows_per_poly;
-    narrow.count = wide.count = 0;
-    narrow.src_poly_stride = wide.src_poly_stride =
-        map.src_mod ? map.src_poly_stride : (long long)map.rows_per_poly * ctx.n;
-    for (int r = 0; r < map.rows_per_poly; ++r) {
-        const int slot = map.slot[r / map.group];
-        const bool is_narrow = ctx.slots[slot].dev.bits <= kNarrowBits;
-        RowList &l = is_narrow ? narrow : wide;
-        l.row[l.count] = (unsigned short)r;
-        l.slot[l.count] = (unsigned char)slot;
-        l.src_row[l.count] = (unsigned char)(map.src_mod ? r % map.src_mod : r);
-        l.reduce[l.count] = 0;
-        if (map.src_mod) {
-            // inputs are residues mod the source modulus: fine as they are while they stay inside the lazy input range
-            // of the butterflies (< 2p NARROW, < 4p WIDE); otherwise re-reduce on load (Bfv+Keys.swift:168-172)
-            const u64 p = ctx.slots[slot].dev.p, src_p = ctx.slots[map.src_slot[r % map.src_mod]].dev.p;
-            l.reduce[l.count] = (src_p > p && (src_p - 1) / p >= (is_narrow ? 2u : 4u)) ? 1 : 0;
+static void build_row_list(const Context &ctx, const NttRowMap &map, bool inverse, RowList &rl) {
+    rl.rows_per_poly = map.rows_per_poly;
+    rl.count = 0;
+    rl.src_poly_stride = map.src_mod ? map.src_poly_stride : (long long)map.rows_per_poly * ctx.n;
+    // class-major order (the cheap NARROW rows last, so the tail of the launch is made of short rows)
+    for (int cls = kWide; cls >= kNarrow; --cls) {
+        for (int r = 0; r < map.rows_per_poly; ++r) {
+            const int slot = map.slot[r / map.group];
+            if (class_of_bits(ctx.slots[slot].dev.bits) != cls) continue;
+            const int i = rl.count++;
+            rl.row[i] = (unsigned short)r;
+            rl.slot[i] = (unsigned char)slot;
+            rl.src_row[i] = (unsigned char)(map.src_mod && !inverse ? r % map.src_mod : r);
+            int flags = cls;
+            if (map.src_mod && !inverse) {
+                // inputs are residues mod the source modulus: fine as they are while they stay inside the lazy input
+                // range of the butterflies (< 2p NARROW, < 8p MID, < 4p WIDE); otherwise re-reduce on load
+                // (Bfv+Keys.swift:168-172)
+                const u64 p = ctx.slots[slot].dev.p, src_p = ctx.slots[map.src_slot[r % map.src_mod]].dev.p;
+                const u64 room = cls == kNarrow ? 2u : cls == kMid ? 8u : 4u;
+                if (src_p > p && (src_p - 1) / p >= room) flags |= 4;
+            }
+            rl.flags[i] = (unsigned char)flags;
         }
-        ++l.count;
     }
 }
 
-template <int LOGN, bool NARROW, bool INVERSE>
-static cudaError_t launch_class(const Context &ctx, const RowList &rl, const u64 *in, u64 *out, int64_t polys,
-                                int scale_mode, cudaStream_t stream) {
-    if (rl.count == 0 || polys == 0) return cudaSuccess;
-    constexpr int threads = (1 << LOGN) / 16;
-    constexpr size_t smem = sizeof(u64) * smem_words(LOGN);
-    const int64_t blocks = polys * rl.count;
-    if (blocks > 0x7fffffffLL) return cudaErrorInvalidValue;
-    cudaError_t e;
-    ++g_kernel_launches;
-    if (INVERSE) {
-        auto k = ntt_inv_fast_kernel<LOGN, NARROW>;
-        if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-        k<<<(unsigned)blocks, threads, smem, stream>>>(in, out, ctx.d_slots, rl, scale_mode);
-    } else {
-        auto k = ntt_fwd_fast_kernel<LOGN, NARROW>;
-        if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-        k<<<(unsigned)blocks, threads, smem, stream>>>(in, out, ctx.d_slots, rl);
-    }
-    return cudaGetLastError();
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+// 2-D view of a u64 buffer for the row copies: dimension 0 = the 16 words of a 128-byte line, dimension 1 = lines
+static bool make_line_map(CUtensorMap *map, const u64 *base, int logn) {
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc || (reinterpret_cast<uintptr_t>(base) & 15)) return false;
+    const int lines = (1 << logn) / kLineWords;
+    const cuuint64_t dims[2] = {kLineWords, (cuuint64_t)1 << 31};  // extent only bounds the coordinates
+    const cuuint64_t strides[1] = {kLineWords * sizeof(u64)};
+    const cuuint32_t box[2] = {kLineWords, (cuuint32_t)(lines > kBoxLines ? kBoxLines : lines)};
+    const cuuint32_t elem_strides[2] = {1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, const_cast<u64 *>(base), dims, strides, box, elem_strides,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 template <int LOGN, bool INVERSE>
 static cudaError_t launch_logn(const Context &ctx, const NttRowMap &map, const u64 *in, u64 *out, int64_t rows,
                                int scale_mode, cudaStream_t stream) {
     if (rows % map.rows_per_poly) return cudaErrorInvalidValue;
-    RowList narrow, wide;
-    build_row_lists(ctx, map, narrow, wide);
-    const int64_t polys = rows / map.rows_per_poly;
-    cudaError_t e = launch_class<LOGN, true, INVERSE>(ctx, narrow, in, out, polys, scale_mode, stream);
-    if (e != cudaSuccess) return e;
-    return launch_class<LOGN, false, INVERSE>(ctx, wide, in, out, polys, scale_mode, stream);
+    if (rows == 0) return cudaSuccess;
+    if (rows > 0x7fffffffLL) return cudaErrorInvalidValue;
+    RowList rl;
+    build_row_list(ctx, map, INVERSE, rl);
+    if (rl.src_poly_stride % kLineWords) return cudaErrorInvalidValue;
+    CUtensorMap map_in, map_out;
+    if (!make_line_map(&map_in, in, LOGN) || !make_line_map(&map_out, out, LOGN)) return cudaErrorInvalidValue;
+    const int polys = (int)(rows / map.rows_per_poly);
+    constexpr int threads = (1 << LOGN) / 16;
+    constexpr size_t smem = ntt_smem_bytes<LOGN>();
+    auto k = ntt_rows_kernel<LOGN, INVERSE>;
+    static int ctas_per_sm[64] = {0};  // per instantiation and device
+    static std::mutex mu;
+    int per_sm;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        int &c = ctas_per_sm[ctx.device & 63];
+        if (c == 0) {
+            cudaError_t e;
+            if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+            int n = 0;
+            if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, threads, smem)) != cudaSuccess) return e;
+            if (n < 1) return cudaErrorInvalidConfiguration;
+            c = n;
+        }
+        per_sm = c;
+    }
+    const int64_t grid = std::min<int64_t>(rows, (int64_t)ctx.sm_count * per_sm);
+    ++g_kernel_launches;
+    k<<<(unsigned)grid, threads, smem, stream>>>(map_in, map_out, ctx.d_slots, rl, polys, scale_mode);
+    return cudaGetLastError();
 }
 
 bool ntt_fast_supported(const Context &ctx) { return ctx.logn >= kMinLogN && ctx.logn <= kMaxLogN; }

@@ -14,72 +14,67 @@
 using namespace hecuda;
 using namespace hecuda::fast;
 
-// the emulated "registers" of thread tau are x[tau*16 .. tau*16+15]; memory moves use the kernels' own helpers
-template <int LOGN, int LB, int C>
-static void emu_load(std::vector<u64> &x, const u64 *src, int tau, bool smem) {
-    u64(&xr)[16] = *reinterpret_cast<u64(*)[16]>(&x[tau * 16]);
-    if (smem) load_smem<LOGN, LB, C>(xr, src, tau);
-    else load_global<LOGN, LB, C>(xr, src, tau);
-}
-template <int LOGN, int LB, int C>
-static void emu_store(std::vector<u64> &x, u64 *dst, int tau, bool smem) {
-    u64(&xr)[16] = *reinterpret_cast<u64(*)[16]>(&x[tau * 16]);
-    if (smem) store_smem<LOGN, LB, C>(xr, dst, tau);
-    else store_global<LOGN, LB, C>(xr, dst, tau);
-}
-
-template <int LOGN, bool NARROW, int K>
-static void fwd_pass_k(std::vector<u64> &x, std::vector<u64> &sm, const u64 *src, u64 *dst, const RowMod &m) {
+// the emulated "registers" of thread tau are x[tau*16 .. tau*16+15]; the row lives in the kernels' swizzled
+// shared-memory layout for the whole transform, moved in and out line by line exactly like the TMA copies
+template <int LOGN, int CLS, int K>
+static void fwd_pass_k(std::vector<u64> &x, std::vector<u64> &sm, const RowMod &m) {
     constexpr int P = plan_passes(LOGN), T = (1 << LOGN) / 16;
     constexpr int C = fwd_c(LOGN, K), LB = fwd_lb(LOGN, K);
     for (int tau = 0; tau < T; ++tau) {  // phase 1: every thread reads
-        if (K == 0) emu_load<LOGN, LB, C>(x, src, tau, false);
-        else emu_load<LOGN, LB, C>(x, sm.data(), tau, true);
+        u64(&xr)[16] = *reinterpret_cast<u64(*)[16]>(&x[tau * 16]);
+        load_smem<LOGN, LB, C>(xr, sm.data(), tau);
     }
     for (int tau = 0; tau < T; ++tau) {
         u64(&xr)[16] = *reinterpret_cast<u64(*)[16]>(&x[tau * 16]);
-        fwd_pass<LOGN, LB, C, NARROW>(xr, tau, m);
-        if (K == P - 1) fwd_finish<LOGN, NARROW>(xr, m);
+        fwd_pass<LOGN, LB, C, CLS>(xr, tau, m);
+        if (K == P - 1) fwd_finish<CLS>(xr, m);
     }
     for (int tau = 0; tau < T; ++tau) {
-        if (K == P - 1) emu_store<LOGN, LB, C>(x, dst, tau, false);
-        else emu_store<LOGN, LB, C>(x, sm.data(), tau, true);
+        u64(&xr)[16] = *reinterpret_cast<u64(*)[16]>(&x[tau * 16]);
+        store_smem<LOGN, LB, C>(xr, sm.data(), tau);
     }
 }
-template <int LOGN, bool NARROW, int K>
-static void inv_pass_k(std::vector<u64> &x, std::vector<u64> &sm, const u64 *src, u64 *dst, const RowMod &m) {
-    constexpr int P = plan_passes(LOGN), T = (1 << LOGN) / 16;
+template <int LOGN, int CLS, int K>
+static void inv_pass_k(std::vector<u64> &x, std::vector<u64> &sm, const RowMod &m) {
+    constexpr int T = (1 << LOGN) / 16;
     constexpr int C = inv_c(LOGN, K), LB = inv_lb(LOGN, K);
     for (int tau = 0; tau < T; ++tau) {
-        if (K == 0) emu_load<LOGN, LB, C>(x, src, tau, false);
-        else emu_load<LOGN, LB, C>(x, sm.data(), tau, true);
+        u64(&xr)[16] = *reinterpret_cast<u64(*)[16]>(&x[tau * 16]);
+        load_smem<LOGN, LB, C>(xr, sm.data(), tau);
     }
     for (int tau = 0; tau < T; ++tau) {
         u64(&xr)[16] = *reinterpret_cast<u64(*)[16]>(&x[tau * 16]);
-        if (NARROW && K > 0 && inv_reduce_at(LOGN, K)) inv_reduce<0>(xr, m);
-        inv_pass<LOGN, LB, C, NARROW, inv_bound_in(LOGN, K)>(xr, tau, m);
+        if (CLS == kNarrow && K > 0 && inv_reduce_at(LOGN, K)) inv_reduce(xr, m);
+        inv_pass<LOGN, LB, C, CLS, inv_bound_in(LOGN, K)>(xr, tau, m);
     }
     for (int tau = 0; tau < T; ++tau) {
-        if (K == P - 1) emu_store<LOGN, LB, C>(x, dst, tau, false);
-        else emu_store<LOGN, LB, C>(x, sm.data(), tau, true);
+        u64(&xr)[16] = *reinterpret_cast<u64(*)[16]>(&x[tau * 16]);
+        store_smem<LOGN, LB, C>(xr, sm.data(), tau);
     }
 }
 
-template <int LOGN, bool NARROW>
+template <int LOGN, int CLS>
 static void run(bool inverse, const u64 *src, u64 *dst, const RowMod &m) {
     constexpr int P = plan_passes(LOGN), T = (1 << LOGN) / 16;
     std::vector<u64> x(T * 16), sm(smem_words(LOGN), 0xDEADBEEFDEADBEEFull);
+    // "TMA in" with CU_TENSOR_MAP_SWIZZLE_128B: 16-byte chunk c of line l lands at chunk c ^ (l & 7)
+    for (int line = 0; line < T; ++line)
+        for (int c = 0; c < 8; ++c)
+            memcpy(&sm[kLineWords * line + 2 * (c ^ (line & 7))], src + kLineWords * line + 2 * c, 16);
     if (!inverse) {
-        fwd_pass_k<LOGN, NARROW, 0>(x, sm, src, dst, m);
-        fwd_pass_k<LOGN, NARROW, 1>(x, sm, src, dst, m);
-        if (P == 4) fwd_pass_k<LOGN, NARROW, (P == 4 ? 2 : 1)>(x, sm, src, dst, m);
-        fwd_pass_k<LOGN, NARROW, P - 1>(x, sm, src, dst, m);
+        fwd_pass_k<LOGN, CLS, 0>(x, sm, m);
+        fwd_pass_k<LOGN, CLS, 1>(x, sm, m);
+        if (P == 4) fwd_pass_k<LOGN, CLS, (P == 4 ? 2 : 1)>(x, sm, m);
+        fwd_pass_k<LOGN, CLS, P - 1>(x, sm, m);
     } else {
-        inv_pass_k<LOGN, NARROW, 0>(x, sm, src, dst, m);
-        inv_pass_k<LOGN, NARROW, 1>(x, sm, src, dst, m);
-        if (P == 4) inv_pass_k<LOGN, NARROW, (P == 4 ? 2 : 1)>(x, sm, src, dst, m);
-        inv_pass_k<LOGN, NARROW, P - 1>(x, sm, src, dst, m);
+        inv_pass_k<LOGN, CLS, 0>(x, sm, m);
+        inv_pass_k<LOGN, CLS, 1>(x, sm, m);
+        if (P == 4) inv_pass_k<LOGN, CLS, (P == 4 ? 2 : 1)>(x, sm, m);
+        inv_pass_k<LOGN, CLS, P - 1>(x, sm, m);
     }
+    for (int line = 0; line < T; ++line)  // "TMA out": the same swizzle, undone by the copy engine
+        for (int c = 0; c < 8; ++c)
+            memcpy(dst + kLineWords * line + 2 * c, &sm[kLineWords * line + 2 * (c ^ (line & 7))], 16);
 }
 
 int main(int argc, char **argv) {
@@ -103,22 +98,36 @@ int main(int argc, char **argv) {
         pw = host::mulmod(pw, psi, p);
         ipw = host::mulmod(ipw, psi_inv, p);
     }
-    RowMod m;
-    m.p = p;
-    m.two_p = 2 * p;
-    m.mu1 = (u64)(((unsigned __int128)1 << 64) / p);
-    m.np = 0 - p;
-    m.four_p = 4 * p;
-    m.red_shift = host::bit_length(p) > 7 ? host::bit_length(p) - 7 : 0;
-    m.red_recip = (u32)((((unsigned __int128)1) << (m.red_shift + 18)) / p);
-    m.tw = inverse ? itw.data() : tw.data();
+    // transposed tables of the line-owning pass, exactly as context.cu builds them
+    const int threads = n / 16;
+    std::vector<ulonglong2> tr(15 * (size_t)threads), itr(15 * (size_t)threads);
+    for (int k = 0; k < 15; ++k)
+        for (int tau = 0; tau < threads; ++tau) {
+            tr[(size_t)k * threads + tau] = tw[fwd_last_source(logn, k, tau)];
+            itr[(size_t)k * threads + tau] = itw[inv_first_source(logn, k, tau)];
+        }
+    ModSlot slot;
+    memset(&slot, 0, sizeof(slot));
+    slot.p = p;
+    slot.mu1 = (u64)(((unsigned __int128)1 << 64) / p);
+    slot.bits = host::bit_length(p);
+    slot.red_shift = slot.bits > 12 ? slot.bits - 12 : 0;
+    slot.red_recip = (u32)((((unsigned __int128)1) << (slot.red_shift + 32)) / p);
     u64 n_inv = host::invmod((u64)n % p, p);
     if (t) n_inv = host::mulmod(n_inv, t % p, p);
     const u64 n_inv_w = host::mulmod(n_inv, itw[1].x, p);
-    m.c0 = n_inv; m.c0p = host::shoup_factor(n_inv, p);
-    m.c1 = n_inv_w; m.c1p = host::shoup_factor(n_inv_w, p);
-    const bool narrow = host::bit_length(p) <= kNarrowBits;
-#define RUN(L) case L: if (narrow) run<L, true>(inverse, in.data(), out.data(), m); else run<L, false>(inverse, in.data(), out.data(), m); break;
+    slot.inv_scale[0].c0 = n_inv; slot.inv_scale[0].c0p = host::shoup_factor(n_inv, p);
+    slot.inv_scale[0].c1 = n_inv_w; slot.inv_scale[0].c1p = host::shoup_factor(n_inv_w, p);
+    const int cls = class_of_bits(slot.bits);
+    RowMod m;
+    m.np = 0 - p;
+    m.kp = cls == kWide ? 2 * p : 4 * p;
+    m.tw = inverse ? itw.data() : tw.data();
+    slot.tw_t = tr.data();
+    slot.itw_t = itr.data();
+    m.slot = &slot;
+    m.scale_mode = inverse ? 0 : -1;
+#define RUN(L) case L: if (cls == kNarrow) run<L, kNarrow>(inverse, in.data(), out.data(), m); else if (cls == kMid) run<L, kMid>(inverse, in.data(), out.data(), m); else run<L, kWide>(inverse, in.data(), out.data(), m); break;
     switch (logn) { RUN(10) RUN(11) RUN(12) RUN(13) RUN(14) default: return 4; }
     for (int i = 0; i < n; ++i) printf("%llu\n", out[i]);
     return 0;

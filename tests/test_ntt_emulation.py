@@ -2,7 +2,7 @@
 
 tests/emu/ntt_emulate.cu instantiates the very same __host__ __device__ pass functions the sm_100a kernels call
 (csrc/ntt_fast.cuh) and replays them thread by thread on the host; the result must equal the oracle's NTT.
-Also checks that the chosen pass plans are shared-memory bank-conflict free with the e + (e >> 4) padding."""
+Also checks that the chosen pass plans are shared-memory bank-conflict free in the TMA 128-byte swizzle."""
 import os
 import shutil
 import subprocess
@@ -18,7 +18,7 @@ EMU_SRC = os.path.join(ROOT, "tests", "emu", "ntt_emulate.cu")
 EMU_BIN = os.path.join(ROOT, "tests", "emu", "ntt_emulate")
 NVCC = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 
-PLANS = {10: (4, 4, 2), 11: (1, 4, 4, 2), 12: (4, 2, 4, 2), 13: (4, 4, 4, 1), 14: (4, 4, 4, 2)}
+PLANS = {10: (3, 3, 4), 11: (4, 3, 4), 12: (4, 4, 4), 13: (3, 3, 3, 4), 14: (4, 3, 3, 4)}
 
 
 @pytest.fixture(scope="module")
@@ -39,7 +39,7 @@ def run_emu(binary, logn, p, direction, t, data):
 
 
 @pytest.mark.parametrize("logn", [10, 11, 12, 13, 14])
-@pytest.mark.parametrize("bits", [30, 55, 56, 57, 61])
+@pytest.mark.parametrize("bits", [30, 55, 56, 57, 61, 62])
 def test_emulated_kernels_match_oracle(emu, logn, bits):
     n = 1 << logn
     p = orc.generate_primes([bits], False, n)[0]
@@ -71,19 +71,29 @@ def _passes(logn, inverse):
 @pytest.mark.parametrize("logn", sorted(PLANS))
 @pytest.mark.parametrize("inverse", [False, True])
 def test_plans_cover_all_elements_and_are_conflict_free(logn, inverse):
+    """Replays the index map of ntt_fast.cuh (registers = stage bits x low passenger bits) and the 128-byte TMA swizzle
+    phys(e) = e ^ (((e >> 4) & 7) << 1): every pass touches each element exactly once, and every shared-memory access is
+    bank-conflict free -- 128-bit accesses are served per quarter warp (8 lanes x 16 bytes must hit 8 distinct
+    16-byte bank groups), 64-bit accesses per half warp (16 distinct 8-byte bank pairs)."""
     n, T = 1 << logn, (1 << logn) // 16
     assert sum(PLANS[logn]) == logn
     for LB, C in _passes(logn, inverse):
-        G = 16 >> C
+        E = 0 if LB == 0 else 4 - C
+        assert LB == 0 or LB >= E
+        vec = E >= 1 or LB == 0
         seen = set()
-        for g in range(G):
-            for a in range(1 << C):
-                for w0 in range(0, T, 16):  # 64-bit shared accesses are served per half-warp
-                    slots = []
-                    for tau in range(w0, min(w0 + 16, T)):
-                        sb = tau + g * T
-                        e = ((sb >> LB) << (LB + C)) | (a << LB) | (sb & ((1 << LB) - 1))
-                        seen.add(e)
-                        slots.append((e + (e >> 4)) % 16)
-                    assert max(Counter(slots).values()) == 1, (logn, inverse, LB, C)
+        for r in range(0, 16, 2 if vec else 1):
+            lanes = 8 if vec else 16
+            for w0 in range(0, T, lanes):
+                slots = []
+                for tau in range(w0, min(w0 + lanes, T)):
+                    lo, hi = tau & ((1 << (LB - E)) - 1), tau >> (LB - E)
+                    e = (hi << (LB + C)) | ((r >> E) << LB) | (lo << E) | (r & ((1 << E) - 1))
+                    seen.add(e)
+                    if vec:
+                        assert e % 2 == 0
+                        seen.add(e + 1)
+                    phys = e ^ (((e >> 4) & 7) << 1)  # words (128-byte TMA swizzle)
+                    slots.append((phys // 2) % 8 if vec else phys % 16)
+                assert max(Counter(slots).values()) == 1, (logn, inverse, LB, C, r, w0)
         assert seen == set(range(n))
