@@ -213,6 +213,14 @@ int32_t host_pipeline(const hecuda_context *h, int64_t batch, int64_t chunk_hint
     }
     int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(chunk_hint, batch));
     if (batch >= 64) chunk = std::min<int64_t>(chunk, std::max<int64_t>(16, (batch + min_stages - 1) / min_stages));
+    // On any early return, earlier stages may still have copies into / out of the caller's buffers in flight on the
+    // other streams: wait for all of them so the caller may free or reuse its buffers as soon as it sees the error.
+    struct DrainOnExit {
+        std::vector<Workspace *> &ws;
+        ~DrainOnExit() {
+            for (Workspace *w : ws) cudaStreamSynchronize(w->stream);
+        }
+    } drain{ws};
     int k = 0;
     for (int64_t done = 0; done < batch; done += chunk, ++k) {
         Workspace &w = *ws[k % depth];
@@ -495,7 +503,7 @@ int32_t hecuda_evk_create(const hecuda_context *h, const uint64_t *relin_key, he
     if (!relin_key) return fail(HECUDA_ERR_MISSING_KEY, "missingRelinearizationKey");
     int32_t rc = hecuda_evk_create_empty(h, out);
     if (rc) return rc;
-    cudaError_t e = cudaMemcpy((*out)->d_relin, relin_key, (*out)->words * sizeof(u64), cudaMemcpyHostToDevice);
+    cudaError_t e = upload((*out)->d_relin, relin_key, (*out)->words * sizeof(u64));
     if (e != cudaSuccess) {
         hecuda_evk_destroy(*out);
         *out = nullptr;
@@ -508,6 +516,7 @@ int32_t hecuda_evk_destroy(hecuda_evk *k) {
     if (!k) return HECUDA_OK;
     if (k->d_relin) cudaFree(k->d_relin);
     for (auto &kv : k->galois) cudaFree(kv.second);
+    for (hecuda::u64 *p : k->retired) cudaFree(p);
     delete k;
     return HECUDA_OK;
 }
@@ -615,7 +624,7 @@ int32_t hecuda_evk_set_galois_key(hecuda_evk *k, uint32_t element, const uint64_
     if (!valid_galois_element(element, k->owner->ctx->n)) return fail(HECUDA_ERR_INVALID_ARGUMENT, "invalid Galois element");
     u64 *d = nullptr;
     CK(cudaMalloc(&d, k->words * sizeof(u64)));
-    cudaError_t e = cudaMemcpy(d, key, k->words * sizeof(u64), cudaMemcpyHostToDevice);
+    cudaError_t e = upload(d, key, k->words * sizeof(u64));
     if (e != cudaSuccess) {
         cudaFree(d);
         return cuda_fail(e, "cudaMemcpy(galois key)");
@@ -623,7 +632,9 @@ int32_t hecuda_evk_set_galois_key(hecuda_evk *k, uint32_t element, const uint64_
     std::lock_guard<std::mutex> g(k->mu);
     auto it = k->galois.find(element);
     if (it != k->galois.end()) {
-        cudaFree(it->second);
+        // kernels already enqueued by other threads may still read the key being replaced (callers copy the device
+        // pointer out under the mutex and launch afterwards): retire the buffer, free it with the handle
+        k->retired.push_back(it->second);
         it->second = d;
     } else {
         k->galois[element] = d;
@@ -762,10 +773,10 @@ int32_t hecuda_bfv_inner_product_plaintexts(const hecuda_context *h, const uint6
     u64 *d_cts = nullptr;
     unsigned char *d_present = nullptr;
     CK(cudaMalloc(&d_cts, ct_words * sizeof(u64)));
-    cudaError_t e = cudaMemcpy(d_cts, cts, ct_words * sizeof(u64), cudaMemcpyHostToDevice);
+    cudaError_t e = upload(d_cts, cts, ct_words * sizeof(u64));
     if (e == cudaSuccess && present) {
         e = cudaMalloc(&d_present, (size_t)out_count * terms);
-        if (e == cudaSuccess) e = cudaMemcpy(d_present, present, (size_t)out_count * terms, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = upload(d_present, present, (size_t)out_count * terms);
     }
     if (e != cudaSuccess) {
         cudaFree(d_cts);

@@ -27,6 +27,20 @@ const char *last_error_cstr();
         if (e_ != cudaSuccess) return ::hecuda::api::cuda_fail(e_, #expr); \
     } while (0)
 
+// Setup-time uploads (keys, databases, per-call operands staged outside a workspace).  cudaMemcpy from pageable host
+// memory may return once the data is staged, before the DMA has reached the device, and cudaMemset on device memory is
+// asynchronous; the consumers run on cudaStreamNonBlocking workspace streams or caller streams that do not
+// synchronise with the legacy default stream.  So every such upload waits for the legacy stream before the pointer is
+// published or used on another stream.
+inline cudaError_t upload(void *dst, const void *src, size_t bytes) {
+    cudaError_t e = cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice);
+    return e != cudaSuccess ? e : cudaStreamSynchronize(cudaStreamLegacy);
+}
+inline cudaError_t fill(void *dst, int value, size_t bytes) {
+    cudaError_t e = cudaMemset(dst, value, bytes);
+    return e != cudaSuccess ? e : cudaStreamSynchronize(cudaStreamLegacy);
+}
+
 // Scratch for one in-flight chunk.  Grows on demand, never shrinks.
 struct Workspace {
     cudaStream_t stream = nullptr;
@@ -89,6 +103,7 @@ struct hecuda_evk {
     size_t words = 0;
     bool loaded = false;
     std::map<uint32_t, hecuda::u64 *> galois;  // GaloisKey.keys: element -> key-switch key (Keys.swift:150-163), same layout
+    std::vector<hecuda::u64 *> retired;        // replaced Galois keys, kept until destroy (in-flight kernels may read them)
     std::mutex mu;
 };
 

@@ -96,6 +96,8 @@ static DivRoundConsts build_divround(const std::vector<u64> &base) {
 
 Context *Context::create(int64_t n, const u64 *coeff_moduli, int nmod, u64 t, std::string &err) {
     if (n < 2 || (n & (n - 1)) || n > (1 << 17)) { err = "invalidDegree: N must be a power of two in [2, 2^17]"; return nullptr; }
+    // the NTT kernels keep a whole row in one CTA's shared memory: N <= 2^14 (a 2^15 row is 256 KB)
+    if (n > (1 << fast::kMaxLogN)) { err = "unsupportedHeOperation: polynomial degrees above 2^" + std::to_string(fast::kMaxLogN) + " are not supported by the NTT kernels"; return nullptr; }
     if (nmod < 2) { err = "invalidEncryptionParameters: need >= 1 ciphertext modulus plus the key-switching modulus"; return nullptr; }
     if (nmod - 1 > kMaxL) { err = "unsupportedHeOperation: more than " + std::to_string(kMaxL) + " ciphertext moduli"; return nullptr; }
     if (t < 2) { err = "invalidEncryptionParameters: plaintext modulus"; return nullptr; }

@@ -138,7 +138,7 @@ int32_t hecuda_bfv_decrypt(const hecuda_context *h, const uint64_t *secret_key, 
     // SecretKey.poly has K = L + 1 rows (Eval); rows 0..l-1 are the ones a level-l ciphertext uses
     u64 *d_sk = nullptr;
     CK(cudaMalloc(&d_sk, (size_t)l * c.n * sizeof(u64)));
-    cudaError_t e = cudaMemcpy(d_sk, secret_key, (size_t)l * c.n * sizeof(u64), cudaMemcpyHostToDevice);
+    cudaError_t e = upload(d_sk, secret_key, (size_t)l * c.n * sizeof(u64));
     if (e != cudaSuccess) {
         cudaFree(d_sk);
         return cuda_fail(e, "secret key upload");
@@ -167,7 +167,7 @@ int32_t hecuda_bfv_decrypt(const hecuda_context *h, const uint64_t *secret_key, 
     if (d_scratch) cudaFreeAsync(d_scratch, s);
     if (d_out) cudaFreeAsync(d_out, s);
     cudaError_t e2 = cudaStreamSynchronize(s);
-    cudaMemset(d_sk, 0, (size_t)l * c.n * sizeof(u64));  // zeroize the key copy (the reference zeroizes SecretKey storage)
+    fill(d_sk, 0, (size_t)l * c.n * sizeof(u64));  // zeroize the key copy (the reference zeroizes SecretKey storage)
     cudaFree(d_sk);
     if (e == cudaSuccess) e = e2;
     return e == cudaSuccess ? HECUDA_OK : cuda_fail(e, "decrypt");

@@ -17,6 +17,7 @@
 #include <mutex>
 
 #include <algorithm>
+#include <cstdlib>
 #include "kernels.cuh"
 #include "ntt_fast.cuh"
 
@@ -140,7 +141,7 @@ template <int LOGN, bool INVERSE>
 __global__ void __launch_bounds__((1 << LOGN) / 16, (1024 / ((1 << LOGN) / 16)))
     ntt_rows_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_out,
                     const ModSlot *__restrict__ slots, const __grid_constant__ RowList rl, const int polys,
-                    const int scale_mode) {
+                    const int scale_mode, const int debug_flags) {
     extern __shared__ __align__(1024) u64 sm[];  // row first: the 128-byte swizzle wants it 1024-byte aligned
     constexpr int kLines = (1 << LOGN) / kLineWords;
     constexpr int kBoxes = kLines > kBoxLines ? kLines / kBoxLines : 1;
@@ -182,7 +183,7 @@ __global__ void __launch_bounds__((1 << LOGN) / 16, (1024 / ((1 << LOGN) / 16)))
 #pragma unroll
             for (int b = 0; b < kBoxes; ++b) tma_load_box(sm + b * kLinesPerBox * kLineWords, &map_in, line + b * kLinesPerBox, bar_row);
             const int next = task + gridDim.x;
-            if (next < tasks) {
+            if (next < tasks && !(debug_flags & 1)) {
                 const int nw = next / polys;
                 const int np_ = next - nw * polys;
                 const int64_t nword = INVERSE ? ((int64_t)np_ * rl.rows_per_poly + rl.row[nw]) << LOGN
@@ -205,6 +206,8 @@ __global__ void __launch_bounds__((1 << LOGN) / 16, (1024 / ((1 << LOGN) / 16)))
         }
         mbar_wait(bar_row, phase_row);
         phase_row ^= 1;
+        if (debug_flags & 4) {  // experiments: data movement only
+        } else
 #ifndef HE_EXPERIMENT_ONLY_CLASS
         if (INVERSE) {
             if (cls == kNarrow) inv_row<LOGN, kNarrow>(sm, tau, m);
@@ -223,7 +226,7 @@ __global__ void __launch_bounds__((1 << LOGN) / 16, (1024 / ((1 << LOGN) / 16)))
         // ---- TMA out: every thread makes its generic-proxy writes visible to the async proxy, then one thread copies
         fence_proxy_async_smem();
         __syncthreads();
-        if (tau == 0) {
+        if (tau == 0 && !(debug_flags & 2)) {
             const int line = (int)(out_word >> 4);
 #pragma unroll
             for (int b = 0; b < kBoxes; ++b) tma_store_box(&map_out, line + b * kLinesPerBox, sm + b * kLinesPerBox * kLineWords);
@@ -323,7 +326,11 @@ static cudaError_t launch_logn(const Context &ctx, const NttRowMap &map, const u
     }
     const int64_t grid = std::min<int64_t>(rows, (int64_t)ctx.sm_count * per_sm);
     ++g_kernel_launches;
-    k<<<(unsigned)grid, threads, smem, stream>>>(map_in, map_out, ctx.d_slots, rl, polys, scale_mode);
+    static const int debug_flags = [] {  // experiments only: bit 0 = no L2 prefetch of the next row, bit 1 = no TMA-out, bit 2 = no compute
+        const char *env = std::getenv("HECUDA_NTT_DEBUG");
+        return env ? std::atoi(env) : 0;
+    }();
+    k<<<(unsigned)grid, threads, smem, stream>>>(map_in, map_out, ctx.d_slots, rl, polys, scale_mode, debug_flags);
     return cudaGetLastError();
 }
 

@@ -415,18 +415,18 @@ int32_t hecuda_pir_database_create(const hecuda_context *h, const uint64_t *plai
     cudaError_t e = cudaMalloc(&db->d_plain, row_words * count * sizeof(u64));
     if (e == cudaSuccess) e = cudaMalloc(&db->d_present, (size_t)count);
     if (e == cudaSuccess)
-        e = present ? cudaMemcpy(db->d_present, present, (size_t)count, cudaMemcpyHostToDevice)
-                    : cudaMemset(db->d_present, 1, (size_t)count);
+        e = present ? upload(db->d_present, present, (size_t)count)
+                    : fill(db->d_present, 1, (size_t)count);
     if (e == cudaSuccess) {
         if (eval_format) {
-            e = cudaMemcpy(db->d_plain, plaintexts, row_words * count * sizeof(u64), cudaMemcpyHostToDevice);
+            e = upload(db->d_plain, plaintexts, row_words * count * sizeof(u64));
         } else {  // Plaintext.convertToEvalFormat (Plaintext.swift:149-171) in slabs of <= 64 MB of coefficients
             const int64_t slab = std::max<int64_t>(1, (int64_t)((size_t)8 * 1024 * 1024 / c.n));
             u64 *d_coeff = nullptr;
             e = cudaMalloc(&d_coeff, (size_t)std::min(slab, count) * c.n * sizeof(u64));
             for (int64_t done = 0; e == cudaSuccess && done < count; done += slab) {
                 const int64_t items = std::min(slab, count - done);
-                e = cudaMemcpy(d_coeff, plaintexts + (size_t)done * c.n, (size_t)items * c.n * sizeof(u64), cudaMemcpyHostToDevice);
+                e = upload(d_coeff, plaintexts + (size_t)done * c.n, (size_t)items * c.n * sizeof(u64));
                 if (e == cudaSuccess) e = launch_plaintext_to_eval(c, d_coeff, c.L, db->d_plain + row_words * done, items, nullptr);
                 if (e == cudaSuccess) e = cudaStreamSynchronize(nullptr);
             }
@@ -559,16 +559,18 @@ int32_t hecuda_mulpir_compute_response_wire(const hecuda_context *h, const hecud
     CK(tmp.alloc_bytes((void **)&d_bytes[0], ((b0 + 7) & ~(size_t)7) * replies + 8));
     CK(tmp.alloc_bytes((void **)&d_bytes[1], ((b1 + 7) & ~(size_t)7) * replies + 8));
     CK(tmp.alloc_bytes((void **)&d_reply, (b0 + b1) * replies));
+    // from here on copies of the caller's buffers are in flight on `s`: every return path waits for the stream first
+    struct DrainOnExit {
+        cudaStream_t s;
+        ~DrainOnExit() { wait_stream(s); }
+    } drain{s};
     CK(cudaMemcpyAsync(d_poly0, query_poly0, in_bytes * query_ct_count, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(d_seeds, query_seeds, (size_t)32 * query_ct_count, cudaMemcpyHostToDevice, s));
     // Query.ciphertexts arrive as SerializedCiphertext.seeded (SerializedCiphertext.swift:41-49)
     cudaError_t e = expand_seeded_device(c, c.L, d_poly0, d_seeds, d_query, query_ct_count, s);
     if (e != cudaSuccess) return cuda_fail(e, "expand seeded query");
     rc = compute_response_device(h, k, dbs, db_count, shape, d_query, query_ct_count, indices_count, d_resp, s);
-    if (rc) {
-        wait_stream(s);
-        return rc;
-    }
+    if (rc) return rc;
     // Response ciphertexts leave as .full(polys:skipLSBs:) with Bfv.skipLSBsForDecryption (Bfv+Decrypt.swift:51-110):
     // poly 0 and poly 1 are packed with different numbers of dropped low bits
     const size_t pw = (size_t)c.n * sizeof(u64);

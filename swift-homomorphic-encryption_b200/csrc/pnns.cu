@@ -401,10 +401,10 @@ int32_t hecuda_pnns_matrix_create(const hecuda_context *h, const uint64_t *plain
     std::vector<unsigned char> present((size_t)slots, 0);
     u64 *d_in = nullptr;
     cudaError_t e = cudaMalloc(&m->d_plain, row_words * slots * sizeof(u64));
-    if (e == cudaSuccess) e = cudaMemset(m->d_plain, 0, row_words * slots * sizeof(u64));
+    if (e == cudaSuccess) e = fill(m->d_plain, 0, row_words * slots * sizeof(u64));
     if (e == cudaSuccess) e = cudaMalloc(&m->d_present, (size_t)slots);
     if (e == cudaSuccess) e = cudaMalloc(&d_in, in_words * count * sizeof(u64));
-    if (e == cudaSuccess) e = cudaMemcpy(d_in, plaintexts, in_words * count * sizeof(u64), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = upload(d_in, plaintexts, in_words * count * sizeof(u64));
     // plaintext index resultCount * (j + babyStep * g) + r  ->  slot (r, g, j)      (MatrixMultiplication.swift:203-205)
     for (int64_t r = 0; e == cudaSuccess && r < results; ++r)
         for (int g = 0; e == cudaSuccess && g < giant_step; ++g) {
@@ -426,7 +426,7 @@ int32_t hecuda_pnns_matrix_create(const hecuda_context *h, const uint64_t *plain
             }
             for (int64_t j = 0; j < terms; ++j) present[(size_t)(slot + j)] = 1;
         }
-    if (e == cudaSuccess) e = cudaMemcpy(m->d_present, present.data(), (size_t)slots, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = upload(m->d_present, present.data(), (size_t)slots);
     cudaFree(d_in);
     if (e != cudaSuccess) {
         hecuda_pnns_matrix_destroy(m);
