@@ -50,7 +50,11 @@ enum {
 enum {
     HECUDA_BASE_Q = 0,         /* ciphertext context q_0..q_{rows-1}            (Context.swift:102-112) */
     HECUDA_BASE_Q_BSK = 1,     /* [q_0..q_{L-1}, Bsk], rows = 2L+1               (RnsTool.swift:228-233) */
-    HECUDA_BASE_KEYSWITCH = 2  /* q_0..q_{rows-2}, q_ks                          (Context.swift:114-127) */
+    HECUDA_BASE_KEYSWITCH = 2, /* q_0..q_{rows-2}, q_ks                          (Context.swift:114-127) */
+    HECUDA_BASE_Q_AUX = 3      /* [q_0..q_{L-1}, aux], rows = 2L+1: the base hecuda_bfv_multiply computes in.  Its
+                                  auxiliary primes are below 2^55 when BEHZ's exactness conditions allow (they do for
+                                  every predefined parameter set), else they are Bsk; the product does not depend on the
+                                  choice (csrc/context.cu).  HECUDA_AUX_BASE=reference in the environment forces Bsk. */
 };
 
 int32_t hecuda_version(void);
@@ -74,6 +78,8 @@ int32_t hecuda_context_destroy(hecuda_context *ctx);
 /* Introspection used by the parity tests (the reference exposes the same values as public lets). */
 int32_t hecuda_context_ciphertext_moduli_count(const hecuda_context *ctx, int32_t *count);
 int32_t hecuda_context_bsk_moduli(const hecuda_context *ctx, uint64_t *out, int32_t capacity, int32_t *count);
+/* The L+1 auxiliary primes of HECUDA_BASE_Q_AUX (equal to Bsk when the faster base is not admissible). */
+int32_t hecuda_context_aux_moduli(const hecuda_context *ctx, uint64_t *out, int32_t capacity, int32_t *count);
 /* rootOfUnityPowers / inverse powers of `modulus` in the reference's bit-reversed order (PolyRq+Ntt.swift:125-137);
  * inverse table is indexed like the forward one (inv[i] = roots[i]^-1). */
 int32_t hecuda_context_root_tables(const hecuda_context *ctx, uint64_t modulus, uint64_t *roots, uint64_t *inverse_roots);

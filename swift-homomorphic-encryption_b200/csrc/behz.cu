@@ -278,7 +278,8 @@ static inline dim3 poly_grid(int64_t n, int64_t polys, int cols) {
 }
 
 cudaError_t launch_lift(const Context &ctx, const u64 *in, int polys_in, u64 *ext, int ext_polys, int out_poly_offset,
-                        int64_t items, cudaStream_t stream) {
+                        int64_t items, cudaStream_t stream, bool reference_base) {
+    const LiftConsts &consts = reference_base ? ctx.lift : ctx.lift_mul;
     int64_t polys = items * polys_in;
     if (polys == 0) return cudaSuccess;
     const int64_t pstride_in = (int64_t)ctx.L * ctx.n;
@@ -290,10 +291,10 @@ cudaError_t launch_lift(const Context &ctx, const u64 *in, int polys_in, u64 *ex
         ++g_kernel_launches;
         if (cols == 2) {
             HE_DISPATCH_L(ctx.L, (lift_kernel<LL, 2><<<grid, kThreads, 0, stream>>>(in, polys_in, ext, ext_polys,
-                                                                                 out_poly_offset, ctx.lift, (int)ctx.n)));
+                                                                                 out_poly_offset, consts, (int)ctx.n)));
         } else {
             HE_DISPATCH_L(ctx.L, (lift_kernel<LL, 1><<<grid, kThreads, 0, stream>>>(in, polys_in, ext, ext_polys,
-                                                                                 out_poly_offset, ctx.lift, (int)ctx.n)));
+                                                                                 out_poly_offset, consts, (int)ctx.n)));
         }
         // advance whole items only (32768 is even and polys_in is 1 or 2)
         in += slab * pstride_in;
@@ -303,11 +304,12 @@ cudaError_t launch_lift(const Context &ctx, const u64 *in, int polys_in, u64 *ex
     return cudaGetLastError();
 }
 
-cudaError_t launch_tensor(const Context &ctx, const u64 *ext, u64 *ten, int64_t items, cudaStream_t stream) {
+cudaError_t launch_tensor(const Context &ctx, const u64 *ext, u64 *ten, int64_t items, cudaStream_t stream,
+                          bool reference_base) {
     if (items == 0) return cudaSuccess;
     TensorConsts tc;
     tc.R = 2 * ctx.L + 1;
-    const NttRowMap map = ctx.map_qbsk();
+    const NttRowMap map = reference_base ? ctx.map_qbsk() : ctx.map_qaux();
     for (int r = 0; r < tc.R; ++r) {
         tc.p[r] = ctx.slots[map.slot[r]].dev.p;
         tc.ninv[r] = ctx.slots[map.slot[r]].dev.ninv;
@@ -330,12 +332,12 @@ cudaError_t launch_tensor(const Context &ctx, const u64 *ext, u64 *ten, int64_t 
 }
 
 cudaError_t launch_tensor_sum(const Context &ctx, const u64 *ext, u64 *ten, int64_t pairs, int64_t groups,
-                              cudaStream_t stream) {
+                              cudaStream_t stream, bool reference_base) {
     if (groups == 0) return cudaSuccess;
     if (ctx.n < 2 || pairs < 1) return cudaErrorInvalidValue;
     TensorSumConsts tc;
     tc.R = 2 * ctx.L + 1;
-    const NttRowMap map = ctx.map_qbsk();
+    const NttRowMap map = reference_base ? ctx.map_qbsk() : ctx.map_qaux();
     u64 pmax = 0;
     for (int r = 0; r < tc.R; ++r) {
         const ModSlot &S = ctx.slots[map.slot[r]].dev;
@@ -362,8 +364,10 @@ cudaError_t launch_tensor_sum(const Context &ctx, const u64 *ext, u64 *ten, int6
     return cudaGetLastError();
 }
 
-cudaError_t launch_floor(const Context &ctx, const u64 *in, u64 *out, int64_t polys, cudaStream_t stream) {
+cudaError_t launch_floor(const Context &ctx, const u64 *in, u64 *out, int64_t polys, cudaStream_t stream,
+                         bool reference_base) {
     if (polys == 0) return cudaSuccess;
+    const FloorConsts &consts = reference_base ? ctx.floor : ctx.floor_mul;
     const int R = 2 * ctx.L + 1;
     while (polys > 0) {
         int64_t slab = polys >= 32768 ? (polys / 32768) * 32768 : polys;
@@ -371,9 +375,9 @@ cudaError_t launch_floor(const Context &ctx, const u64 *in, u64 *out, int64_t po
         const dim3 grid = poly_grid(ctx.n, slab, cols);
         ++g_kernel_launches;
         if (cols == 2) {
-            HE_DISPATCH_L(ctx.L, (floor_kernel<LL, 2><<<grid, kThreads, 0, stream>>>(in, out, ctx.floor, (int)ctx.n)));
+            HE_DISPATCH_L(ctx.L, (floor_kernel<LL, 2><<<grid, kThreads, 0, stream>>>(in, out, consts, (int)ctx.n)));
         } else {
-            HE_DISPATCH_L(ctx.L, (floor_kernel<LL, 1><<<grid, kThreads, 0, stream>>>(in, out, ctx.floor, (int)ctx.n)));
+            HE_DISPATCH_L(ctx.L, (floor_kernel<LL, 1><<<grid, kThreads, 0, stream>>>(in, out, consts, (int)ctx.n)));
         }
         in += slab * (int64_t)R * ctx.n;
         out += slab * (int64_t)ctx.L * ctx.n;

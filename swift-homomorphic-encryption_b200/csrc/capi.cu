@@ -87,6 +87,10 @@ bool make_map(const Context &c, int32_t base, int32_t rows, NttRowMap &map, std:
             if (rows != 2 * c.L + 1) { err = "invalidPolyContext: BASE_Q_BSK needs 2L+1 rows"; return false; }
             map = c.map_qbsk();
             return true;
+        case HECUDA_BASE_Q_AUX:
+            if (rows != 2 * c.L + 1) { err = "invalidPolyContext: BASE_Q_AUX needs 2L+1 rows"; return false; }
+            map = c.map_qaux();
+            return true;
         case HECUDA_BASE_KEYSWITCH:
             if (rows < 2 || rows > c.L + 1) { err = "invalidPolyContext: BASE_KEYSWITCH needs 2..L+1 rows"; return false; }
             map = c.map_ks(rows - 1);
@@ -109,7 +113,7 @@ cudaError_t multiply_chunk(const Context &c, u64 *scratch, const u64 *lhs, const
     const size_t poly_words = (size_t)R * c.n;
     cudaError_t e;
     u64 *ext = scratch, *ten = scratch + 4 * poly_words * items;
-    const NttRowMap map = c.map_qbsk();
+    const NttRowMap map = c.map_qaux();
     // computeBehzPolys for both operands: lift + forward NTT      (Bfv+Multiply.swift:51-57)
     if ((e = launch_lift(c, lhs, 2, ext, 4, 0, items, s)) != cudaSuccess) return e;
     if ((e = launch_lift(c, rhs, 2, ext, 4, 2, items, s)) != cudaSuccess) return e;
@@ -166,7 +170,7 @@ cudaError_t inner_product_chunk(const Context &c, u64 *scratch, const u64 *lhs, 
     const size_t poly_words = (size_t)R * c.n;
     const int64_t items = groups * pairs;
     u64 *ext = scratch, *ten = scratch + 4 * poly_words * items;
-    const NttRowMap map = c.map_qbsk();
+    const NttRowMap map = c.map_qaux();
     cudaError_t e;
     if ((e = launch_lift(c, lhs, 2, ext, 4, 0, items, s)) != cudaSuccess) return e;
     if ((e = launch_lift(c, rhs, 2, ext, 4, 2, items, s)) != cudaSuccess) return e;
@@ -354,6 +358,15 @@ int32_t hecuda_context_bsk_moduli(const hecuda_context *h, uint64_t *out, int32_
     if (out) {
         if (capacity < *count) return fail(HECUDA_ERR_INVALID_ARGUMENT, "capacity too small");
         std::memcpy(out, h->ctx->bsk.data(), sizeof(u64) * h->ctx->bsk.size());
+    }
+    return HECUDA_OK;
+}
+int32_t hecuda_context_aux_moduli(const hecuda_context *h, uint64_t *out, int32_t capacity, int32_t *count) {
+    if (!h || !count) return fail(HECUDA_ERR_INVALID_ARGUMENT, "null argument");
+    *count = (int32_t)h->ctx->aux.size();
+    if (out) {
+        if (capacity < *count) return fail(HECUDA_ERR_INVALID_ARGUMENT, "capacity too small");
+        std::memcpy(out, h->ctx->aux.data(), sizeof(u64) * h->ctx->aux.size());
     }
     return HECUDA_OK;
 }

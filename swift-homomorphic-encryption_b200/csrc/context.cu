@@ -3,6 +3,8 @@
 
 #include <cuda_runtime.h>
 
+#include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "hostmath.hpp"
@@ -125,13 +127,47 @@ Context *Context::create(int64_t n, const u64 *coeff_moduli, int nmod, u64 t, st
         for (int i = 0; i < nmod; ++i)
             if (b == coeff_moduli[i]) { err = "coprimeModuli: coefficient modulus collides with the BEHZ base"; delete c; return nullptr; }
 
+    // ---- the auxiliary base the fused multiply computes in.  What Bfv.mulAssign returns does not depend on which
+    // auxiliary primes BEHZ uses, as long as they are large enough for its exactness conditions: the lifted
+    // operands y = (x~ + q r_m~) / m~, the tensor product D = y1 * y2 and F = floor(t D / q) - u (u = the overflow of the
+    // fast base conversion of [t D]_q, a function of the q residues alone) are fixed integers, and the
+    // Shenoy-Kumaresan conversion back to q is exact (RnsTool.swift:324-456).  So the multiply runs over L + 1 primes
+    // below 2^55, whose NTT rows never need a conditional subtraction (ntt_fast.cuh, NARROW class), instead of the
+    // reference's 61-bit Bsk; the reference base stays available for the stage-level entry points.  Conditions checked:
+    //   q * B_aux > 8 N q^2   (D is represented exactly),   B_aux(L primes) * m_sk > 16 t N q   (F survives SK)
+    c->aux = c->bsk;
+    {
+        const char *env = std::getenv("HECUDA_AUX_BASE");
+        const bool want_fast = !(env && std::string(env) == "reference");
+        std::vector<u64> cand = smallest_ntt_primes(55, L + 1 + nmod, (u64)n);
+        std::vector<u64> pick;
+        for (u64 v : cand) {
+            bool used = false;
+            for (int i = 0; i < nmod; ++i) used |= coeff_moduli[i] == v;
+            if (!used && (int)pick.size() < L + 1) pick.push_back(v);
+        }
+        double log_q = 0, log_aux = 0, log_aux_l = 0;
+        for (u64 v : c->q) log_q += std::log2((double)v);
+        for (size_t j = 0; j < pick.size(); ++j) {
+            log_aux += std::log2((double)pick[j]);
+            if ((int)j < L) log_aux_l += std::log2((double)pick[j]);
+        }
+        const double log_n = (double)c->logn, log_t = std::log2((double)t);
+        const bool enough = (int)pick.size() == L + 1 && log_aux >= log_q + log_n + 4 &&
+                            log_aux_l + std::log2((double)pick.back()) >= log_t + log_n + log_q + 5;
+        if (want_fast && enough) c->aux = pick;
+    }
+    c->aux_is_reference = c->aux == c->bsk;
+
     // ---- NTT slots
-    const int nslots = 2 * L + 2;
+    const int nslots = c->aux_is_reference ? 2 * L + 2 : 3 * L + 3;
     c->slots.resize(nslots);
     std::vector<u64> slot_mod(nslots);
     for (int i = 0; i < L; ++i) slot_mod[c->slot_q(i)] = c->q[i];
     for (int j = 0; j <= L; ++j) slot_mod[c->slot_bsk(j)] = c->bsk[j];
     slot_mod[c->slot_ks()] = c->q_ks;
+    if (!c->aux_is_reference)
+        for (int j = 0; j <= L; ++j) slot_mod[c->slot_aux(j)] = c->aux[j];
     const size_t table_bytes = sizeof(ulonglong2) * (size_t)n;
     const bool fast = c->logn >= fast::kMinLogN && c->logn <= fast::kMaxLogN;
     const int threads = (int)(n / 16);
@@ -165,9 +201,10 @@ Context *Context::create(int64_t n, const u64 *coeff_moduli, int nmod, u64 t, st
 
     // ---- BEHZ constants (top level)
     const u64 *Q = c->q.data();
-    const u64 *BSK = c->bsk.data();
-    const u64 msk = c->bsk[L];
-    LiftConsts &lf = c->lift;
+    auto build_behz = [&](const std::vector<u64> &base, bool reference_base, LiftConsts &lf, FloorConsts &fl) {
+    const u64 *BSK = base.data();
+    const u64 msk = base[L];
+    auto slot_of = [&](int j) { return reference_base ? c->slot_bsk(j) : c->slot_aux(j); };
     std::memset(&lf, 0, sizeof(lf));
     lf.L = L;
     {
@@ -185,17 +222,16 @@ Context *Context::create(int64_t n, const u64 *coeff_moduli, int nmod, u64 t, st
     for (int j = 0; j <= L; ++j) {
         const u64 bj = BSK[j];
         lf.b[j] = bj;
-        lf.b_ninv[j] = c->slots[c->slot_bsk(j)].dev.ninv;
-        const u64 r64 = c->slots[c->slot_bsk(j)].dev.r64;
+        lf.b_ninv[j] = c->slots[slot_of(j)].dev.ninv;
+        const u64 r64 = c->slots[slot_of(j)].dev.r64;
         const u64 mt_inv = mulmod(invmod(kMTilde % bj, bj), r64, bj);  // m~^-1 2^64
         for (int i = 0; i < L; ++i) lf.mat[j][i] = mulmod(punctured_mod(Q, L, i, bj), mt_inv, bj);
         lf.qr[j] = mulmod(prod_mod(Q, L, bj), mt_inv, bj);
     }
-    FloorConsts &fl = c->floor;
     std::memset(&fl, 0, sizeof(fl));
     fl.L = L;
     const u64 b_mod_msk = prod_mod(BSK, L, msk);
-    const u64 r64_msk = c->slots[c->slot_bsk(L)].dev.r64;
+    const u64 r64_msk = c->slots[slot_of(L)].dev.r64;
     const u64 b_inv_msk = mulmod(invmod(b_mod_msk, msk), r64_msk, msk);  // B^-1 2^64
     fl.a_msk = (msk - b_inv_msk) % msk;
     for (int i = 0; i < L; ++i) {
@@ -212,8 +248,8 @@ Context *Context::create(int64_t n, const u64 *coeff_moduli, int nmod, u64 t, st
     for (int j = 0; j <= L; ++j) {
         const u64 bj = BSK[j];
         fl.b[j] = bj;
-        fl.b_ninv[j] = c->slots[c->slot_bsk(j)].dev.ninv;
-        const u64 q_inv = mulmod(invmod(prod_mod(Q, L, bj), bj), c->slots[c->slot_bsk(j)].dev.r64, bj);  // Q^-1 2^64
+        fl.b_ninv[j] = c->slots[slot_of(j)].dev.ninv;
+        const u64 q_inv = mulmod(invmod(prod_mod(Q, L, bj), bj), c->slots[slot_of(j)].dev.r64, bj);  // Q^-1 2^64
         fl.fq[j] = q_inv;
         for (int i = 0; i < L; ++i) {
             const u64 v = mulmod(punctured_mod(Q, L, i, bj), q_inv, bj);
@@ -226,6 +262,14 @@ Context *Context::create(int64_t n, const u64 *coeff_moduli, int nmod, u64 t, st
         fl.inb_wp[k] = shoup_factor(fl.inb_w[k], bk);
         fl.amat[k] = mulmod(punctured_mod(BSK, L, k, msk), b_inv_msk, msk);
     }
+    };
+    build_behz(c->bsk, true, c->lift, c->floor);
+    if (c->aux_is_reference) {
+        c->lift_mul = c->lift;
+        c->floor_mul = c->floor;
+    } else {
+        build_behz(c->aux, false, c->lift_mul, c->floor_mul);
+    }
 
     // ---- range check behind the single conditional subtraction after the lift / approximate-floor sums:
     // (b_j^2 + L q_max b_j) / 2^64 < b_j  <=>  b_j + L q_max < 2^64   (see behz.cu)
@@ -233,6 +277,7 @@ Context *Context::create(int64_t n, const u64 *coeff_moduli, int nmod, u64 t, st
         u64 qmax = 0, bmax = 0;
         for (u64 v : c->q) qmax = v > qmax ? v : qmax;
         for (u64 v : c->bsk) bmax = v > bmax ? v : bmax;
+        for (u64 v : c->aux) bmax = v > bmax ? v : bmax;
         if ((u128)bmax + (u128)L * qmax >= ((u128)1 << 64)) {
             err = "unsupportedHeOperation: " + std::to_string(L) + " ciphertext moduli of this size exceed the lazy-sum bound";
             delete c;
@@ -278,6 +323,12 @@ NttRowMap Context::map_qbsk() const {
     m.src_poly_stride = 0;
     for (int r = 0; r < L; ++r) m.slot[r] = (unsigned char)slot_q(r);
     for (int j = 0; j <= L; ++j) m.slot[L + j] = (unsigned char)slot_bsk(j);
+    return m;
+}
+NttRowMap Context::map_qaux() const {
+    NttRowMap m = map_qbsk();
+    if (!aux_is_reference)
+        for (int j = 0; j <= L; ++j) m.slot[L + j] = (unsigned char)slot_aux(j);
     return m;
 }
 NttRowMap Context::map_ks(int l) const {

@@ -15,7 +15,7 @@
 namespace hecuda {
 
 constexpr int kMaxL = 16;               // ciphertext moduli supported by the kernels
-constexpr int kMaxSlots = 2 * kMaxL + 2;  // q_0..q_{L-1} | bsk_0..bsk_L | q_ks
+constexpr int kMaxSlots = 3 * kMaxL + 3;  // q_0..q_{L-1} | bsk_0..bsk_L | q_ks | aux_0..aux_L
 constexpr int kMaxRows = 2 * kMaxL + 1;
 
 // One NTT-capable modulus.  Twiddle tables are interleaved (w, floor(w 2^64 / p)) pairs, indexed like the
@@ -118,11 +118,15 @@ class Context {
     int sm_count;
     std::vector<u64> q;    // q_0..q_{L-1}
     u64 q_ks;
-    std::vector<u64> bsk;  // L+1 primes
-    std::vector<HostSlot> slots;  // L q's, L+1 bsk, 1 q_ks
+    std::vector<u64> bsk;  // L+1 primes: the reference's BEHZ base (RnsTool.swift:30-33)
+    std::vector<u64> aux;  // L+1 primes: the base ct x ct multiply actually computes in (context.cu); == bsk when
+    bool aux_is_reference = true;  // the conditions for the faster base do not hold (or HECUDA_AUX_BASE=reference)
+    std::vector<HostSlot> slots;  // L q's, L+1 bsk, 1 q_ks, then L+1 aux (when different from bsk)
     ModSlot *d_slots = nullptr;   // device array [2L+2]
-    LiftConsts lift;
+    LiftConsts lift;        // over [Q, Bsk]: stage-level entry points
     FloorConsts floor;
+    LiftConsts lift_mul;    // over [Q, aux]: Bfv.mulAssign / innerProduct
+    FloorConsts floor_mul;
     std::vector<DivRoundConsts> ks_divround;   // index l (1..L): base [q_0..q_{l-1}, q_ks]
     std::vector<DivRoundConsts> ms_divround;   // index l (2..L): base [q_0..q_{l-1}]
     void *d_pool = nullptr;  // twiddle storage
@@ -130,8 +134,10 @@ class Context {
     int slot_q(int i) const { return i; }
     int slot_bsk(int j) const { return L + j; }
     int slot_ks() const { return 2 * L + 1; }
+    int slot_aux(int j) const { return aux_is_reference ? slot_bsk(j) : 2 * L + 2 + j; }
     NttRowMap map_q(int rows) const;      // rows of the ciphertext context
     NttRowMap map_qbsk() const;           // [Q, Bsk]
+    NttRowMap map_qaux() const;           // [Q, aux]
     NttRowMap map_ks(int l) const;        // [q_0..q_{l-1}, q_ks]
     NttRowMap map_single(int slot) const;
     // (l+1) x l digit rows, row (r, j) = [target row j]_{m_r}; gathered from target polynomials `stride` words apart

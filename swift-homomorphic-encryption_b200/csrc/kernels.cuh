@@ -32,17 +32,20 @@ cudaError_t launch_ntt_forward_fast(const Context &ctx, const NttRowMap &map, co
 cudaError_t launch_ntt_inverse_fast(const Context &ctx, const NttRowMap &map, const u64 *in, u64 *out, int64_t rows,
                                     int scale_mode, cudaStream_t stream);
 
-// ---- BEHZ steps of ct x ct multiply (behz.cu)
+// ---- BEHZ steps of ct x ct multiply (behz.cu).  reference_base: compute over the reference's [Q, Bsk] (stage-level
+// entry points) instead of the [Q, aux] base the fused multiply uses (context.hpp).
 // lift: `items` x polys_in x L x N  ->  ext[item][out_poly_offset + p][R][N]  with ext item stride ext_polys*R*N
 cudaError_t launch_lift(const Context &ctx, const u64 *in, int polys_in, u64 *ext, int ext_polys, int out_poly_offset,
-                        int64_t items, cudaStream_t stream);
+                        int64_t items, cudaStream_t stream, bool reference_base = false);
 // tensor: ext[item][4][R][N] (Eval) -> ten[item][3][R][N]
-cudaError_t launch_tensor(const Context &ctx, const u64 *ext, u64 *ten, int64_t items, cudaStream_t stream);
+cudaError_t launch_tensor(const Context &ctx, const u64 *ext, u64 *ten, int64_t items, cudaStream_t stream,
+                          bool reference_base = false);
 // tensor sum: ext[group][pair][4][R][N] (Eval) -> ten[group][3][R][N]  (Bfv.innerProduct(_:_:), Bfv.swift:315-361)
 cudaError_t launch_tensor_sum(const Context &ctx, const u64 *ext, u64 *ten, int64_t pairs, int64_t groups,
-                              cudaStream_t stream);
+                              cudaStream_t stream, bool reference_base = false);
 // floor: polys x R x N (Coeff, already scaled by t) -> polys x L x N
-cudaError_t launch_floor(const Context &ctx, const u64 *in, u64 *out, int64_t polys, cudaStream_t stream);
+cudaError_t launch_floor(const Context &ctx, const u64 *in, u64 *out, int64_t polys, cudaStream_t stream,
+                         bool reference_base = false);
 
 // ---- key switching and modulus switching (keyswitch.cu)
 // mac: dig (Eval) x key -> prod[item][2][l+1][N] (Eval)

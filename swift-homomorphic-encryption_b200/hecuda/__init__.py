@@ -22,7 +22,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), "libhecuda.so")
 
 HECUDA_OK = 0
-BASE_Q, BASE_Q_BSK, BASE_KEYSWITCH = 0, 1, 2
+BASE_Q, BASE_Q_BSK, BASE_KEYSWITCH, BASE_Q_AUX = 0, 1, 2, 3
 u64p = C.POINTER(C.c_uint64)
 
 # every symbol include/hecuda.h declares: (restype, argtypes)
@@ -40,6 +40,7 @@ SYMBOLS = {
     "hecuda_context_destroy": (C.c_int32, [_VP]),
     "hecuda_context_ciphertext_moduli_count": (C.c_int32, [_VP, C.POINTER(C.c_int32)]),
     "hecuda_context_bsk_moduli": (C.c_int32, [_VP, u64p, C.c_int32, C.POINTER(C.c_int32)]),
+    "hecuda_context_aux_moduli": (C.c_int32, [_VP, u64p, C.c_int32, C.POINTER(C.c_int32)]),
     "hecuda_context_root_tables": (C.c_int32, [_VP, C.c_uint64, u64p, u64p]),
     "hecuda_ntt_forward": (C.c_int32, [_VP, C.c_int32, _VP, C.c_int32, C.c_int64]),
     "hecuda_ntt_inverse": (C.c_int32, [_VP, C.c_int32, _VP, C.c_int32, C.c_int64]),
@@ -208,6 +209,8 @@ class Context:
         out = np.zeros(self.L + 1, dtype=np.uint64)
         _check(lib.hecuda_context_bsk_moduli(h, out.ctypes.data_as(u64p), len(out), C.byref(n)))
         self.bskModuli = [int(v) for v in out]
+        _check(lib.hecuda_context_aux_moduli(h, out.ctypes.data_as(u64p), len(out), C.byref(n)))
+        self.auxModuli = [int(v) for v in out]  # the base Bfv.mulAssign computes in (BASE_Q_AUX)
 
     @property
     def ciphertextModuli(self):
