@@ -62,6 +62,12 @@ const char *hecuda_last_error(void);
 int32_t hecuda_device_count(int32_t *count);
 int32_t hecuda_set_device(int32_t device); /* one process (or thread) per GPU; contexts belong to a device */
 
+/* Host-side NUMA placement for the GPU `device`: restricts the calling thread (and threads it creates afterwards) to
+ * the CPUs local to the GPU's PCIe root and prefers that NUMA node for page allocations, so that staging buffers
+ * allocated afterwards with hecuda_host_alloc sit next to the GPU.  One process per GPU calls it once after
+ * hecuda_set_device.  numa_node = -1 when the platform does not report one (then nothing is changed).  The reference
+ * has no counterpart (it never leaves the host); a Swift host calls this beside its first use of the context. */
+int32_t hecuda_bind_host_to_device(int32_t device, int32_t *numa_node, int32_t *cpu_count);
 /* Pinned host buffers for the host-pointer entry points (pageable memory works too, but cannot overlap copies). */
 int32_t hecuda_host_alloc(void **ptr, uint64_t bytes);
 int32_t hecuda_host_free(void *ptr);

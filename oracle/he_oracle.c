@@ -417,6 +417,15 @@ int orc_ntt_forward(int64_t n, const uint64_t *moduli, int32_t nmod, uint64_t *d
     }
     return 0;
 }
+/* rows in place on `threads` OpenMP threads (the benchmark's CPU arm: PolyBenchmark forwardNtt over many polynomials) */
+int orc_ntt_forward_threads(int64_t n, const uint64_t *moduli, int32_t nmod, uint64_t *data, int64_t rows, int32_t threads) {
+    for (int m = 0; m < nmod; m++)
+        if (!ntt_tables_get(n, moduli[m])) return -1; /* build the tables before the parallel region */
+    if (threads < 1) threads = 1;
+#pragma omp parallel for num_threads(threads) schedule(static)
+    for (i64 r = 0; r < rows; r++) ntt_forward_row(ntt_tables_get(n, moduli[r % nmod]), data + r * n);
+    return 0;
+}
 int orc_ntt_inverse(int64_t n, const uint64_t *moduli, int32_t nmod, uint64_t *data, int64_t rows) {
     for (i64 r = 0; r < rows; r++) {
         const ntt_tables *t = ntt_tables_get(n, moduli[r % nmod]);

@@ -40,6 +40,7 @@ uint64_t orc_shoup_mul_lazy(uint64_t x, uint64_t multiplicand, uint64_t p);
 /* In-place forward / inverse negacyclic NTT of `rows` rows, row i under modulus moduli[i % nmod]. */
 int orc_ntt_forward(int64_t n, const uint64_t *moduli, int32_t nmod, uint64_t *data, int64_t rows);
 int orc_ntt_inverse(int64_t n, const uint64_t *moduli, int32_t nmod, uint64_t *data, int64_t rows);
+int orc_ntt_forward_threads(int64_t n, const uint64_t *moduli, int32_t nmod, uint64_t *data, int64_t rows, int32_t threads);
 /* Root tables as the reference builds them (for parity of the product's setup). */
 int orc_ntt_tables(int64_t n, uint64_t p, uint64_t *roots, uint64_t *inv_roots_reordered, uint64_t *inv_degree,
                    uint64_t *inv_degree_root);

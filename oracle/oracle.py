@@ -56,6 +56,7 @@ def lib():
             getattr(L, name).argtypes = [C.c_uint64] * 3
         L.orc_ntt_forward.argtypes = [C.c_int64, u64p, C.c_int32, u64p, C.c_int64]
         L.orc_ntt_inverse.argtypes = [C.c_int64, u64p, C.c_int32, u64p, C.c_int64]
+        L.orc_ntt_forward_threads.argtypes = [C.c_int64, u64p, C.c_int32, u64p, C.c_int64, C.c_int32]
         L.orc_ntt_tables.argtypes = [C.c_int64, C.c_uint64, u64p, u64p, u64p, u64p]
         L.orc_divide_round_qlast.argtypes = [C.c_int64, u64p, C.c_int32, u64p]
         for name in ("orc_poly_add", "orc_poly_sub", "orc_poly_mul"):
@@ -148,6 +149,15 @@ def ntt_forward(n: int, moduli, data):
     if lib().orc_ntt_forward(n, _p(m), len(m), _p(d), d.shape[0]) != 0:
         raise ValueError("invalidNttModulus")
     return d
+
+
+def ntt_forward_inplace(n: int, moduli, data, threads: int = 1):
+    """In place over the rows of a C-contiguous uint64 array, on `threads` OpenMP threads (no copy: timing use)."""
+    m = _arr(moduli)
+    assert data.dtype == np.uint64 and data.flags.c_contiguous
+    if lib().orc_ntt_forward_threads(n, _p(m), len(m), _p(data), data.size // n, threads) != 0:
+        raise ValueError("invalidNttModulus")
+    return data
 
 
 def ntt_inverse(n: int, moduli, data):

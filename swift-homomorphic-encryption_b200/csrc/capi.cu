@@ -6,8 +6,13 @@
 #include "../../include/hecuda.h"
 
 #include <cuda_runtime.h>
+#include <sched.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 
 #include <algorithm>
+#include <cctype>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -276,6 +281,51 @@ int32_t hecuda_device_count(int32_t *count) {
 }
 int32_t hecuda_set_device(int32_t device) {
     CK(cudaSetDevice(device));
+    return HECUDA_OK;
+}
+
+// NUMA placement of the host side of one GPU: pin the calling thread (threads it creates later inherit the mask) to the
+// CPUs local to the GPU's PCIe root and prefer that node for page allocations, so that pinned staging buffers
+// allocated afterwards (hecuda_host_alloc) and the copies out of them do not cross the socket interconnect.
+int32_t hecuda_bind_host_to_device(int32_t device, int32_t *numa_node, int32_t *cpu_count) {
+    if (numa_node) *numa_node = -1;
+    if (cpu_count) *cpu_count = 0;
+    char bus[32] = {0};
+    CK(cudaDeviceGetPCIBusId(bus, sizeof(bus), device));
+    for (char *c = bus; *c; ++c) *c = (char)std::tolower((unsigned char)*c);
+    const std::string dir = std::string("/sys/bus/pci/devices/") + bus + "/";
+    int node = -1;
+    if (FILE *f = std::fopen((dir + "numa_node").c_str(), "r")) {
+        if (std::fscanf(f, "%d", &node) != 1) node = -1;
+        std::fclose(f);
+    }
+    char list[4096] = {0};
+    if (FILE *f = std::fopen((dir + "local_cpulist").c_str(), "r")) {
+        if (!std::fgets(list, sizeof(list), f)) list[0] = 0;
+        std::fclose(f);
+    }
+    cpu_set_t current, want;
+    CPU_ZERO(&want);
+    if (sched_getaffinity(0, sizeof(current), &current) != 0) return HECUDA_OK;  // nothing to intersect with: leave as is
+    int picked = 0;
+    for (char *tok = std::strtok(list, ",\n"); tok; tok = std::strtok(nullptr, ",\n")) {
+        int lo = 0, hi = 0;
+        const int fields = std::sscanf(tok, "%d-%d", &lo, &hi);
+        if (fields < 1) continue;
+        if (fields == 1) hi = lo;
+        for (int c = lo; c <= hi && c < CPU_SETSIZE; ++c)
+            if (CPU_ISSET(c, &current)) {
+                CPU_SET(c, &want);
+                ++picked;
+            }
+    }
+    if (picked > 0) sched_setaffinity(0, sizeof(want), &want);
+    if (node >= 0 && node < 64) {  // MPOL_PREFERRED: fall back to other nodes rather than fail when the node is full
+        unsigned long mask = 1ul << node;
+        syscall(SYS_set_mempolicy, 1 /* MPOL_PREFERRED */, &mask, sizeof(mask) * 8);
+    }
+    if (numa_node) *numa_node = node;
+    if (cpu_count) *cpu_count = picked;
     return HECUDA_OK;
 }
 

@@ -39,6 +39,7 @@ SYMBOLS = {
     "hecuda_context_create": (C.c_int32, [C.c_int64, u64p, C.c_int32, C.c_uint64, C.POINTER(_VP)]),
     "hecuda_context_destroy": (C.c_int32, [_VP]),
     "hecuda_context_ciphertext_moduli_count": (C.c_int32, [_VP, C.POINTER(C.c_int32)]),
+    "hecuda_bind_host_to_device": (C.c_int32, [C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "hecuda_context_bsk_moduli": (C.c_int32, [_VP, u64p, C.c_int32, C.POINTER(C.c_int32)]),
     "hecuda_context_aux_moduli": (C.c_int32, [_VP, u64p, C.c_int32, C.POINTER(C.c_int32)]),
     "hecuda_context_root_tables": (C.c_int32, [_VP, C.c_uint64, u64p, u64p]),
@@ -160,6 +161,15 @@ def device_count() -> int:
 
 def set_device(i: int):
     _check(load_library().hecuda_set_device(i))
+
+
+def bind_host_to_device(device: int) -> dict:
+    """Pins this thread (and threads created later) to the CPUs next to GPU `device` and prefers its NUMA node for
+    page allocations (hecuda_bind_host_to_device).  Call once per process after set_device, before allocating
+    PinnedBuffers.  Returns {"numa_node": n, "cpus": count} (numa_node -1 = not reported, nothing changed)."""
+    node, cpus = C.c_int32(-1), C.c_int32(0)
+    _check(load_library().hecuda_bind_host_to_device(device, C.byref(node), C.byref(cpus)))
+    return {"numa_node": node.value, "cpus": cpus.value}
 
 
 def kernel_launch_count() -> int:

@@ -35,10 +35,8 @@ def uniform(rng, moduli, shape_prefix, n):
     return out
 
 
-def main():
-    entries = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20
-    entry_size = int(sys.argv[2]) if len(sys.argv) > 2 else 64
-    threads = int(sys.argv[3]) if len(sys.argv) > 3 else 8
+def run(entries=1 << 20, entry_size=64, threads=8, per_thread=30, cpu=True):
+    """Returns the result dict on rank 0 (None on the other ranks)."""
     n, t = 4096, 17
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     if world > 1:  # one database shard per GPU (KeywordDatabase shards are independent): weak scaling, no data-path collective
@@ -94,7 +92,6 @@ def main():
         wire_reply, wire_skips = pir.PirWire.computeResponse(server, packed, seeds, key)
     wire_latency_ms = (time.perf_counter() - t0) / reps * 1e3
 
-    per_thread = 30
     def worker(count=per_thread):
         for _ in range(count):
             one()
@@ -121,7 +118,7 @@ def main():
     qps = world * threads * per_thread / concurrent_s
     if rank != 0:
         dist.destroy_process_group()
-        return
+        return None
 
     db_bytes = count * L * n * 8
     out = {
@@ -133,14 +130,14 @@ def main():
         "wire": {"latency_ms": round(wire_latency_ms, 3), "request_bytes": int(packed.nbytes + seeds.nbytes),
                  "reply_bytes": int(wire_reply.nbytes), "skip_lsbs": wire_skips,
                  "unpacked_request_bytes": int(query.nbytes), "unpacked_reply_bytes": int(2 * n * 8 * chunk_count)},
-        "threads": threads, "n_gpus": world, "scaling": "weak (one shard per GPU)",
+        "threads": threads, "queries_per_thread": per_thread, "concurrent_s": concurrent_s, "n_gpus": world, "scaling": "weak (one shard per GPU)",
         "value": round(qps, 1), "unit": "queries/s",
         "db_scan_gbs_at_value": round(qps * db_bytes / 1e9, 1),
         "gpu_launches": hecuda.kernel_launch_count(),
     }
     if world > 1:
         dist.destroy_process_group()
-    if os.environ.get("PIR_CPU", "1") == "1" and world == 1:
+    if cpu and os.environ.get("PIR_CPU", "1") == "1" and world == 1:
         from oracle import oracle as orc
         from oracle import pir_oracle as opir
         o = orc.Context(n, PIR_MODULI, t)
@@ -171,7 +168,16 @@ def main():
         out["cpu_baseline"] = {"value": round(1.0 / total, 4), "unit": "queries/s", "cores": orc.num_threads(), "kind": "port",
                                "sample": f"expand {expand_s:.2f}s + first-dimension scan {scan_s:.2f}s (timed on {cap * dim0} "
                                          f"of {count} plaintexts, scaled) + ct x ct / relinearize {tail_s:.2f}s"}
-    print(json.dumps(out))
+    return out
+
+
+def main():
+    entries = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20
+    entry_size = int(sys.argv[2]) if len(sys.argv) > 2 else 64
+    threads = int(sys.argv[3]) if len(sys.argv) > 3 else 8
+    out = run(entries, entry_size, threads)
+    if out is not None:
+        print(json.dumps(out))
 
 
 if __name__ == "__main__":
