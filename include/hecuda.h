@@ -90,6 +90,14 @@ int32_t hecuda_context_aux_moduli(const hecuda_context *ctx, uint64_t *out, int3
  * inverse table is indexed like the forward one (inv[i] = roots[i]^-1). */
 int32_t hecuda_context_root_tables(const hecuda_context *ctx, uint64_t modulus, uint64_t *roots, uint64_t *inverse_roots);
 
+/* _RnsTool.liftQToQBsk (RnsTool.swift:324-331) and _RnsTool.floorQBskToQ (RnsTool.swift:453-456) at the top level, on
+ * their own: Coeff-format polynomials, host pointers.  lift: poly_count x L x N canonical residues mod q_i ->
+ * poly_count x (2L+1) x N over [q_0..q_{L-1}, Bsk]; floor: poly_count x (2L+1) x N (the caller has already multiplied by
+ * t, Bfv+Multiply.swift:40) -> poly_count x L x N.  These run over the reference's Bsk whatever base hecuda_bfv_multiply
+ * uses internally (HECUDA_BASE_Q_AUX). */
+int32_t hecuda_rnstool_lift_q_to_qbsk(const hecuda_context *ctx, const uint64_t *polys, uint64_t *out, int64_t poly_count);
+int32_t hecuda_rnstool_floor_qbsk_to_q(const hecuda_context *ctx, const uint64_t *polys, uint64_t *out, int64_t poly_count);
+
 /* PolyRq.forwardNtt() / inverseNtt() -- PolyRq+Ntt.swift:230,541 (PolyContext.forwardNtt(poly:) :209-222,
  * inverseNtt(poly:) :524-533), batched: data = poly_count x row_count x N, in place. */
 int32_t hecuda_ntt_forward(const hecuda_context *ctx, int32_t base, uint64_t *data, int32_t row_count, int64_t poly_count);

@@ -94,7 +94,8 @@ __global__ void __launch_bounds__(kThreads) lift_kernel(const u64 *__restrict__ 
             u128 acc = (u128)rc * c.qr[j];
 #pragma unroll
             for (int i = 0; i < L; ++i) mac128(acc, z[k][i], c.mat[j][i]);
-            o[k] = csub(mont_reduce(acc, c.b[j], c.b_ninv[j]), c.b[j]);
+            const u64 red = mont_reduce(acc, c.b[j], c.b_ninv[j]);
+            o[k] = c.wide_sums ? barrett64(red, c.b[j], c.b_mu1[j]) : csub(red, c.b[j]);
         }
         stc<COLS>(dst + (int64_t)(L + j) * n, o);
     }
@@ -234,7 +235,7 @@ __global__ void __launch_bounds__(kThreads) floor_kernel(const u64 *__restrict__
             mac128(acc, w[i], c.amat[i]);
         }
         u64 alpha = mont_reduce(acc, msk, c.b_ninv[L]);
-        alpha = csub(csub(csub(alpha, 4 * msk), 2 * msk), msk);
+        alpha = c.wide_sums ? barrett64(alpha, msk, c.msk_mu1) : csub(csub(csub(alpha, 4 * msk), 2 * msk), msk);
         const bool exceeds = alpha > (msk >> 1);
         const u64 alpha_c = exceeds ? msk - alpha : alpha;
 #pragma unroll

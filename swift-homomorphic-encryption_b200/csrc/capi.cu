@@ -487,6 +487,32 @@ int32_t hecuda_ntt_inverse(const hecuda_context *h, int32_t base, uint64_t *data
     if (!make_map(*h->ctx, base, rows, map, err)) return fail(HECUDA_ERR_INVALID_ARGUMENT, err);
     return ntt_host(h, map, data, (size_t)rows * h->ctx->n, polys, rows, true);
 }
+// Stage-level BEHZ entry points over the reference's [Q, Bsk] (RnsTool.swift:324-331, 453-456), Coeff format.
+int32_t hecuda_rnstool_lift_q_to_qbsk(const hecuda_context *h, const uint64_t *polys, uint64_t *out, int64_t count) {
+    int32_t rc = check_ctx(h);
+    if (rc) return rc;
+    if (count < 0 || ((!polys || !out) && count)) return fail(HECUDA_ERR_INVALID_ARGUMENT, "invalid buffers / poly_count");
+    const Context &c = *h->ctx;
+    const size_t in_words = (size_t)c.L * c.n, out_words = (size_t)(2 * c.L + 1) * c.n;
+    std::vector<HostIo> in = {{(const u64 *)polys, in_words}};
+    return host_pipeline(h, count, std::max<int64_t>(1, (int64_t)((size_t)4 * 1024 * 1024 / out_words)), 0, in, (u64 *)out, out_words,
+                         [&](Workspace &w, const std::vector<const u64 *> &d_in, u64 *d_out, int64_t n_items) {
+                             return launch_lift(c, d_in[0], 1, d_out, 1, 0, n_items, w.stream, /*reference_base=*/true);
+                         });
+}
+int32_t hecuda_rnstool_floor_qbsk_to_q(const hecuda_context *h, const uint64_t *polys, uint64_t *out, int64_t count) {
+    int32_t rc = check_ctx(h);
+    if (rc) return rc;
+    if (count < 0 || ((!polys || !out) && count)) return fail(HECUDA_ERR_INVALID_ARGUMENT, "invalid buffers / poly_count");
+    const Context &c = *h->ctx;
+    const size_t in_words = (size_t)(2 * c.L + 1) * c.n, out_words = (size_t)c.L * c.n;
+    std::vector<HostIo> in = {{(const u64 *)polys, in_words}};
+    return host_pipeline(h, count, std::max<int64_t>(1, (int64_t)((size_t)4 * 1024 * 1024 / in_words)), 0, in, (u64 *)out, out_words,
+                         [&](Workspace &w, const std::vector<const u64 *> &d_in, u64 *d_out, int64_t n_items) {
+                             return launch_floor(c, d_in[0], d_out, n_items, w.stream, /*reference_base=*/true);
+                         });
+}
+
 static int32_t ntt_rows_host(const hecuda_context *h, uint64_t modulus, uint64_t *data, int64_t rows, bool inverse) {
     int32_t rc = check_ctx(h);
     if (rc) return rc;

@@ -271,18 +271,26 @@ Context *Context::create(int64_t n, const u64 *coeff_moduli, int nmod, u64 t, st
         build_behz(c->aux, false, c->lift_mul, c->floor_mul);
     }
 
-    // ---- range check behind the single conditional subtraction after the lift / approximate-floor sums:
-    // (b_j^2 + L q_max b_j) / 2^64 < b_j  <=>  b_j + L q_max < 2^64   (see behz.cu)
-    {
+    // ---- ranges of the lazy sums (behz.cu).  The fast path ends the lift sums with one conditional subtraction
+    // ((b_j^2 + L q_max b_j) / 2^64 < b_j  <=>  b_j + L q_max < 2^64) and alpha with three (< 8 m_sk); parameter sets with
+    // many wide moduli take a Barrett reduction there instead.  Every 128-bit accumulator must stay below 2^128.
+    auto check_ranges = [&](const std::vector<u64> &base, LiftConsts &lf, FloorConsts &fl) -> bool {
         u64 qmax = 0, bmax = 0;
         for (u64 v : c->q) qmax = v > qmax ? v : qmax;
-        for (u64 v : c->bsk) bmax = v > bmax ? v : bmax;
-        for (u64 v : c->aux) bmax = v > bmax ? v : bmax;
-        if ((u128)bmax + (u128)L * qmax >= ((u128)1 << 64)) {
-            err = "unsupportedHeOperation: " + std::to_string(L) + " ciphertext moduli of this size exceed the lazy-sum bound";
-            delete c;
-            return nullptr;
-        }
+        for (u64 v : base) bmax = v > bmax ? v : bmax;
+        const double worst = std::log2((double)(L + 2)) + std::log2((double)qmax) + std::log2((double)bmax);
+        if (worst >= 127.0) return false;
+        // (b + L q_max < 2^64 also keeps f_msk < 2 m_sk and with it alpha < 8 m_sk for every supported L)
+        const bool wide = (u128)bmax + (u128)L * qmax >= ((u128)1 << 64);
+        lf.wide_sums = fl.wide_sums = wide ? 1 : 0;
+        for (int j = 0; j <= L; ++j) lf.b_mu1[j] = (u64)(((u128)1 << 64) / base[j]);
+        fl.msk_mu1 = (u64)(((u128)1 << 64) / base[L]);
+        return true;
+    };
+    if (!check_ranges(c->bsk, c->lift, c->floor) || !check_ranges(c->aux, c->lift_mul, c->floor_mul)) {
+        err = "unsupportedHeOperation: " + std::to_string(L) + " ciphertext moduli of this size overflow the 128-bit lazy sums";
+        delete c;
+        return nullptr;
     }
 
     // ---- divide-and-round constants

@@ -64,6 +64,8 @@ struct NttRowMap {       // which modulus slot each row of a polynomial uses:
 //   out_j = [ (sum_i z_i mat[j][i] + r_c qr[j]) 2^-64 ]_{b_j}   with mat, qr pre-multiplied by 2^64 (Montgomery)
 struct LiftConsts {
     int L;
+    int wide_sums;                   // the lazy sums may exceed 2 b_j: finish with a Barrett reduction (many wide moduli)
+    u64 b_mu1[kMaxL + 1];            // floor(2^64 / b_j)
     u64 q[kMaxL];
     u64 in_w[kMaxL], in_wp[kMaxL];   // m~ (Q/q_i)^-1 mod q_i
     u32 punct_mt[kMaxL];             // (Q/q_i) mod 2^32
@@ -79,6 +81,8 @@ struct LiftConsts {
 //   out_i = [sum_k w_k omat[i][k] + alpha' D_i]_{q_i},  (alpha', D) = alpha > m_sk/2 ? (m_sk-alpha, B) : (alpha, -B)
 struct FloorConsts {
     int L;
+    int wide_sums;                     // alpha may exceed 8 m_sk: finish with a Barrett reduction
+    u64 msk_mu1;                       // floor(2^64 / m_sk)
     u64 q[kMaxL], q_ninv[kMaxL];
     u64 inq_w[kMaxL], inq_wp[kMaxL];   // (Q/q_i)^-1 mod q_i
     u64 b[kMaxL + 1], b_ninv[kMaxL + 1];

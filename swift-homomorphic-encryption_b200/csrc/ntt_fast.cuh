@@ -261,22 +261,20 @@ HE_HD u64 shoup4(u64 y, u64 w, u64 wp, u64 np) {
 #if defined(__CUDA_ARCH__)
     u64 v;
     asm volatile("{\n\t"
-        ".reg .u32 y0, y1, w0, w1, p0, p1, n0, n1, a1, b1, q0, q1, v0, v1;\n\t"
+        ".reg .u32 y0, y1, w0, w1, p0, p1, n0, n1, a1, b1, q0, q1, v0, v1, z;\n\t"
         ".reg .u64 A, B, Q, V;\n\t"
         "mov.b64 {y0, y1}, %1;\n\t"
         "mov.b64 {w0, w1}, %2;\n\t"
         "mov.b64 {p0, p1}, %3;\n\t"
         "mov.b64 {n0, n1}, %4;\n\t"
-        "mul.wide.u32 A, y1, p0;\n\t"
-        "mul.wide.u32 B, y0, p1;\n\t"
-        "mul.wide.u32 Q, y1, p1;\n\t"
+        "mul.hi.u32 a1, y1, p0;\n\t"
+        "mul.hi.u32 b1, y0, p1;\n\t"
+        "mov.u32 z, 0;\n\t"
+        "mov.b64 A, {a1, z};\n\t"
+        "mov.b64 B, {b1, z};\n\t"
+        "mad.wide.u32 Q, y1, p1, A;\n\t"
+        "add.u64 Q, Q, B;\n\t"
         "mov.b64 {q0, q1}, Q;\n\t"
-        "mov.b64 {v0, a1}, A;\n\t"
-        "mov.b64 {v0, b1}, B;\n\t"
-        "add.cc.u32 q0, q0, a1;\n\t"
-        "addc.u32 q1, q1, 0;\n\t"
-        "add.cc.u32 q0, q0, b1;\n\t"
-        "addc.u32 q1, q1, 0;\n\t"
         "mul.wide.u32 V, y0, w0;\n\t"
         "mad.wide.u32 V, q0, n0, V;\n\t"
         "mov.b64 {v0, v1}, V;\n\t"

@@ -39,6 +39,8 @@ SYMBOLS = {
     "hecuda_context_create": (C.c_int32, [C.c_int64, u64p, C.c_int32, C.c_uint64, C.POINTER(_VP)]),
     "hecuda_context_destroy": (C.c_int32, [_VP]),
     "hecuda_context_ciphertext_moduli_count": (C.c_int32, [_VP, C.POINTER(C.c_int32)]),
+    "hecuda_rnstool_lift_q_to_qbsk": (C.c_int32, [_VP, _VP, _VP, C.c_int64]),
+    "hecuda_rnstool_floor_qbsk_to_q": (C.c_int32, [_VP, _VP, _VP, C.c_int64]),
     "hecuda_bind_host_to_device": (C.c_int32, [C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "hecuda_context_bsk_moduli": (C.c_int32, [_VP, u64p, C.c_int32, C.POINTER(C.c_int32)]),
     "hecuda_context_aux_moduli": (C.c_int32, [_VP, u64p, C.c_int32, C.POINTER(C.c_int32)]),
@@ -517,6 +519,28 @@ class Bfv:
         count = b.size // size
         out = np.empty((count, rowCount, context.degree), dtype=np.uint64)
         _check(load_library().hecuda_poly_load(context._h, base, b.ctypes.data_as(C.c_void_p), skipLSBs, _ptr(out), rowCount, count))
+        return out
+
+    @staticmethod
+    def liftQToQBsk(context: Context, polys):
+        """_RnsTool.liftQToQBsk (RnsTool.swift:324-331): (..., L, N) Coeff -> (..., 2L+1, N) over [Q, Bsk]."""
+        d = _host(polys)
+        L, n = context.L, context.degree
+        if d.shape[-2:] != (L, n):
+            raise HeError(-1, "invalidPolyContext: liftQToQBsk takes top-level polynomials")
+        out = np.empty(d.shape[:-2] + (2 * L + 1, n), dtype=np.uint64)
+        _check(load_library().hecuda_rnstool_lift_q_to_qbsk(context._h, _ptr(d), _ptr(out), d.size // (L * n)))
+        return out
+
+    @staticmethod
+    def floorQBskToQ(context: Context, polys):
+        """_RnsTool.floorQBskToQ (RnsTool.swift:453-456): (..., 2L+1, N) Coeff over [Q, Bsk] -> (..., L, N)."""
+        d = _host(polys)
+        L, n = context.L, context.degree
+        if d.shape[-2:] != (2 * L + 1, n):
+            raise HeError(-1, "invalidPolyContext: floorQBskToQ takes polynomials over [Q, Bsk]")
+        out = np.empty(d.shape[:-2] + (L, n), dtype=np.uint64)
+        _check(load_library().hecuda_rnstool_floor_qbsk_to_q(context._h, _ptr(d), _ptr(out), d.size // ((2 * L + 1) * n)))
         return out
 
     @staticmethod
