@@ -33,6 +33,7 @@ extern "C" {
 #endif
 
 typedef struct hecuda_context hecuda_context; /* Context<Bfv<UInt64>>, Context.swift:19 */
+typedef struct hecuda_comm hecuda_comm;       /* NCCL communicator of the key broadcast (no reference counterpart) */
 typedef struct hecuda_evk hecuda_evk;         /* EvaluationKey<Bfv<UInt64>>, Keys.swift:66-99,222 */
 typedef struct hecuda_pnns_matrix hecuda_pnns_matrix;   /* PlaintextMatrix<Bfv<UInt64>, Eval>, .diagonal packing */
 typedef struct hecuda_pir_database hecuda_pir_database; /* ProcessedDatabase<Bfv<UInt64>>, IndexPir/IndexPirDatabase.swift */
@@ -126,6 +127,20 @@ int32_t hecuda_evk_destroy(hecuda_evk *evk);
  * ncclBroadcast can replicate it from rank 0. */
 int32_t hecuda_evk_create_empty(const hecuda_context *ctx, hecuda_evk **out);
 int32_t hecuda_evk_device_buffer(hecuda_evk *evk, void **device_ptr, uint64_t *bytes);
+
+/* Multi-GPU setup: ciphertext batches shard over the GPUs with no data-path collective; the only
+ * exchange is the evaluation key, broadcast once over NCCL (NVLink / NVSwitch) from the rank that received it from the
+ * client.  One process per GPU.  Rank 0 calls hecuda_comm_unique_id and hands the 128 bytes to the other ranks over the
+ * host's own channel; every rank then calls hecuda_comm_create (collective), creates its key -- hecuda_evk_create with
+ * the key material on the root, hecuda_evk_create_empty elsewhere -- and calls hecuda_evk_broadcast (collective) with
+ * the same has_relin flag and Galois element list (the EvaluationKeyConfig, known to every rank, Keys.swift:228-262).
+ * NCCL is opened at run time (libnccl.so.2, or $HECUDA_NCCL_LIBRARY); without it these return HECUDA_ERR_UNSUPPORTED. */
+#define HECUDA_COMM_UNIQUE_ID_BYTES 128
+int32_t hecuda_comm_unique_id(uint8_t *id /* HECUDA_COMM_UNIQUE_ID_BYTES */);
+int32_t hecuda_comm_create(const uint8_t *id, int32_t rank, int32_t world_size, hecuda_comm **out);
+int32_t hecuda_comm_destroy(hecuda_comm *comm);
+int32_t hecuda_evk_broadcast(hecuda_evk *evk, hecuda_comm *comm, int32_t root, int32_t has_relin, const uint32_t *elements,
+                             int32_t element_count);
 
 /* Bfv.relinearize(_:using:) -- Bfv/Bfv.swift:201-219 (key switch: Bfv+Keys.swift:123-208).
  * ct3: batch x 3 x l x N (Coeff), l = moduli_count in [1, L]; out: batch x 2 x l x N (Coeff). */

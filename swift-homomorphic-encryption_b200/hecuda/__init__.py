@@ -41,6 +41,10 @@ SYMBOLS = {
     "hecuda_context_ciphertext_moduli_count": (C.c_int32, [_VP, C.POINTER(C.c_int32)]),
     "hecuda_rnstool_lift_q_to_qbsk": (C.c_int32, [_VP, _VP, _VP, C.c_int64]),
     "hecuda_rnstool_floor_qbsk_to_q": (C.c_int32, [_VP, _VP, _VP, C.c_int64]),
+    "hecuda_comm_unique_id": (C.c_int32, [_VP]),
+    "hecuda_comm_create": (C.c_int32, [_VP, C.c_int32, C.c_int32, C.POINTER(_VP)]),
+    "hecuda_comm_destroy": (C.c_int32, [_VP]),
+    "hecuda_evk_broadcast": (C.c_int32, [_VP, _VP, C.c_int32, C.c_int32, _VP, C.c_int32]),
     "hecuda_bind_host_to_device": (C.c_int32, [C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "hecuda_context_bsk_moduli": (C.c_int32, [_VP, u64p, C.c_int32, C.POINTER(C.c_int32)]),
     "hecuda_context_aux_moduli": (C.c_int32, [_VP, u64p, C.c_int32, C.POINTER(C.c_int32)]),
@@ -163,6 +167,40 @@ def device_count() -> int:
 
 def set_device(i: int):
     _check(load_library().hecuda_set_device(i))
+
+
+class Communicator:
+    """NCCL communicator of the evaluation-key broadcast, through the C ABI (hecuda_comm_*): what a torch-free host uses.
+    Rank 0 calls Communicator.uniqueId() and hands the 128 bytes to the other ranks; every rank then constructs the
+    communicator (collective) and calls broadcast (collective) on its EvaluationKey."""
+
+    @staticmethod
+    def uniqueId() -> bytes:
+        buf = (C.c_uint8 * 128)()
+        _check(load_library().hecuda_comm_unique_id(buf))
+        return bytes(buf)
+
+    def __init__(self, unique_id: bytes, rank: int, world_size: int):
+        h = C.c_void_p()
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        _check(load_library().hecuda_comm_create(buf, rank, world_size, C.byref(h)))
+        self._h, self.rank, self.world_size = h, rank, world_size
+
+    def broadcast(self, key: "EvaluationKey", root: int = 0, has_relin: bool = True, galois_elements=()):
+        elems = (C.c_uint32 * max(1, len(galois_elements)))(*[int(e) for e in galois_elements])
+        _check(load_library().hecuda_evk_broadcast(key._h, self._h, root, 1 if has_relin else 0, elems, len(galois_elements)))
+        return key
+
+    def close(self):
+        if self._h is not None:
+            load_library().hecuda_comm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def bind_host_to_device(device: int) -> dict:

@@ -61,14 +61,14 @@ def test_product_does_not_import_oracle():
                 assert "he_oracle" not in src and "from oracle" not in src and "import oracle" not in src, f
 
 
-def _build_c_example(tmp_path):
+def _build_c_example(tmp_path, name="multiply_relinearize"):
     import shutil
     import subprocess
     gcc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else shutil.which("gcc")
     libdir = os.path.join(ROOT, "swift-homomorphic-encryption_b200")
-    out = str(tmp_path / "multiply_relinearize")
+    out = str(tmp_path / name)
     subprocess.check_call([gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-O1", "-I" + os.path.join(ROOT, "include"),
-                           os.path.join(ROOT, "examples", "multiply_relinearize.c"), "-L" + libdir, "-lhecuda",
+                           os.path.join(ROOT, "examples", name + ".c"), "-L" + libdir, "-lhecuda",
                            "-Wl,-rpath," + libdir, "-o", out])
     return out
 
@@ -89,3 +89,47 @@ def test_c_example_runs_on_gpu(tmp_path):
     run = subprocess.run([_build_c_example(tmp_path)], capture_output=True, text=True)
     assert run.returncode == 0, run.stderr
     assert "16 products" in run.stdout
+
+
+def test_key_broadcast_example_links(tmp_path):
+    """examples/evk_broadcast.c (multi-GPU setup through the C ABI: NCCL communicator + evaluation-key broadcast) is
+    strict C99 and links; without a GPU it fails loudly."""
+    import subprocess
+    exe = _build_c_example(tmp_path, "evk_broadcast")
+    import torch
+    if not torch.cuda.is_available():
+        run = subprocess.run([exe, "0", "1", str(tmp_path / "id")], capture_output=True, text=True)
+        assert run.returncode != 0
+
+
+def _checksums(outputs):
+    import re
+    return [int(re.search(r"checksum (\d+)", o).group(1)) for o in outputs]
+
+
+@pytest.mark.gpu
+def test_key_broadcast_example_single_process(tmp_path):
+    import subprocess
+    run = subprocess.run([_build_c_example(tmp_path, "evk_broadcast"), "0", "1", str(tmp_path / "id")], capture_output=True, text=True)
+    assert run.returncode == 0, run.stderr
+    assert "ciphertexts [0, 8)" in run.stdout
+
+
+@pytest.mark.gpu
+def test_key_broadcast_over_nccl_two_processes(tmp_path):
+    """Two processes, two GPUs, no torch: rank 0 creates the relinearization and Galois keys, hecuda_evk_broadcast moves
+    them over NCCL, each rank relinearizes and rotates its half of the batch; the halves' checksums add up to the
+    single-process checksum (mod 2^64)."""
+    import subprocess
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    exe = _build_c_example(tmp_path, "evk_broadcast")
+    single = subprocess.run([exe, "0", "1", str(tmp_path / "id1")], capture_output=True, text=True)
+    assert single.returncode == 0, single.stderr
+    idfile = str(tmp_path / "id2")
+    procs = [subprocess.Popen([exe, str(r), "2", idfile], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=300) for p in procs]
+    assert all(p.returncode == 0 for p in procs), [o[1] for o in outs]
+    halves = _checksums([o[0] for o in outs])
+    assert sum(halves) % (1 << 64) == _checksums([single.stdout])[0]
