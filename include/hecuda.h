@@ -81,6 +81,14 @@ int32_t hecuda_host_unregister(void *ptr);
  * constants (RnsTool.swift:30-33,132-251) and key-/mod-switch constants (PolyContext.swift:108-111). */
 int32_t hecuda_context_create(int64_t poly_degree, const uint64_t *coefficient_moduli, int32_t moduli_count,
                               uint64_t plaintext_modulus, hecuda_context **out);
+/* Context<Bfv<UInt32>>: the reference's 32-bit scalar type (HeScheme.swift, ModularArithmetic/Scalar.swift:498-511) --
+ * moduli below 2^30, m~ = 2^16, rnsCorrectionFactor 2^30 - 20405, 29-bit Bsk primes.  Buffers of the hecuda_u32_* entry
+ * points are uint32_t in the same layouts as their uint64_t counterparts; residues cross PCIe as 4 bytes and the NTT
+ * butterflies run in 32-bit arithmetic.  The uint64_t entry points also accept such a context (64-bit storage of the
+ * same residues); the application drivers (MulPir / PNNS / codec / decrypt) are uint64_t-only. */
+int32_t hecuda_context_create_u32(int64_t poly_degree, const uint32_t *coefficient_moduli, int32_t moduli_count,
+                                  uint32_t plaintext_modulus, hecuda_context **out);
+int32_t hecuda_context_word_bits(const hecuda_context *ctx, int32_t *bits); /* 64 or 32 */
 int32_t hecuda_context_destroy(hecuda_context *ctx);
 /* Introspection used by the parity tests (the reference exposes the same values as public lets). */
 int32_t hecuda_context_ciphertext_moduli_count(const hecuda_context *ctx, int32_t *count);
@@ -370,6 +378,19 @@ int32_t hecuda_bfv_decrypt(const hecuda_context *ctx, const uint64_t *secret_key
 
 /* Bookkeeping for bench.py: number of kernel launches issued by this library in the calling process so far. */
 uint64_t hecuda_kernel_launch_count(void);
+
+/* ---- Bfv<UInt32> data path: uint32_t buffers, context from hecuda_context_create_u32 (else INVALID_ARGUMENT).
+ * Each mirrors the uint64_t entry point of the same name (same shapes, same errors). */
+int32_t hecuda_u32_ntt_forward(const hecuda_context *ctx, int32_t base, uint32_t *data, int32_t row_count, int64_t poly_count);
+int32_t hecuda_u32_ntt_inverse(const hecuda_context *ctx, int32_t base, uint32_t *data, int32_t row_count, int64_t poly_count);
+int32_t hecuda_u32_bfv_multiply(const hecuda_context *ctx, const uint32_t *lhs, const uint32_t *rhs, uint32_t *out, int64_t batch);
+int32_t hecuda_u32_evk_create(const hecuda_context *ctx, const uint32_t *relin_key, hecuda_evk **out);
+int32_t hecuda_u32_bfv_relinearize(const hecuda_context *ctx, const hecuda_evk *evk, const uint32_t *ct3, int32_t moduli_count,
+                                   uint32_t *out, int64_t batch);
+int32_t hecuda_u32_bfv_mod_switch_down(const hecuda_context *ctx, const uint32_t *ct, int32_t poly_count, int32_t moduli_count,
+                                       uint32_t *out, int64_t batch);
+int32_t hecuda_u32_rnstool_lift_q_to_qbsk(const hecuda_context *ctx, const uint32_t *polys, uint32_t *out, int64_t poly_count);
+int32_t hecuda_u32_rnstool_floor_qbsk_to_q(const hecuda_context *ctx, const uint32_t *polys, uint32_t *out, int64_t poly_count);
 
 #ifdef __cplusplus
 }

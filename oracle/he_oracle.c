@@ -560,10 +560,15 @@ void orc_convert_approximate(int64_t n, const uint64_t *q, int32_t nq, const uin
  * BEHZ RNS tool -- Sources/HomomorphicEncryption/RnsTool.swift
  * ===================================================================================== */
 
-#define ORC_MTILDE ((u64)1 << 32)                  /* ModularArithmetic/Scalar.swift:522-524 */
-#define ORC_GAMMA ((((u64)1) << 62) - 40797)       /* ModularArithmetic/Scalar.swift:516-520 */
+/* Word-size constants (ModularArithmetic/Scalar.swift:498-525): Bfv<UInt64> uses m~ = 2^32, gamma = 2^62 - 40797 and
+ * 61-bit Bsk primes; Bfv<UInt32> uses m~ = 2^16, gamma = 2^30 - 20405 and 29-bit Bsk primes (bitWidth - 3).  The residues
+ * are the same numbers whatever the storage width, so one restatement with these three constants covers both. */
+#define ORC_MTILDE (rt->mtilde)
+#define ORC_GAMMA (rt->gamma)
 
 struct orc_rnstool {
+    int word_bits;     /* 64 or 32 */
+    u64 mtilde, gamma; /* T.mTilde, T.rnsCorrectionFactor */
     i64 n;
     int nq, nb; /* nb = nq + 1 = |Bsk| */
     u64 q[ORC_MAX_MODULI];
@@ -619,9 +624,14 @@ static u64 q_div_t_mod(const u64 *moduli, int n, u64 t, u64 qi) {
     return r;
 }
 
-orc_rnstool *orc_rnstool_create(int64_t n, const uint64_t *q, int32_t nq, uint64_t t) {
-    if (nq < 1 || nq + 2 > ORC_MAX_MODULI) return NULL;
+orc_rnstool *orc_rnstool_create_w(int64_t n, const uint64_t *q, int32_t nq, uint64_t t, int32_t word_bits) {
+    if (nq < 1 || nq + 2 > ORC_MAX_MODULI || (word_bits != 64 && word_bits != 32)) return NULL;
+    for (int i = 0; i < nq; i++)
+        if (word_bits == 32 && q[i] >= ((u64)1 << 30)) return NULL; /* Modulus<UInt32>.max, Modulus.swift:177-180 */
     orc_rnstool *rt = (orc_rnstool *)calloc(1, sizeof(orc_rnstool));
+    rt->word_bits = word_bits;
+    rt->mtilde = word_bits == 64 ? ((u64)1 << 32) : ((u64)1 << 16);
+    rt->gamma = word_bits == 64 ? ((((u64)1) << 62) - 40797) : ((((u64)1) << 30) - 20405);
     rt->n = n;
     rt->nq = nq;
     rt->nb = nq + 1;
@@ -630,7 +640,7 @@ orc_rnstool *orc_rnstool_create(int64_t n, const uint64_t *q, int32_t nq, uint64
     for (int i = 0; i < nq; i++) { rt->q[i] = q[i]; rt->qmod[i] = modulus_make(q[i]); }
     /* Bsk primes: RnsTool.swift:30-33 -- (bitWidth-3)-bit, ascending, NTT-friendly for degree n */
     int32_t bits[ORC_MAX_MODULI];
-    for (int i = 0; i < rt->nb; i++) bits[i] = 61;
+    for (int i = 0; i < rt->nb; i++) bits[i] = word_bits - 3;
     if (orc_generate_primes(bits, rt->nb, 1, n, rt->bsk) != rt->nb) { free(rt); return NULL; }
     for (int i = 0; i < nq; i++) rt->qbsk[i] = q[i];
     for (int j = 0; j < rt->nb; j++) rt->qbsk[nq + j] = rt->bsk[j];
@@ -675,6 +685,9 @@ orc_rnstool *orc_rnstool_create(int64_t n, const uint64_t *q, int32_t nq, uint64
     baseconv_init(&rt->b_to_msk, rt->bsk, nB, &msk, 1);
     baseconv_init(&rt->b_to_q, rt->bsk, nB, q, nq);
     return rt;
+}
+orc_rnstool *orc_rnstool_create(int64_t n, const uint64_t *q, int32_t nq, uint64_t t) {
+    return orc_rnstool_create_w(n, q, nq, t, 64);
 }
 void orc_rnstool_destroy(orc_rnstool *rt) { free(rt); }
 int32_t orc_rnstool_bsk(const orc_rnstool *rt, uint64_t *out) {
@@ -808,6 +821,10 @@ struct orc_context {
 };
 
 orc_context *orc_context_create(int64_t n, const uint64_t *coeff_moduli, int32_t nmod, uint64_t t) {
+    return orc_context_create_w(n, coeff_moduli, nmod, t, 64);
+}
+/* word_bits = 32: Context<Bfv<UInt32>> (same residues, Bfv<UInt32>'s m~ / gamma / Bsk) */
+orc_context *orc_context_create_w(int64_t n, const uint64_t *coeff_moduli, int32_t nmod, uint64_t t, int32_t word_bits) {
     if (nmod < 2 || nmod > ORC_MAX_MODULI / 2 - 2) return NULL;
     /* keep the per-call scratch on the heap (no mmap/munmap + page faults per multiply): a fair CPU baseline */
     mallopt(M_MMAP_THRESHOLD, 1 << 30);
@@ -826,7 +843,7 @@ orc_context *orc_context_create(int64_t n, const uint64_t *coeff_moduli, int32_t
         /* NOTE: below the top level the reference carves its Bsk/m~ base out of the top-level one
          * (RnsTool.swift:185-186); only scaleAndRound -- which does not touch that base -- is used from
          * tools[l < L] here.  ct x ct multiply is top level only ("levels"). */
-        ctx->tools[l] = orc_rnstool_create(n, ctx->q, l, t);
+        ctx->tools[l] = orc_rnstool_create_w(n, ctx->q, l, t, word_bits);
         if (!ctx->tools[l]) { free(ctx); return NULL; }
     }
     orc_rnstool *top = ctx->tools[ctx->L];

@@ -54,6 +54,7 @@ void orc_poly_mul(int64_t n, const uint64_t *moduli, int32_t nmod, uint64_t *lhs
 /* ---- RNS tool built from arbitrary Q (for the reference's RnsToolTests KATs) ---- */
 typedef struct orc_rnstool orc_rnstool;
 orc_rnstool *orc_rnstool_create(int64_t n, const uint64_t *q, int32_t nq, uint64_t t);
+orc_rnstool *orc_rnstool_create_w(int64_t n, const uint64_t *q, int32_t nq, uint64_t t, int32_t word_bits);
 void orc_rnstool_destroy(orc_rnstool *);
 int32_t orc_rnstool_bsk(const orc_rnstool *, uint64_t *out); /* writes nq+1 Bsk primes, returns count */
 /* poly in base [Bsk, m~] ((nq+2) x n) -> base Bsk ((nq+1) x n), in place */
@@ -77,6 +78,7 @@ void orc_convert_approximate(int64_t n, const uint64_t *q, int32_t nq, const uin
 /* ---- BFV context (Context.swift:94-143) ---- */
 /* coeff_moduli = q_0..q_{L-1}, q_ks (nmod = L+1 >= 2); t = plaintext modulus */
 orc_context *orc_context_create(int64_t n, const uint64_t *coeff_moduli, int32_t nmod, uint64_t t);
+orc_context *orc_context_create_w(int64_t n, const uint64_t *coeff_moduli, int32_t nmod, uint64_t t, int32_t word_bits);
 void orc_context_destroy(orc_context *);
 int32_t orc_context_L(const orc_context *);
 int32_t orc_context_bsk(const orc_context *, uint64_t *out);

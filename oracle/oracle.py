@@ -64,6 +64,8 @@ def lib():
             getattr(L, name).argtypes = [C.c_int64, u64p, C.c_int32, u64p, u64p]
         L.orc_rnstool_create.restype = C.c_void_p
         L.orc_rnstool_create.argtypes = [C.c_int64, u64p, C.c_int32, C.c_uint64]
+        L.orc_rnstool_create_w.restype = C.c_void_p
+        L.orc_rnstool_create_w.argtypes = [C.c_int64, u64p, C.c_int32, C.c_uint64, C.c_int32]
         L.orc_rnstool_destroy.argtypes = [C.c_void_p]
         L.orc_rnstool_bsk.argtypes = [C.c_void_p, u64p]
         L.orc_rnstool_small_montgomery_reduce.argtypes = [C.c_void_p, u64p]
@@ -77,6 +79,8 @@ def lib():
         L.orc_convert_approximate.argtypes = [C.c_int64, u64p, C.c_int32, u64p, C.c_int32, u64p, u64p]
         L.orc_context_create.restype = C.c_void_p
         L.orc_context_create.argtypes = [C.c_int64, u64p, C.c_int32, C.c_uint64]
+        L.orc_context_create_w.restype = C.c_void_p
+        L.orc_context_create_w.argtypes = [C.c_int64, u64p, C.c_int32, C.c_uint64, C.c_int32]
         L.orc_context_destroy.argtypes = [C.c_void_p]
         L.orc_context_L.argtypes = [C.c_void_p]
         L.orc_context_bsk.argtypes = [C.c_void_p, u64p]
@@ -248,10 +252,11 @@ def fill_uniform(seed: int, moduli, n: int, rows: int):
 class RnsTool:
     """_RnsTool at the top level for base q (RnsTool.swift:18-121)."""
 
-    def __init__(self, n: int, q, t: int):
-        self.n, self.q, self.t = n, [int(v) for v in q], t
+    def __init__(self, n: int, q, t: int, word_bits: int = 64):
+        """word_bits = 32: the reference's Bfv<UInt32> constants (m~ = 2^16, gamma = 2^30 - 20405, 29-bit Bsk)."""
+        self.n, self.q, self.t, self.word_bits = n, [int(v) for v in q], t, word_bits
         qa = _arr(q)
-        self.h = lib().orc_rnstool_create(n, _p(qa), len(qa), t)
+        self.h = lib().orc_rnstool_create_w(n, _p(qa), len(qa), t, word_bits)
         if not self.h:
             raise ValueError("rnstool_create failed")
         out = np.zeros(len(q) + 1, dtype=np.uint64)
@@ -303,10 +308,11 @@ class RnsTool:
 class Context:
     """Context<Bfv<UInt64>> (Context.swift:94-143): coeff_moduli = [q_0..q_{L-1}, q_ks]."""
 
-    def __init__(self, n: int, coeff_moduli, t: int):
-        self.n, self.moduli, self.t = n, [int(v) for v in coeff_moduli], int(t)
+    def __init__(self, n: int, coeff_moduli, t: int, word_bits: int = 64):
+        """word_bits = 32: Context<Bfv<UInt32>> -- the same residues with Bfv<UInt32>'s m~ / gamma / Bsk."""
+        self.n, self.moduli, self.t, self.word_bits = n, [int(v) for v in coeff_moduli], int(t), word_bits
         m = _arr(coeff_moduli)
-        self.h = lib().orc_context_create(n, _p(m), len(m), t)
+        self.h = lib().orc_context_create_w(n, _p(m), len(m), t, word_bits)
         if not self.h:
             raise ValueError("orc_context_create failed")
         self.L = len(self.moduli) - 1

@@ -82,15 +82,15 @@ __global__ void __launch_bounds__(kThreads) lift_kernel(const u64 *__restrict__ 
     bool neg[COLS];
 #pragma unroll
     for (int k = 0; k < COLS; ++k) {
-        r[k] = acc_mt[k] * c.neg_inv_q_mt;   // [-x' Q^-1]_{m~}, RnsTool.swift:343-348
-        neg[k] = r[k] >= 0x80000000u;        // centered representative r - m~ (:357-360)
+        r[k] = (acc_mt[k] * c.neg_inv_q_mt) & c.mt_mask;  // [-x' Q^-1]_{m~}, RnsTool.swift:343-348
+        neg[k] = r[k] >= c.mt_half;                       // centered representative r - m~ (:357-360)
     }
 #pragma unroll
     for (int j = 0; j <= L; ++j) {
         u64 o[COLS];
 #pragma unroll
         for (int k = 0; k < COLS; ++k) {
-            const u64 rc = neg[k] ? (u64)r[k] + c.b[j] - 0x100000000ull : (u64)r[k];
+            const u64 rc = neg[k] ? (u64)r[k] + c.neg_off[j] : (u64)r[k];
             u128 acc = (u128)rc * c.qr[j];
 #pragma unroll
             for (int i = 0; i < L; ++i) mac128(acc, z[k][i], c.mat[j][i]);

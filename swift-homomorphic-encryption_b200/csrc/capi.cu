@@ -193,6 +193,14 @@ size_t inner_product_scratch_words(const Context &c, int64_t pairs) {
 
 namespace {
 
+// The u32 entry points (Bfv<UInt32> contexts) run the same bodies: the calling thread marks its host buffers as uint32
+// for the duration of the call and the pipeline widens after the H2D copy / narrows before the D2H copy.
+thread_local bool tl_io32 = false;
+struct Io32Scope {
+    Io32Scope() { tl_io32 = true; }
+    ~Io32Scope() { tl_io32 = false; }
+};
+
 // Generic double-buffered host pipeline: for each chunk, copy inputs in, run `body`, copy outputs out.
 struct HostIo {
     const u64 *src;  // host
@@ -238,22 +246,42 @@ int32_t host_pipeline(const hecuda_context *h, int64_t batch, int64_t chunk_hint
         // slot 0 = kernel scratch, slot 4 = staged inputs (back to back), slot 5 = staged output
         size_t in_words = 0;
         for (const HostIo &io : inputs) in_words += io.words_per_item * (size_t)items;
+        const bool io32 = tl_io32;
+        const size_t out_words = out_words_per_item * (size_t)items;
         CK(w.reserve(0, scratch_words_per_item * (size_t)items));
         CK(w.reserve(4, in_words));
-        CK(w.reserve(5, out_words_per_item * (size_t)items));
+        CK(w.reserve(5, out_words));
+        if (io32) {  // slots 6 / 7: the uint32 images (each input starts on a 16-byte boundary)
+            CK(w.reserve(6, in_words / 2 + inputs.size() * 2 + 2));
+            CK(w.reserve(7, out_words / 2 + 2));
+        }
         std::vector<const u64 *> d_in;
-        size_t off = 0;
+        size_t off = 0, off32 = 0;
         for (const HostIo &io : inputs) {
             const size_t words = io.words_per_item * (size_t)items;
-            CK(cudaMemcpyAsync(w.buf[4] + off, io.src + io.words_per_item * (size_t)done, words * sizeof(u64),
-                               cudaMemcpyHostToDevice, w.stream));
+            if (io32) {
+                u32 *raw = reinterpret_cast<u32 *>(w.buf[6]) + off32;
+                CK(cudaMemcpyAsync(raw, reinterpret_cast<const u32 *>(io.src) + io.words_per_item * (size_t)done,
+                                   words * sizeof(u32), cudaMemcpyHostToDevice, w.stream));
+                CK(launch_widen(raw, w.buf[4] + off, (int64_t)words, w.stream));
+                off32 += (words + 3) & ~(size_t)3;
+            } else {
+                CK(cudaMemcpyAsync(w.buf[4] + off, io.src + io.words_per_item * (size_t)done, words * sizeof(u64),
+                                   cudaMemcpyHostToDevice, w.stream));
+            }
             d_in.push_back(w.buf[4] + off);
             off += words;
         }
         cudaError_t e = body(w, d_in, w.buf[5], items);
         if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
-        CK(cudaMemcpyAsync(host_out + out_words_per_item * (size_t)done, w.buf[5],
-                           out_words_per_item * (size_t)items * sizeof(u64), cudaMemcpyDeviceToHost, w.stream));
+        if (io32) {
+            CK(launch_narrow(w.buf[5], reinterpret_cast<u32 *>(w.buf[7]), (int64_t)out_words, w.stream));
+            CK(cudaMemcpyAsync(reinterpret_cast<u32 *>(host_out) + out_words_per_item * (size_t)done, w.buf[7],
+                               out_words * sizeof(u32), cudaMemcpyDeviceToHost, w.stream));
+        } else {
+            CK(cudaMemcpyAsync(host_out + out_words_per_item * (size_t)done, w.buf[5], out_words * sizeof(u64),
+                               cudaMemcpyDeviceToHost, w.stream));
+        }
     }
     for (Workspace *w : ws) CK(cudaStreamSynchronize(w->stream));
     return HECUDA_OK;
@@ -347,15 +375,32 @@ int32_t hecuda_host_unregister(void *ptr) {
     return HECUDA_OK;
 }
 
+static int32_t context_create(int64_t poly_degree, const uint64_t *coefficient_moduli, int32_t moduli_count,
+                              uint64_t plaintext_modulus, int word_bits, hecuda_context **out);
 int32_t hecuda_context_create(int64_t poly_degree, const uint64_t *coefficient_moduli, int32_t moduli_count,
                               uint64_t plaintext_modulus, hecuda_context **out) {
+    return context_create(poly_degree, coefficient_moduli, moduli_count, plaintext_modulus, 64, out);
+}
+int32_t hecuda_context_create_u32(int64_t poly_degree, const uint32_t *coefficient_moduli, int32_t moduli_count,
+                                  uint32_t plaintext_modulus, hecuda_context **out) {
+    if (!coefficient_moduli || moduli_count < 0) return fail(HECUDA_ERR_INVALID_ARGUMENT, "null argument");
+    std::vector<uint64_t> wide(coefficient_moduli, coefficient_moduli + moduli_count);
+    return context_create(poly_degree, wide.data(), moduli_count, plaintext_modulus, 32, out);
+}
+int32_t hecuda_context_word_bits(const hecuda_context *h, int32_t *bits) {
+    if (!h || !bits) return fail(HECUDA_ERR_INVALID_ARGUMENT, "null argument");
+    *bits = h->ctx->word_bits;
+    return HECUDA_OK;
+}
+static int32_t context_create(int64_t poly_degree, const uint64_t *coefficient_moduli, int32_t moduli_count,
+                              uint64_t plaintext_modulus, int word_bits, hecuda_context **out) {
     if (!out || !coefficient_moduli) return fail(HECUDA_ERR_INVALID_ARGUMENT, "null argument");
     *out = nullptr;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fail(HECUDA_ERR_NO_DEVICE, "no CUDA device: libhecuda has no CPU fallback");
     std::string err;
-    Context *c = Context::create(poly_degree, (const u64 *)coefficient_moduli, moduli_count, plaintext_modulus, err);
+    Context *c = Context::create(poly_degree, (const u64 *)coefficient_moduli, moduli_count, plaintext_modulus, err, word_bits);
     if (!c) {
         const bool unsupported = err.rfind("unsupported", 0) == 0;
         return fail(unsupported ? HECUDA_ERR_UNSUPPORTED : HECUDA_ERR_INVALID_ARGUMENT, err);
@@ -983,5 +1028,69 @@ int32_t hecuda_poly_multiply_power_of_x(const hecuda_context *h, int32_t base, c
 }
 
 uint64_t hecuda_kernel_launch_count(void) { return g_kernel_launches.load(); }
+
+
+// ---------------------------------------------------------------- Bfv<UInt32>: uint32 buffers at the boundary
+// (the reference's second scalar type, HeScheme.swift / Scalar.swift:498-511).  Same layouts as the uint64 entry points;
+// the context must have been made by hecuda_context_create_u32 (its m~, gamma and Bsk).
+static int32_t need_word32(const hecuda_context *h) {
+    if (!h || !h->ctx) return fail(HECUDA_ERR_INVALID_ARGUMENT, "invalidContext: null context");
+    if (h->ctx->word_bits != 32) return fail(HECUDA_ERR_INVALID_ARGUMENT, "invalidContext: not a Bfv<UInt32> context (hecuda_context_create_u32)");
+    return HECUDA_OK;
+}
+int32_t hecuda_u32_ntt_forward(const hecuda_context *h, int32_t base, uint32_t *data, int32_t rows, int64_t polys) {
+    int32_t rc = need_word32(h);
+    if (rc) return rc;
+    Io32Scope scope;
+    return hecuda_ntt_forward(h, base, reinterpret_cast<uint64_t *>(data), rows, polys);
+}
+int32_t hecuda_u32_ntt_inverse(const hecuda_context *h, int32_t base, uint32_t *data, int32_t rows, int64_t polys) {
+    int32_t rc = need_word32(h);
+    if (rc) return rc;
+    Io32Scope scope;
+    return hecuda_ntt_inverse(h, base, reinterpret_cast<uint64_t *>(data), rows, polys);
+}
+int32_t hecuda_u32_bfv_multiply(const hecuda_context *h, const uint32_t *lhs, const uint32_t *rhs, uint32_t *out, int64_t batch) {
+    int32_t rc = need_word32(h);
+    if (rc) return rc;
+    Io32Scope scope;
+    return hecuda_bfv_multiply(h, reinterpret_cast<const uint64_t *>(lhs), reinterpret_cast<const uint64_t *>(rhs),
+                               reinterpret_cast<uint64_t *>(out), batch);
+}
+int32_t hecuda_u32_evk_create(const hecuda_context *h, const uint32_t *relin_key, hecuda_evk **out) {
+    int32_t rc = need_word32(h);
+    if (rc) return rc;
+    if (!relin_key) return fail(HECUDA_ERR_MISSING_KEY, "missingRelinearizationKey");
+    const Context &c = *h->ctx;
+    const size_t words = (size_t)c.L * 2 * (c.L + 1) * c.n;
+    std::vector<uint64_t> wide(relin_key, relin_key + words);  // setup-time: widened on the host
+    return hecuda_evk_create(h, wide.data(), out);
+}
+int32_t hecuda_u32_bfv_relinearize(const hecuda_context *h, const hecuda_evk *evk, const uint32_t *ct3, int32_t l, uint32_t *out,
+                                   int64_t batch) {
+    int32_t rc = need_word32(h);
+    if (rc) return rc;
+    Io32Scope scope;
+    return hecuda_bfv_relinearize(h, evk, reinterpret_cast<const uint64_t *>(ct3), l, reinterpret_cast<uint64_t *>(out), batch);
+}
+int32_t hecuda_u32_bfv_mod_switch_down(const hecuda_context *h, const uint32_t *ct, int32_t polys, int32_t l, uint32_t *out,
+                                       int64_t batch) {
+    int32_t rc = need_word32(h);
+    if (rc) return rc;
+    Io32Scope scope;
+    return hecuda_bfv_mod_switch_down(h, reinterpret_cast<const uint64_t *>(ct), polys, l, reinterpret_cast<uint64_t *>(out), batch);
+}
+int32_t hecuda_u32_rnstool_lift_q_to_qbsk(const hecuda_context *h, const uint32_t *polys, uint32_t *out, int64_t count) {
+    int32_t rc = need_word32(h);
+    if (rc) return rc;
+    Io32Scope scope;
+    return hecuda_rnstool_lift_q_to_qbsk(h, reinterpret_cast<const uint64_t *>(polys), reinterpret_cast<uint64_t *>(out), count);
+}
+int32_t hecuda_u32_rnstool_floor_qbsk_to_q(const hecuda_context *h, const uint32_t *polys, uint32_t *out, int64_t count) {
+    int32_t rc = need_word32(h);
+    if (rc) return rc;
+    Io32Scope scope;
+    return hecuda_rnstool_floor_qbsk_to_q(h, reinterpret_cast<const uint64_t *>(polys), reinterpret_cast<uint64_t *>(out), count);
+}
 
 }  // extern "C"

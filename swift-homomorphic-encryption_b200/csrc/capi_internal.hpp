@@ -45,8 +45,8 @@ inline cudaError_t fill(void *dst, int value, size_t bytes) {
 struct Workspace {
     cudaStream_t stream = nullptr;
     bool owns_stream = false;
-    u64 *buf[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    size_t cap[6] = {0, 0, 0, 0, 0, 0};
+    u64 *buf[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t cap[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     cudaError_t reserve(int i, size_t words) {
         if (cap[i] >= words) return cudaSuccess;
         if (buf[i]) {
@@ -60,7 +60,7 @@ struct Workspace {
         return e;
     }
     void release() {
-        for (int i = 0; i < 6; ++i)
+        for (int i = 0; i < 8; ++i)
             if (buf[i]) cudaFree(buf[i]);
         if (owns_stream && stream) cudaStreamDestroy(stream);
     }

@@ -13,7 +13,6 @@
 namespace hecuda {
 using namespace host;
 
-static constexpr u64 kMTilde = 1ull << 32;  // Sources/ModularArithmetic/Scalar.swift:522-524
 
 static void fill_barrett(u64 p, u64 &mu1, u64 &mu_hi, u64 &mu_lo) {
     mu1 = (u64)(((u128)1 << 64) / p);
@@ -96,7 +95,10 @@ static DivRoundConsts build_divround(const std::vector<u64> &base) {
     return c;
 }
 
-Context *Context::create(int64_t n, const u64 *coeff_moduli, int nmod, u64 t, std::string &err) {
+Context *Context::create(int64_t n, const u64 *coeff_moduli, int nmod, u64 t, std::string &err, int word_bits) {
+    if (word_bits != 64 && word_bits != 32) { err = "invalidEncryptionParameters: word size must be 32 or 64"; return nullptr; }
+    for (int i = 0; i < nmod; ++i)  // Modulus<T>.max = 2^(bitWidth - 2) - 1, Sources/ModularArithmetic/Modulus.swift:177-180
+        if (coeff_moduli[i] >> (word_bits - 2)) { err = "invalidModulus: " + std::to_string(coeff_moduli[i]) + " exceeds the maximum of this word size"; return nullptr; }
     if (n < 2 || (n & (n - 1)) || n > (1 << 17)) { err = "invalidDegree: N must be a power of two in [2, 2^17]"; return nullptr; }
     // the NTT kernels keep a whole row in one CTA's shared memory: N <= 2^14 (a 2^15 row is 256 KB)
     if (n > (1 << fast::kMaxLogN)) { err = "unsupportedHeOperation: polynomial degrees above 2^" + std::to_string(fast::kMaxLogN) + " are not supported by the NTT kernels"; return nullptr; }
@@ -112,6 +114,10 @@ Context *Context::create(int64_t n, const u64 *coeff_moduli, int nmod, u64 t, st
     c->logn = bit_length((u64)n) - 1;
     c->L = nmod - 1;
     c->t = t;
+    c->word_bits = word_bits;
+    c->mtilde = word_bits == 64 ? (1ull << 32) : (1ull << 16);                       // Scalar.swift:509-511, 522-524
+    c->gamma = word_bits == 64 ? ((1ull << 62) - 40797) : ((1ull << 30) - 20405);    // Scalar.swift:503-507, 516-520
+    const u64 kMTilde = c->mtilde;
     cudaGetDevice(&c->device);
     c->sm_count = 1;
     cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device);
@@ -120,8 +126,8 @@ Context *Context::create(int64_t n, const u64 *coeff_moduli, int nmod, u64 t, st
     c->q_ks = coeff_moduli[L];
     for (u64 qi : c->q)
         if (t >= qi) { err = "invalidEncryptionParameters: plaintext modulus must be below every coefficient modulus"; delete c; return nullptr; }
-    // BEHZ auxiliary base: the L+1 smallest 61-bit NTT primes (RnsTool.swift:30-33)
-    c->bsk = smallest_ntt_primes(61, L + 1, (u64)n);
+    // BEHZ auxiliary base: the L+1 smallest (bitWidth - 3)-bit NTT primes (RnsTool.swift:30-33)
+    c->bsk = smallest_ntt_primes(word_bits - 3, L + 1, (u64)n);
     if ((int)c->bsk.size() != L + 1) { err = "notEnoughPrimes for Bsk"; delete c; return nullptr; }
     for (u64 b : c->bsk)
         for (int i = 0; i < nmod; ++i)
@@ -139,23 +145,28 @@ Context *Context::create(int64_t n, const u64 *coeff_moduli, int nmod, u64 t, st
     {
         const char *env = std::getenv("HECUDA_AUX_BASE");
         const bool want_fast = !(env && std::string(env) == "reference");
-        std::vector<u64> cand = smallest_ntt_primes(55, L + 1 + nmod, (u64)n);
-        std::vector<u64> pick;
-        for (u64 v : cand) {
-            bool used = false;
-            for (int i = 0; i < nmod; ++i) used |= coeff_moduli[i] == v;
-            if (!used && (int)pick.size() < L + 1) pick.push_back(v);
-        }
-        double log_q = 0, log_aux = 0, log_aux_l = 0;
+        // cheapest NTT class first: primes below 2^30 (32-bit butterflies) when q is small enough for them, else below 2^55
+        const int widths[2] = {30, 55};
+        double log_q = 0;
         for (u64 v : c->q) log_q += std::log2((double)v);
-        for (size_t j = 0; j < pick.size(); ++j) {
-            log_aux += std::log2((double)pick[j]);
-            if ((int)j < L) log_aux_l += std::log2((double)pick[j]);
-        }
         const double log_n = (double)c->logn, log_t = std::log2((double)t);
-        const bool enough = (int)pick.size() == L + 1 && log_aux >= log_q + log_n + 4 &&
-                            log_aux_l + std::log2((double)pick.back()) >= log_t + log_n + log_q + 5;
-        if (want_fast && enough) c->aux = pick;
+        for (int wi = 0; wi < 2 && want_fast && c->aux == c->bsk && word_bits == 64; ++wi) {
+            std::vector<u64> cand = smallest_ntt_primes(widths[wi], L + 1 + nmod, (u64)n);
+            std::vector<u64> pick;
+            for (u64 v : cand) {
+                bool used = false;
+                for (int i = 0; i < nmod; ++i) used |= coeff_moduli[i] == v;
+                if (!used && (int)pick.size() < L + 1) pick.push_back(v);
+            }
+            double log_aux = 0, log_aux_l = 0;
+            for (size_t j = 0; j < pick.size(); ++j) {
+                log_aux += std::log2((double)pick[j]);
+                if ((int)j < L) log_aux_l += std::log2((double)pick[j]);
+            }
+            const bool enough = (int)pick.size() == L + 1 && log_aux >= log_q + log_n + 4 &&
+                                log_aux_l + std::log2((double)pick.back()) >= log_t + log_n + log_q + 5;
+            if (enough) c->aux = pick;
+        }
     }
     c->aux_is_reference = c->aux == c->bsk;
 
@@ -219,6 +230,9 @@ Context *Context::create(int64_t n, const u64 *coeff_moduli, int nmod, u64 t, st
         lf.in_wp[i] = shoup_factor(lf.in_w[i], qi);
         lf.punct_mt[i] = (u32)punctured_mod(Q, L, i, kMTilde);
     }
+    lf.mt_mask = (u32)(kMTilde - 1);
+    lf.mt_half = (u32)(kMTilde >> 1);
+    for (int j = 0; j <= L; ++j) lf.neg_off[j] = ((kMTilde + BSK[j] - 1) / BSK[j]) * BSK[j] - kMTilde;
     for (int j = 0; j <= L; ++j) {
         const u64 bj = BSK[j];
         lf.b[j] = bj;

@@ -68,8 +68,10 @@ struct LiftConsts {
     u64 b_mu1[kMaxL + 1];            // floor(2^64 / b_j)
     u64 q[kMaxL];
     u64 in_w[kMaxL], in_wp[kMaxL];   // m~ (Q/q_i)^-1 mod q_i
-    u32 punct_mt[kMaxL];             // (Q/q_i) mod 2^32
-    u32 neg_inv_q_mt;                // -Q^-1 mod 2^32
+    u32 punct_mt[kMaxL];             // (Q/q_i) mod m~
+    u32 neg_inv_q_mt;                // -Q^-1 mod m~
+    u32 mt_mask, mt_half;            // m~ - 1, m~ / 2   (m~ = 2^32 for Bfv<UInt64>, 2^16 for Bfv<UInt32>, Scalar.swift:498-525)
+    u64 neg_off[kMaxL + 1];          // k b_j - m~ >= 0 with the least such k: the centered r - m~ as a residue mod b_j
     u64 b[kMaxL + 1], b_ninv[kMaxL + 1];
     u64 mat[kMaxL + 1][kMaxL];       // (Q/q_i) m~^-1 2^64 mod b_j
     u64 qr[kMaxL + 1];               // Q m~^-1 2^64 mod b_j
@@ -111,11 +113,15 @@ struct HostSlot {
 
 class Context {
    public:
-    static Context *create(int64_t n, const u64 *coeff_moduli, int nmod, u64 t, std::string &err);
+    // word_bits: the reference's scalar type -- 64 = Bfv<UInt64>, 32 = Bfv<UInt32> (its m~, gamma and Bsk, moduli < 2^30)
+    static Context *create(int64_t n, const u64 *coeff_moduli, int nmod, u64 t, std::string &err, int word_bits = 64);
     ~Context();
 
     int64_t n;
     int logn;
+    int word_bits = 64;
+    u64 mtilde = 1ull << 32;   // T.mTilde
+    u64 gamma = (1ull << 62) - 40797;  // T.rnsCorrectionFactor
     int L;           // ciphertext moduli
     u64 t;
     int device;

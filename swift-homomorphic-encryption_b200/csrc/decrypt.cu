@@ -15,11 +15,12 @@ using namespace hecuda::api;
 
 namespace {
 
-constexpr u64 kGamma = (1ull << 62) - 40797;  // UInt64.rnsCorrectionFactor (ModularArithmetic/Scalar.swift:516-520)
+// gamma = T.rnsCorrectionFactor comes from the context: 2^62 - 40797 (UInt64) or 2^30 - 20405 (UInt32), Scalar.swift:503-520
 
 struct DecryptConsts {
     int l;
     u64 t;
+    u64 gamma;                 // T.rnsCorrectionFactor
     u64 q[kMaxL];
     u64 gamma_t[kMaxL];        // gamma * t mod q_i                       (prodGammaTModQ, RnsTool.swift:145-146)
     u64 inv_punctured[kMaxL];  // (q / q_i)^-1 mod q_i                    (RnsBaseConverter)
@@ -61,13 +62,13 @@ __global__ void __launch_bounds__(256) scale_and_round_kernel(const u64 *__restr
         const u64 x = mulmod_dev(dot[(item * c.l + i) * (int64_t)n + e], c.gamma_t[i], c.q[i]);
         const u64 y = mulmod_dev(x, c.inv_punctured[i], c.q[i]);
         mod_t = (mod_t + mulmod_dev(y % c.t, c.punctured_t[i], c.t)) % c.t;
-        mod_g = (u64)(((u128)mod_g + mulmod_dev(y % kGamma, c.punctured_g[i], kGamma)) % kGamma);
+        mod_g = (u64)(((u128)mod_g + mulmod_dev(y % c.gamma, c.punctured_g[i], c.gamma)) % c.gamma);
     }
     mod_t = mulmod_dev(mod_t, c.neg_inv_q_t, c.t);
-    mod_g = mulmod_dev(mod_g, c.neg_inv_q_g, kGamma);
-    const u64 s_greater = (c.t - (kGamma - mod_g) % c.t) % c.t;
+    mod_g = mulmod_dev(mod_g, c.neg_inv_q_g, c.gamma);
+    const u64 s_greater = (c.t - (c.gamma - mod_g) % c.t) % c.t;
     const u64 s_less = mod_g % c.t;
-    const u64 s = mod_g > kGamma / 2 ? s_greater : s_less;
+    const u64 s = mod_g > c.gamma / 2 ? s_greater : s_less;
     const u64 m = mod_t >= s ? mod_t - s : mod_t + c.t - s;
     out[item * (int64_t)n + e] = mulmod_dev(m, c.inv_gamma_scaled, c.t);
 }
@@ -76,6 +77,7 @@ DecryptConsts make_consts(const Context &ctx, int l, u64 scaling_factor) {
     DecryptConsts c;
     c.l = l;
     c.t = ctx.t;
+    const u64 kGamma = c.gamma = ctx.gamma;
     u64 q[kMaxL];
     for (int i = 0; i < l; ++i) q[i] = c.q[i] = ctx.slots[ctx.slot_q(i)].dev.p;
     for (int i = 0; i < l; ++i) {
@@ -132,7 +134,7 @@ int32_t hecuda_bfv_decrypt(const hecuda_context *h, const uint64_t *secret_key, 
     if (polys < 2 || polys > 3) return fail(HECUDA_ERR_INVALID_ARGUMENT, "invalidCiphertext: poly_count must be 2 or 3");
     if (l < 1 || l > c.L) return fail(HECUDA_ERR_INVALID_ARGUMENT, "invalidCiphertext: moduli_count out of range");
     if (batch < 0 || (batch && (!ciphertexts || !plaintexts))) return fail(HECUDA_ERR_INVALID_ARGUMENT, "invalidCiphertext: null buffer");
-    if (c.t >= kGamma) return fail(HECUDA_ERR_UNSUPPORTED, "plaintext modulus too large");
+    if (c.t >= c.gamma) return fail(HECUDA_ERR_UNSUPPORTED, "plaintext modulus too large");
     if (batch == 0) return HECUDA_OK;
     const DecryptConsts dc = make_consts(c, l, scaling_factor);
     // SecretKey.poly has K = L + 1 rows (Eval); rows 0..l-1 are the ones a level-l ciphertext uses

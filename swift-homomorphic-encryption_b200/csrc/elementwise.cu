@@ -168,3 +168,41 @@ int32_t hecuda_poly_mul_scalars_device(const hecuda_context *h, int32_t base, ui
 }
 
 }  // extern "C"
+
+// ---- word-size conversion at the boundary of a Bfv<UInt32> context: residues travel as uint32 (half the PCIe bytes)
+// and sit zero-extended in 64-bit slots on the device.
+namespace hecuda {
+
+__global__ void __launch_bounds__(256) widen_kernel(const u32 *__restrict__ in, u64 *__restrict__ out, int64_t words) {
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i + 3 < words) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(in + i);
+        reinterpret_cast<ulonglong2 *>(out + i)[0] = make_ulonglong2(v.x, v.y);
+        reinterpret_cast<ulonglong2 *>(out + i)[1] = make_ulonglong2(v.z, v.w);
+    } else {
+        for (int64_t k = i; k < words; ++k) out[k] = in[k];
+    }
+}
+__global__ void __launch_bounds__(256) narrow_kernel(const u64 *__restrict__ in, u32 *__restrict__ out, int64_t words) {
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i + 3 < words) {
+        const ulonglong2 a = reinterpret_cast<const ulonglong2 *>(in + i)[0], b = reinterpret_cast<const ulonglong2 *>(in + i)[1];
+        *reinterpret_cast<uint4 *>(out + i) = make_uint4((u32)a.x, (u32)a.y, (u32)b.x, (u32)b.y);
+    } else {
+        for (int64_t k = i; k < words; ++k) out[k] = (u32)in[k];
+    }
+}
+cudaError_t launch_widen(const u32 *in, u64 *out, int64_t words, cudaStream_t stream) {
+    if (words == 0) return cudaSuccess;
+    ++g_kernel_launches;
+    widen_kernel<<<(unsigned)((words + 1023) / 1024), 256, 0, stream>>>(in, out, words);
+    return cudaGetLastError();
+}
+cudaError_t launch_narrow(const u64 *in, u32 *out, int64_t words, cudaStream_t stream) {
+    if (words == 0) return cudaSuccess;
+    ++g_kernel_launches;
+    narrow_kernel<<<(unsigned)((words + 1023) / 1024), 256, 0, stream>>>(in, out, words);
+    return cudaGetLastError();
+}
+
+}  // namespace hecuda

@@ -82,6 +82,10 @@ cudaError_t launch_poly_load(const Context &ctx, const CodecConsts &c, int skip,
 cudaError_t launch_poly_serialize(const Context &ctx, const CodecConsts &c, int skip, const u64 *in, unsigned char *bytes,
                                   int64_t polys, cudaStream_t stream);
 
+// uint32 <-> uint64 residues at the boundary of a Bfv<UInt32> context (elementwise.cu); both buffers 16-byte aligned
+cudaError_t launch_widen(const u32 *in, u64 *out, int64_t words, cudaStream_t stream);
+cudaError_t launch_narrow(const u64 *in, u32 *out, int64_t words, cudaStream_t stream);
+
 // divideAndRoundQLast over polys x l x N -> polys x (l-1) x N
 cudaError_t launch_mod_switch(const Context &ctx, const u64 *in, int l, u64 *out, int64_t polys, cudaStream_t stream);
 

@@ -195,7 +195,7 @@ __global__ void __launch_bounds__((1 << LOGN) / 16, (1024 / ((1 << LOGN) / 16)))
         const int cls = flags & 3;
         RowMod m;
         m.np = 0 - S.p;
-        m.kp = cls == kWide ? 2 * S.p : 4 * S.p;
+        m.kp = (cls == kWide || cls == kSmall) ? 2 * S.p : 4 * S.p;
         m.tw = nullptr;
         m.tw_s = smem_u32(tw_cache);
         m.slot = &S;
@@ -211,11 +211,13 @@ __global__ void __launch_bounds__((1 << LOGN) / 16, (1024 / ((1 << LOGN) / 16)))
 #ifndef HE_EXPERIMENT_ONLY_CLASS
         if (INVERSE) {
             if (cls == kNarrow) inv_row<LOGN, kNarrow>(sm, tau, m);
+            else if (cls == kSmall) inv_row<LOGN, kSmall>(sm, tau, m);
             else if (cls == kMid) inv_row<LOGN, kMid>(sm, tau, m);
             else inv_row<LOGN, kWide>(sm, tau, m);
         } else {
             const bool reduce_in = (flags & 4) != 0;
             if (cls == kNarrow) fwd_row<LOGN, kNarrow>(sm, tau, m, reduce_in);
+            else if (cls == kSmall) fwd_row<LOGN, kSmall>(sm, tau, m, reduce_in);
             else if (cls == kMid) fwd_row<LOGN, kMid>(sm, tau, m, reduce_in);
             else fwd_row<LOGN, kWide>(sm, tau, m, reduce_in);
         }
@@ -242,8 +244,10 @@ static void build_row_list(const Context &ctx, const NttRowMap &map, bool invers
     rl.rows_per_poly = map.rows_per_poly;
     rl.count = 0;
     rl.src_poly_stride = map.src_mod ? map.src_poly_stride : (long long)map.rows_per_poly * ctx.n;
-    // class-major order (the cheap NARROW rows last, so the tail of the launch is made of short rows)
-    for (int cls = kWide; cls >= kNarrow; --cls) {
+    // class-major order (the cheapest rows last, so the tail of the launch is made of short rows)
+    static const int order[4] = {kWide, kMid, kNarrow, kSmall};
+    for (int oi = 0; oi < 4; ++oi) {
+        const int cls = order[oi];
         for (int r = 0; r < map.rows_per_poly; ++r) {
             const int slot = map.slot[r / map.group];
             if (class_of_bits(ctx.slots[slot].dev.bits) != cls) continue;
@@ -257,7 +261,7 @@ static void build_row_list(const Context &ctx, const NttRowMap &map, bool invers
                 // range of the butterflies (< 2p NARROW, < 8p MID, < 4p WIDE); otherwise re-reduce on load
                 // (Bfv+Keys.swift:168-172)
                 const u64 p = ctx.slots[slot].dev.p, src_p = ctx.slots[map.src_slot[r % map.src_mod]].dev.p;
-                const u64 room = cls == kNarrow ? 2u : cls == kMid ? 8u : 4u;
+                const u64 room = cls == kNarrow ? 2u : cls == kMid ? 8u : cls == kSmall ? 1u : 4u;
                 if (src_p > p && (src_p - 1) / p >= room) flags |= 4;
             }
             rl.flags[i] = (unsigned char)flags;

@@ -39,6 +39,10 @@
 //   MID (p < 2^61): Harvey-style with doubled ranges, [0, 8p) forward (one conditional subtraction of 4p per
 //       butterfly), [0, 4p) inverse.
 //   WIDE (p < 2^62): exact quotient, [0, 4p) forward / [0, 2p) inverse (the reference's own ranges).
+//   SMALL (p < 2^30, the moduli of the reference's Bfv<UInt32> and of the default PIR parameters): the butterflies
+//       run in 32-bit arithmetic -- one IMAD.HI and two IMAD per Shoup product instead of five IMAD.WIDE and four IMAD --
+//       on Harvey's ranges, with the 32-bit Shoup factor taken from the top half of the 64-bit one
+//       (floor(floor(w 2^64 / p) / 2^32) = floor(w 2^32 / p)); residues stay zero-extended in their 64-bit slots.
 #pragma once
 #include "context.hpp"
 #include "modarith.cuh"
@@ -49,8 +53,11 @@ namespace fast {
 constexpr int kMinLogN = 10, kMaxLogN = 14;
 constexpr int kNarrowBits = 55;  // reduction-free butterflies: lazy values < 512 p < 2^64
 constexpr int kMidBits = 61;     // 8 p < 2^64
-enum { kNarrow = 0, kMid = 1, kWide = 2 };
-HE_HD constexpr int class_of_bits(int bits) { return bits <= kNarrowBits ? kNarrow : bits <= kMidBits ? kMid : kWide; }
+constexpr int kSmallBits = 30;   // Modulus<UInt32>.max = 2^30 - 1: the reference's 32-bit word size (Modulus.swift:177-180)
+enum { kNarrow = 0, kMid = 1, kWide = 2, kSmall = 3 };
+HE_HD constexpr int class_of_bits(int bits) {
+    return bits <= kSmallBits ? kSmall : bits <= kNarrowBits ? kNarrow : bits <= kMidBits ? kMid : kWide;
+}
 
 // ---- pass plans: stage counts of the forward passes, in execution order; the inverse runs the mirrored list
 HE_HD constexpr int plan_passes(int logn) { return logn <= 12 ? 3 : 4; }
@@ -314,9 +321,24 @@ HE_HD void reduce_small16(u64 (&x)[16], const RowMod &m) {
     for (int r = 0; r < 16; ++r) x[r] = reduce_small(x[r], p, m.np, shift, recip);
 }
 
+// ---- SMALL class: 32-bit Harvey butterflies on zero-extended residues
+HE_HD u32 csub32(u32 x, u32 m) {  // x < 2m  ->  x mod m   (unsigned wrap-around makes x - m huge when x < m)
+    const u32 d = x - m;
+    return d < x ? d : x;
+}
+HE_HD u32 shoup32(u32 y, u32 w, u32 wp, u32 p) {  // y w mod p in [0, 2p) for any y < 2^32
+    return y * w - mul_hi_u32(y, wp) * p;
+}
+
 template <int CLS>
 HE_HD void ct_butterfly(u64 &x, u64 &y, const ulonglong2 w, const RowMod &m) {
-    if (CLS == kNarrow) {  // no reduction: x grows by < 4p per stage
+    if (CLS == kSmall) {  // [0, 4p) < 2^32
+        const u32 p = (u32)(0 - m.np), p2 = 2 * p;
+        const u32 xr = csub32((u32)x, p2);
+        const u32 v = shoup32((u32)y, (u32)w.x, (u32)(w.y >> 32), p);
+        x = xr + v;
+        y = xr - v + p2;
+    } else if (CLS == kNarrow) {  // no reduction: x grows by < 4p per stage
         const u64 v = shoup4(y, w.x, w.y, m.np);
         const u64 xo = x + v;
         y = x - v + m.kp;
@@ -359,13 +381,24 @@ HE_HD void fwd_pass(u64 (&x)[16], int tau, const RowMod &m) {
 // reduce the outputs of the last forward stage to canonical residues
 template <int CLS>
 HE_HD void fwd_finish(u64 (&x)[16], const RowMod &m) {
-    reduce_small16(x, m);  // NARROW < (2 + 4 LOGN) p, MID < 8p, WIDE < 4p
+    if (CLS == kSmall) {
+        const u32 p = (u32)(0 - m.np);
+#pragma unroll
+        for (int r = 0; r < 16; ++r) x[r] = csub32(csub32((u32)x[r], 2 * p), p);
+    } else {
+        reduce_small16(x, m);  // NARROW < (2 + 4 LOGN) p, MID < 8p, WIDE < 4p
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ inverse
 template <int CLS>
 HE_HD void gs_butterfly(u64 &x, u64 &y, const ulonglong2 w, const RowMod &m, u64 kp) {
-    if (CLS == kNarrow) {  // inputs < kp (a multiple of p), outputs x < 2 kp, y < 4p
+    if (CLS == kSmall) {  // inputs < 2p, outputs < 2p
+        const u32 p = (u32)(0 - m.np), p2 = 2 * p;
+        const u32 s = csub32((u32)x + (u32)y, p2);
+        y = shoup32((u32)x - (u32)y + p2, (u32)w.x, (u32)(w.y >> 32), p);
+        x = s;
+    } else if (CLS == kNarrow) {  // inputs < kp (a multiple of p), outputs x < 2 kp, y < 4p
         const u64 s = x + y;
         y = shoup4(x - y + kp, w.x, w.y, m.np);
         x = s;
@@ -410,6 +443,13 @@ HE_HD void inv_stage(u64 (&x)[16], const int tau, const RowMod &m) {
                 const int a = grp * 2 * HH + k;
 #pragma unroll
                 for (int f = 0; f < F; ++f) {
+                    if (CLS == kSmall) {
+                        const u32 p = (u32)(0 - m.np);
+                        const u32 xa = (u32)x[a * F + f], ya = (u32)x[(a + HH) * F + f];
+                        x[a * F + f] = csub32(shoup32(xa + ya, (u32)c0, (u32)(c0p >> 32), p), p);
+                        x[(a + HH) * F + f] = csub32(shoup32(xa - ya + 2 * p, (u32)c1, (u32)(c1p >> 32), p), p);
+                        continue;
+                    }
                     const u64 xa = x[a * F + f], ya = x[(a + HH) * F + f];
                     const u64 s = xa + ya;          // NARROW < 2 kp <= 2^64, MID < 8p, WIDE < 4p
                     const u64 d = xa - ya + kp;

@@ -41,6 +41,16 @@ SYMBOLS = {
     "hecuda_context_ciphertext_moduli_count": (C.c_int32, [_VP, C.POINTER(C.c_int32)]),
     "hecuda_rnstool_lift_q_to_qbsk": (C.c_int32, [_VP, _VP, _VP, C.c_int64]),
     "hecuda_rnstool_floor_qbsk_to_q": (C.c_int32, [_VP, _VP, _VP, C.c_int64]),
+    "hecuda_context_create_u32": (C.c_int32, [C.c_int64, _VP, C.c_int32, C.c_uint32, C.POINTER(_VP)]),
+    "hecuda_context_word_bits": (C.c_int32, [_VP, C.POINTER(C.c_int32)]),
+    "hecuda_u32_ntt_forward": (C.c_int32, [_VP, C.c_int32, _VP, C.c_int32, C.c_int64]),
+    "hecuda_u32_ntt_inverse": (C.c_int32, [_VP, C.c_int32, _VP, C.c_int32, C.c_int64]),
+    "hecuda_u32_bfv_multiply": (C.c_int32, [_VP, _VP, _VP, _VP, C.c_int64]),
+    "hecuda_u32_evk_create": (C.c_int32, [_VP, _VP, C.POINTER(_VP)]),
+    "hecuda_u32_bfv_relinearize": (C.c_int32, [_VP, _VP, _VP, C.c_int32, _VP, C.c_int64]),
+    "hecuda_u32_bfv_mod_switch_down": (C.c_int32, [_VP, _VP, C.c_int32, C.c_int32, _VP, C.c_int64]),
+    "hecuda_u32_rnstool_lift_q_to_qbsk": (C.c_int32, [_VP, _VP, _VP, C.c_int64]),
+    "hecuda_u32_rnstool_floor_qbsk_to_q": (C.c_int32, [_VP, _VP, _VP, C.c_int64]),
     "hecuda_comm_unique_id": (C.c_int32, [_VP]),
     "hecuda_comm_create": (C.c_int32, [_VP, C.c_int32, C.c_int32, C.POINTER(_VP)]),
     "hecuda_comm_destroy": (C.c_int32, [_VP]),
@@ -241,17 +251,26 @@ class PinnedBuffer:
 
 
 class Context:
-    """Context<Bfv<UInt64>> (Context.swift:19,94-143).  coefficient_moduli = [q_0 .. q_{L-1}, q_ks]."""
+    """Context<Bfv<T>> (Context.swift:19,94-143).  coefficient_moduli = [q_0 .. q_{L-1}, q_ks].
+    scalar = np.uint64 (default) is Context<Bfv<UInt64>>; np.uint32 is Context<Bfv<UInt32>> (use the Bfv32 operations)."""
 
-    def __init__(self, poly_degree: int, coefficient_moduli, plaintext_modulus: int):
+    def __init__(self, poly_degree: int, coefficient_moduli, plaintext_modulus: int, scalar=np.uint64):
         lib = load_library()
         self.degree = int(poly_degree)
         self.coefficientModuli = [int(m) for m in coefficient_moduli]
         self.plaintextModulus = int(plaintext_modulus)
-        mods = _host(self.coefficientModuli)
+        self.scalar = np.dtype(scalar)
         h = C.c_void_p()
-        _check(lib.hecuda_context_create(self.degree, mods.ctypes.data_as(u64p), len(mods), self.plaintextModulus,
-                                         C.byref(h)))
+        if self.scalar == np.dtype(np.uint32):
+            mods = np.ascontiguousarray(self.coefficientModuli, dtype=np.uint64)
+            if mods.size and int(mods.max()) >> 32:
+                raise HeError(-1, "invalidModulus: coefficient modulus does not fit UInt32")
+            mods = mods.astype(np.uint32)
+            _check(lib.hecuda_context_create_u32(self.degree, _ptr(mods), len(mods), self.plaintextModulus, C.byref(h)))
+        else:
+            mods = _host(self.coefficientModuli)
+            _check(lib.hecuda_context_create(self.degree, mods.ctypes.data_as(u64p), len(mods), self.plaintextModulus,
+                                             C.byref(h)))
         self._h = h
         n = C.c_int32(0)
         _check(lib.hecuda_context_ciphertext_moduli_count(h, C.byref(n)))
@@ -609,3 +628,88 @@ class Bfv:
         d = _host(rows).copy()
         _check(load_library().hecuda_ntt_inverse_rows(context._h, modulus, _ptr(d), d.size // context.degree))
         return d
+
+
+def _host32(a) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(a, dtype=np.uint32))
+
+
+class EvaluationKey32:
+    """EvaluationKey<Bfv<UInt32>>: relinearization key as uint32 (L x 2 x K x N, Eval)."""
+
+    def __init__(self, context: Context, relin_key):
+        h = C.c_void_p()
+        k = _host32(relin_key)
+        _check(load_library().hecuda_u32_evk_create(context._h, _ptr(k), C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if self._h is not None:
+            load_library().hecuda_evk_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Bfv32:
+    """The Bfv<UInt32> data path (uint32 arrays, Context(..., scalar=np.uint32)): same shapes as the Bfv methods."""
+
+    @staticmethod
+    def forwardNtt(context: Context, polys, base: int = BASE_Q):
+        d = _host32(polys).copy()
+        rows = d.shape[-2]
+        _check(load_library().hecuda_u32_ntt_forward(context._h, base, _ptr(d), rows, d.size // (rows * context.degree)))
+        return d
+
+    @staticmethod
+    def inverseNtt(context: Context, polys, base: int = BASE_Q):
+        d = _host32(polys).copy()
+        rows = d.shape[-2]
+        _check(load_library().hecuda_u32_ntt_inverse(context._h, base, _ptr(d), rows, d.size // (rows * context.degree)))
+        return d
+
+    @staticmethod
+    def mulAssign(context: Context, lhs, rhs):
+        a, b = _host32(lhs), _host32(rhs)
+        L, n = context.L, context.degree
+        if a.shape != b.shape or a.shape[-3:] != (2, L, n):
+            raise HeError(-1, "invalidCiphertext: multiply takes top-level two-polynomial ciphertexts")
+        out = np.empty(a.shape[:-3] + (3, L, n), dtype=np.uint32)
+        _check(load_library().hecuda_u32_bfv_multiply(context._h, _ptr(a), _ptr(b), _ptr(out), a.size // (2 * L * n)))
+        return out
+
+    @staticmethod
+    def relinearize(context: Context, ciphertext, key: EvaluationKey32):
+        c = _host32(ciphertext)
+        l, n = c.shape[-2], context.degree
+        out = np.empty(c.shape[:-3] + (2, l, n), dtype=np.uint32)
+        _check(load_library().hecuda_u32_bfv_relinearize(context._h, key._h, _ptr(c), l, _ptr(out), c.size // (3 * l * n)))
+        return out
+
+    @staticmethod
+    def modSwitchDown(context: Context, ciphertext):
+        c = _host32(ciphertext)
+        polys, l, n = c.shape[-3], c.shape[-2], context.degree
+        out = np.empty(c.shape[:-3] + (polys, l - 1, n), dtype=np.uint32)
+        _check(load_library().hecuda_u32_bfv_mod_switch_down(context._h, _ptr(c), polys, l, _ptr(out), c.size // (polys * l * n)))
+        return out
+
+    @staticmethod
+    def liftQToQBsk(context: Context, polys):
+        d = _host32(polys)
+        L, n = context.L, context.degree
+        out = np.empty(d.shape[:-2] + (2 * L + 1, n), dtype=np.uint32)
+        _check(load_library().hecuda_u32_rnstool_lift_q_to_qbsk(context._h, _ptr(d), _ptr(out), d.size // (L * n)))
+        return out
+
+    @staticmethod
+    def floorQBskToQ(context: Context, polys):
+        d = _host32(polys)
+        L, n = context.L, context.degree
+        out = np.empty(d.shape[:-2] + (L, n), dtype=np.uint32)
+        _check(load_library().hecuda_u32_rnstool_floor_qbsk_to_q(context._h, _ptr(d), _ptr(out), d.size // ((2 * L + 1) * n)))
+        return out

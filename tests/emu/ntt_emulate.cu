@@ -121,13 +121,13 @@ int main(int argc, char **argv) {
     const int cls = class_of_bits(slot.bits);
     RowMod m;
     m.np = 0 - p;
-    m.kp = cls == kWide ? 2 * p : 4 * p;
+    m.kp = (cls == kWide || cls == kSmall) ? 2 * p : 4 * p;
     m.tw = inverse ? itw.data() : tw.data();
     slot.tw_t = tr.data();
     slot.itw_t = itr.data();
     m.slot = &slot;
     m.scale_mode = inverse ? 0 : -1;
-#define RUN(L) case L: if (cls == kNarrow) run<L, kNarrow>(inverse, in.data(), out.data(), m); else if (cls == kMid) run<L, kMid>(inverse, in.data(), out.data(), m); else run<L, kWide>(inverse, in.data(), out.data(), m); break;
+#define RUN(L) case L: if (cls == kNarrow) run<L, kNarrow>(inverse, in.data(), out.data(), m); else if (cls == kSmall) run<L, kSmall>(inverse, in.data(), out.data(), m); else if (cls == kMid) run<L, kMid>(inverse, in.data(), out.data(), m); else run<L, kWide>(inverse, in.data(), out.data(), m); break;
     switch (logn) { RUN(10) RUN(11) RUN(12) RUN(13) RUN(14) default: return 4; }
     for (int i = 0; i < n; ++i) printf("%llu\n", out[i]);
     return 0;

@@ -39,7 +39,7 @@ def run_emu(binary, logn, p, direction, t, data):
 
 
 @pytest.mark.parametrize("logn", [10, 11, 12, 13, 14])
-@pytest.mark.parametrize("bits", [30, 55, 56, 57, 61, 62])
+@pytest.mark.parametrize("bits", [20, 27, 30, 31, 55, 56, 57, 61, 62])
 def test_emulated_kernels_match_oracle(emu, logn, bits):
     n = 1 << logn
     p = orc.generate_primes([bits], False, n)[0]

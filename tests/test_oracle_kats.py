@@ -298,3 +298,94 @@ def test_scale_and_round(n, bits, t):  # RnsToolTests.swift:21-64: recovers m fr
     data = np.array([crt_decompose(x, q) for x in xs], dtype=np.uint64).T.copy()
     out = rt.scale_and_round(data)
     assert [int(v) for v in out] == ms
+
+
+# ---------------------------------------------------------------- the same RnsToolTests at the reference's UInt32 word size
+# (RnsToolTests.swift runs every test for UInt32 and UInt64: m~ = 2^16, gamma = 2^30 - 20405, 29-bit Bsk,
+#  ModularArithmetic/Scalar.swift:498-511)
+def test_word32_constants():
+    q = orc.generate_primes([27, 28], True, 8)
+    rt = orc.RnsTool(8, q, 2, word_bits=32)
+    assert rt.bsk == orc.generate_primes([29, 29, 29], True, 8)  # RnsTool.swift:30-33 with T.bitWidth - 3 = 29
+    assert all(1 << 28 <= b < 1 << 29 for b in rt.bsk)
+    with pytest.raises(ValueError):
+        orc.RnsTool(8, orc.generate_primes([36], True, 8), 2, word_bits=32)  # above Modulus<UInt32>.max
+
+
+def test_montgomery_reduce_kat_word32():  # RnsToolTests.swift:119-166 with T = UInt32
+    m = 1 << 16
+    (q0,) = orc.generate_primes([28], True)
+    rt = orc.RnsTool(2, [q0], 2, word_bits=32)
+    assert rt.small_montgomery_reduce([[m, 2 * m], [m, 2 * m], [0, 0]]).tolist() == [[1, 2], [1, 2]]
+
+
+@pytest.mark.parametrize("n,bits", [(4, [20, 20]), (8, [27, 28, 28]), (16, [30, 30, 30, 30])])
+def test_lift_q_to_qbsk_word32(n, bits):  # RnsToolTests.swift:169-208
+    q = orc.generate_primes(bits, True)
+    rt = orc.RnsTool(n, q, 2, word_bits=32)
+    Q, qbsk = prod(q), q + rt.bsk
+    QB = prod(qbsk)
+    rnd = random.Random(37)
+    xs = [rnd.randrange(Q) for _ in range(n)]
+    data = np.array([crt_decompose(x, q) for x in xs], dtype=np.uint64).T.copy()
+    out = rt.lift(data)
+    for c, x in enumerate(xs):
+        expected = QB - (Q - x) if x > Q // 2 else x
+        assert [int(out[r, c]) for r in range(len(qbsk))] == crt_decompose(expected, qbsk)
+
+
+@pytest.mark.parametrize("n,bits", [(4, [20, 20]), (8, [27, 28, 28])])
+def test_floor_stages_word32(n, bits):  # RnsToolTests.swift:211-305
+    q = orc.generate_primes(bits, True)
+    rt = orc.RnsTool(n, q, 2, word_bits=32)
+    Q, BSK = prod(q), prod(rt.bsk)
+    qbsk = q + rt.bsk
+    rnd = random.Random(41)
+    xs = [Q * BSK - 1, 1] + [rnd.randrange(Q * BSK) for _ in range(n - 2)]
+    out = rt.approximate_floor(np.array([crt_decompose(x, qbsk) for x in xs], dtype=np.uint64).T.copy())
+    for c, x in enumerate(xs):
+        got = [int(out[r, c]) for r in range(len(rt.bsk))]
+        cands = []
+        for a in range(len(q)):
+            cands += [(x // Q + a) % BSK, (x // Q + BSK - a) % BSK]
+        assert any(got == crt_decompose(v, rt.bsk) for v in cands)
+    ys = [rnd.randrange(Q) for _ in range(n)]
+    out = rt.bsk_to_q(np.array([crt_decompose(y, rt.bsk) for y in ys], dtype=np.uint64).T.copy())
+    for c, y in enumerate(ys):
+        expected = Q - ((BSK - y) % Q) if y > BSK // 2 else y % Q
+        assert [int(out[r, c]) for r in range(len(q))] == crt_decompose(expected % Q, q)
+
+
+def test_scale_and_round_word32():  # RnsToolTests.swift:21-64
+    n, t = 8, 257
+    q = orc.generate_primes([28, 28, 29], True)
+    rt = orc.RnsTool(n, q, t, word_bits=32)
+    Q = prod(q)
+    rnd = random.Random(43)
+    ms = [rnd.randrange(t) for _ in range(n)]
+    xs = [((Q // t) * m + rnd.randrange(-1000, 1000)) % Q for m in ms]
+    out = rt.scale_and_round(np.array([crt_decompose(x, q) for x in xs], dtype=np.uint64).T.copy())
+    assert [int(v) for v in out] == ms
+
+
+def test_multiply_relinearize_decrypts_word32():  # HeApiTestUtils.swift:494-557 run for Bfv<UInt32> (HeAPITests.swift:222-230)
+    n = 64
+    moduli = orc.generate_primes([28, 28, 29], False, n)
+    t = orc.generate_primes([10], True, n)[0]
+    o = orc.Context(n, moduli, t, word_bits=32)
+    sk, rk = o.keygen(7)
+    rnd = np.random.default_rng(3)
+    m1, m2 = rnd.integers(0, t, n, dtype=np.uint64), rnd.integers(0, t, n, dtype=np.uint64)
+    prod3 = o.mul(o.encrypt(1, sk, m1)[None], o.encrypt(2, sk, m2)[None])
+    expect = [0] * n
+    for i in range(n):
+        for j in range(n):
+            v = int(m1[i]) * int(m2[j])
+            if i + j < n:
+                expect[i + j] = (expect[i + j] + v) % t
+            else:
+                expect[i + j - n] = (expect[i + j - n] - v) % t
+    relin = o.relinearize(prod3, rk)
+    assert o.decrypt(sk, prod3[0]).tolist() == expect
+    assert o.decrypt(sk, relin[0]).tolist() == expect
+    assert o.decrypt(sk, o.mod_switch_down(relin)[0]).tolist() == expect
