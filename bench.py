@@ -9,6 +9,7 @@ Workloads (BASELINE.json `configs`):
   C1-8192  the same at N=8192
   C2     Bfv<UInt64> ct x ct multiply, N=8192, 4 coefficient moduli, batch 1024 per GPU        <- the headline metric
   C2-L4  the same with 5 coefficient moduli (L=4)
+  C2-u32 Bfv<UInt32> ct x ct multiply, N=4096, the 27/28/28-bit PIR default moduli (uint32 buffers end to end)
   C3     relinearize + modSwitchDown, N=16384, 8 coefficient moduli, batch 4096 sharded over the GPUs (strong scaling)
   C4     MulPir server computeResponse, 2^20 x 64 B index-PIR database, one shard per GPU (weak scaling)
   C5     PNNS CiphertextMatrix x plaintext-matrix, N=8192, 512-dimensional vectors, one row block per GPU
@@ -51,6 +52,8 @@ WORKLOADS = {
     "C2": ("mul", 8192, Q8192[:4], 557057, 1024),
     "C2-L4": ("mul", 8192, Q8192[:5], 557057, 1024),
     "C3": ("relin", 16384, Q16384, 557057, 4096),
+    # Bfv<UInt32> ct x ct multiply at the PIR default parameters n_4096_logq_27_28_28 (EncryptionParameters.swift:357-367)
+    "C2-u32": ("mul32", 4096, [134176769, 268369921, 268361729], 17, 4096),
     "C4": ("pir", 4096, None, 17, 0),
     "C5": ("pnns", 8192, None, 65537, 0),
 }
@@ -152,7 +155,7 @@ def cpu_items(kind, ctx, n, L, count, seed):
     """Synthetic inputs of `count` units for the oracle."""
     from oracle import oracle as orc
 
-    if kind == "mul":
+    if kind in ("mul", "mul32"):
         return (orc.fill_uniform(seed, ctx.q, n, count * 2 * L).reshape(count, 2, L, n),
                 orc.fill_uniform(seed + 1, ctx.q, n, count * 2 * L).reshape(count, 2, L, n))
     if kind == "relin":
@@ -163,7 +166,7 @@ def cpu_items(kind, ctx, n, L, count, seed):
 def cpu_run(kind, ctx, items, threads, relin_key=None):
     from oracle import oracle as orc
 
-    if kind == "mul":
+    if kind in ("mul", "mul32"):
         return ctx.mul(items[0], items[1], threads=threads)
     if kind == "relin":
         return ctx.mod_switch_down(ctx.relinearize(items[0], relin_key, threads=threads), threads=threads)
@@ -195,7 +198,7 @@ def best_thread_count(kind, ctx, n, L, relin_key):
 def cpu_context(kind, n, moduli, t):
     from oracle import oracle as orc
 
-    ctx = orc.Context(n, moduli, t)
+    ctx = orc.Context(n, moduli, t, word_bits=32 if kind == "mul32" else 64)
     relin_key = ctx.keygen(5)[1] if kind == "relin" else None
     return ctx, relin_key
 
@@ -222,6 +225,7 @@ def cpu_reference_throughput(kind, n, moduli, t, budget_s=12.0):
 METRICS = {
     "ntt": ("forward NTT/s (PolyRq.forwardNtt), one 55-bit modulus", "NTT/s"),
     "mul": ("BFV ct*ct mults/sec at N=8192, 4 coefficient moduli", "mult/s"),
+    "mul32": ("Bfv<UInt32> ct*ct mults/sec at N=4096, 27/28/28-bit coefficient moduli", "mult/s"),
     "relin": ("Bfv relinearize + modSwitchDown per second at N=16384, 8 coefficient moduli", "ciphertexts/s"),
     "pir": ("MulPir computeResponse queries/s (index PIR, 2^20 x 64 B database resident in HBM)", "queries/s"),
     "pnns": ("PNNS encrypted dot products/s (mulTranspose + modSwitchDownToSingle, 512-dimensional vectors)", "dot products/s"),
@@ -236,7 +240,8 @@ def run_reference(args):
     kind = WORKLOADS[args.workload][0]
     metric, unit = METRICS[kind]
     base = {"impl": "reference", "metric": metric, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "higher_is_better": True, "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "warmup": args.warmup, "higher_is_better": True, "vs_baseline": None, "dtype": "u32" if kind == "mul32" else "u64",
+            "data": "synthetic",
             "scaling": "strong" if kind == "relin" else "weak"}
     if kind in ("pir", "pnns"):
         # the application drivers' CPU arm is the oracle timed on a bounded slice of one query, scaled (tools/bench_*.py)
@@ -444,8 +449,8 @@ def oracle_sample_check(kind, n, moduli, t, inputs, got, relin_key=None):
     try:
         from oracle import oracle as orc
 
-        o = orc.Context(n, moduli, t)
-        if kind == "mul":
+        o = orc.Context(n, moduli, t, word_bits=32 if kind == "mul32" else 64)
+        if kind in ("mul", "mul32"):
             want = o.mul(inputs[0], inputs[1])
         else:
             want = o.mod_switch_down(o.relinearize(inputs[0], relin_key))
@@ -455,11 +460,15 @@ def oracle_sample_check(kind, n, moduli, t, inputs, got, relin_key=None):
 
 
 def run_mul(h, name):
-    """C2: Bfv.mulAssign over a batch of synthetic ciphertext pairs."""
+    """C2: Bfv.mulAssign over a batch of synthetic ciphertext pairs.  C2-u32: the same for a Bfv<UInt32> context -- the
+    device-resident value uses the residues zero-extended in 64-bit slots (how they live in HBM), the end-to-end value
+    the uint32 entry point (4-byte residues across PCIe)."""
     args, hecuda, torch = h.args, h.hecuda, h.torch
     n, moduli, t, batch = workload_params(name)
     batch = args.batch or batch
-    ctx = hecuda.Context(n, moduli, t)
+    word32 = WORKLOADS[name][0] == "mul32"
+    kind = "mul32" if word32 else "mul"
+    ctx = hecuda.Context(n, moduli, t, scalar=np.uint32 if word32 else np.uint64)
     L = ctx.L
     lhs, rhs = h.uniform((batch, 2, L, n), moduli[:L]), h.uniform((batch, 2, L, n), moduli[:L])
     out = torch.empty((batch, 3, L, n), dtype=torch.int64, device=h.dev)
@@ -475,13 +484,17 @@ def run_mul(h, name):
     # the dominant kernel: forward NTT over the extended base the multiply computes in (28 of its 49 NTTs), timed
     # alone at the launch shape of one pipeline stage of the host path
     roofline = ntt_roofline(h, ctx, hecuda.BASE_Q_AUX, R, min(batch, 64) * 4, n,
-                            "ntt_rows_kernel<13, forward> over [Q, aux] (7 NARROW rows per polynomial)",
-                            "ntt_forward_dram_bytes_per_row_narrow")
+                            f"ntt_rows_kernel<{n.bit_length() - 1}, forward> over [Q, aux] ({R} "
+                            f"{'SMALL (32-bit butterfly)' if word32 else 'NARROW'} rows per polynomial)",
+                            None if word32 else "ntt_forward_dram_bytes_per_row_narrow")
+    if word32:
+        roofline["bounds"]["int_pipe"]["note"] = ("the 3.3 butterflies/clk/SM ceiling is the 64-bit butterfly's; the 32-bit butterfly "
+                                                  "(1 IMAD.HI + 2 IMAD) is ~3.5x cheaper, so this kernel leans on shared memory / issue")
     roofline["whole_step_stage_model"] = {
         "bytes_per_mult": stage_model_bytes(n, L), "achieved_gbs": stage_model_bytes(n, L) * (value / h.world) / 1e9,
         "frac": stage_model_bytes(n, L) * (value / h.world) / 1e9 / peak}
     checked = 4
-    sample_ok = oracle_sample_check("mul", n, moduli, t, (lhs[:checked].cpu().numpy().view(np.uint64),
+    sample_ok = oracle_sample_check(kind, n, moduli, t, (lhs[:checked].cpu().numpy().view(np.uint64),
                                                            rhs[:checked].cpu().numpy().view(np.uint64)),
                                     out[:checked].cpu().numpy().view(np.uint64)) if h.rank == 0 else None
 
@@ -517,16 +530,24 @@ def run_mul(h, name):
     # ---- e2e: host buffers (pinned), H2D + D2H inside the timed region, through the host-pointer C-ABI call
     e2e = None
     if not args.no_e2e:
-        hl, hr = hecuda.PinnedBuffer((batch, 2, L, n)), hecuda.PinnedBuffer((batch, 2, L, n))
-        ho = hecuda.PinnedBuffer((batch, 3, L, n))
+        dt_host = np.uint32 if word32 else np.uint64
+        hl, hr = hecuda.PinnedBuffer((batch, 2, L, n), dt_host), hecuda.PinnedBuffer((batch, 2, L, n), dt_host)
+        ho = hecuda.PinnedBuffer((batch, 3, L, n), dt_host)
         hl.array[...] = lhs.cpu().numpy().view(np.uint64)
         hr.array[...] = rhs.cpu().numpy().view(np.uint64)
         steps = max(2, min(args.steps, 5))
-        hecuda.Bfv.mulAssign(ctx, hl.array, hr.array, out=ho.array)  # warm-up
+
+        def host_mul():
+            if word32:
+                h.check(h.lib.hecuda_u32_bfv_multiply(ctx._h, hl.array.ctypes.data, hr.array.ctypes.data, ho.array.ctypes.data, batch))
+            else:
+                hecuda.Bfv.mulAssign(ctx, hl.array, hr.array, out=ho.array)
+
+        host_mul()  # warm-up
         h.barrier()
         t0 = time.perf_counter()
         for _ in range(steps):
-            hecuda.Bfv.mulAssign(ctx, hl.array, hr.array, out=ho.array)
+            host_mul()
         torch.cuda.synchronize()
         dt = h.max_over_ranks(time.perf_counter() - t0)
         e2e = {"value": h.world * batch * steps / dt, "unit": "mult/s",
@@ -535,13 +556,14 @@ def run_mul(h, name):
                "matches_device_result": bool(np.array_equal(ho.array[:2], out[:2].cpu().numpy().view(np.uint64))),
                "host_numa": h.numa}
         hl.free(), hr.free(), ho.free()
-    config = {"workload": f"{name}: Bfv<UInt64> ct*ct multiply (Bfv.mulAssign) N={n}, {len(moduli)} "
+    config = {"workload": f"{name}: Bfv<{'UInt32' if word32 else 'UInt64'}> ct*ct multiply (Bfv.mulAssign) N={n}, {len(moduli)} "
                           f"coefficient moduli (L={L} ciphertext + key-switch), t={t}, batch={batch} pairs per GPU",
               "batch_per_gpu": batch, "parallelism": f"batch-sharded x{h.world}, no data-path collective",
-              "l2": "inputs+outputs per step (1.4 GB) exceed L2 (126 MB); no explicit flush",
-              "auxiliary_base": "L+1 primes below 2^55 (BASE_Q_AUX)" if ctx.auxModuli != ctx.bskModuli else "reference Bsk",
+              "l2": f"inputs+outputs per step ({(lhs.numel() * 2 + out.numel()) * 8 / 1e9:.1f} GB) exceed L2 (126 MB); no explicit flush",
+              "auxiliary_base": (f"L+1 primes below 2^{max(ctx.auxModuli).bit_length()} (BASE_Q_AUX)"
+                                 if ctx.auxModuli != ctx.bskModuli else "reference Bsk"),
               "pipeline_chunk": int(os.environ.get("HECUDA_CHUNK", "0")) or "auto"}
-    return dict(kind="mul", n=n, moduli=moduli, t=t, value=value, ms=ms, launches=launches, clocks=clocks, roofline=roofline,
+    return dict(kind=kind, n=n, moduli=moduli, t=t, value=value, ms=ms, launches=launches, clocks=clocks, roofline=roofline,
                 e2e=e2e, config=config, scaling="weak", extra=extra)
 
 
@@ -692,7 +714,7 @@ def main():
         return run_app(args, args.workload)
 
     h = Harness(args)
-    r = {"ntt": run_ntt, "mul": run_mul, "relin": run_relin}[kind](h, args.workload)
+    r = {"ntt": run_ntt, "mul": run_mul, "mul32": run_mul, "relin": run_relin}[kind](h, args.workload)
     if h.rank == 0:
         cpu = None
         if not args.no_cpu_baseline:
@@ -707,7 +729,8 @@ def main():
         line = {
             "metric": metric, "value": r["value"], "unit": unit, "n_gpus": h.world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": r["ms"] / args.steps, "higher_is_better": True, "scaling": r["scaling"], "vs_baseline": None,
-            "dtype": "u64", "data": "synthetic", "config": r["config"], "clocks": r["clocks"], "gpu_launches": r["launches"],
+            "dtype": "u32" if kind == "mul32" else "u64", "data": "synthetic", "config": r["config"], "clocks": r["clocks"],
+            "gpu_launches": r["launches"],
             "roofline": r["roofline"], "cpu_baseline": cpu, "e2e": r["e2e"], "extra": r["extra"],
         }
         print(json.dumps(line))

@@ -425,6 +425,7 @@ static int32_t context_create(int64_t poly_degree, const uint64_t *coefficient_m
     int64_t chunk = (int64_t)((size_t)2048 * 1024 * 1024 / per_item);
     if (const char *env = std::getenv("HECUDA_CHUNK")) chunk = std::atoll(env);
     h->chunk = std::max<int64_t>(1, std::min<int64_t>(chunk, 4096));
+    context_registered(h, true);
     *out = h;
     return HECUDA_OK;
 }
@@ -433,6 +434,8 @@ int32_t hecuda_context_destroy(hecuda_context *h) {
     if (!h) return HECUDA_OK;
     if (h->ctx) cudaSetDevice(h->ctx->device);
     cudaDeviceSynchronize();
+    pir_graphs_purge(h, nullptr);
+    context_registered(h, false);
     for (Workspace *w : h->free_ws) {
         w->release();
         delete w;
@@ -648,6 +651,7 @@ int32_t hecuda_evk_create(const hecuda_context *h, const uint64_t *relin_key, he
 }
 int32_t hecuda_evk_destroy(hecuda_evk *k) {
     if (!k) return HECUDA_OK;
+    if (k->owner) pir_graphs_purge(const_cast<hecuda_context *>(k->owner), k);
     if (k->d_relin) cudaFree(k->d_relin);
     for (auto &kv : k->galois) cudaFree(kv.second);
     for (hecuda::u64 *p : k->retired) cudaFree(p);
@@ -659,6 +663,7 @@ int32_t hecuda_evk_device_buffer(hecuda_evk *k, void **device_ptr, uint64_t *byt
     *device_ptr = k->d_relin;
     *bytes = k->words * sizeof(u64);
     k->loaded = true;  // the caller fills it (e.g. ncclBroadcast from rank 0)
+    ++k->version;
     return HECUDA_OK;
 }
 
@@ -772,6 +777,7 @@ int32_t hecuda_evk_set_galois_key(hecuda_evk *k, uint32_t element, const uint64_
         it->second = d;
     } else {
         k->galois[element] = d;
+        ++k->version;
     }
     return HECUDA_OK;
 }

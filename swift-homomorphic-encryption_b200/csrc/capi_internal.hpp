@@ -70,8 +70,17 @@ struct Workspace {
 }  // namespace api
 }  // namespace hecuda
 
+namespace hecuda {
+namespace api {
+struct PirGraph;  // captured MulPir response pipeline (pir.cu)
+void pir_graphs_purge(hecuda_context *h, const void *evk_or_database);  // drop the graphs that reference a handle (nullptr: all)
+void context_registered(const hecuda_context *h, bool alive);            // contexts whose graph cache may be touched
+}  // namespace api
+}  // namespace hecuda
+
 struct hecuda_context {
     hecuda::Context *ctx = nullptr;
+    std::vector<hecuda::api::PirGraph *> pir_graphs;  // guarded by mu
     int64_t chunk = 32;  // ciphertexts per pipeline stage
     std::mutex mu;
     std::vector<hecuda::api::Workspace *> free_ws;  // pooled workspaces (each with its own stream)
@@ -99,6 +108,7 @@ struct hecuda_context {
 
 struct hecuda_evk {
     const hecuda_context *owner = nullptr;
+    unsigned long long version = 0;  // bumped whenever key material changes (captured graphs bake the key pointers in)
     hecuda::u64 *d_relin = nullptr;  // L x 2 x K x N, Eval
     size_t words = 0;
     bool loaded = false;

@@ -30,7 +30,7 @@ struct RowList {          // rows (within a polynomial) that one launch handles
     int count;
     unsigned short row[kMaxRowList];
     unsigned char slot[kMaxRowList];
-    // 2 bits class | bit 2: re-reduce the gathered input into this row's modulus (forward only)
+    // 3 bits class | bit 3: re-reduce the gathered input into this row's modulus (forward only)
     unsigned char flags[kMaxRowList];
     unsigned char src_row[kMaxRowList];  // input side (forward only): source row
     long long src_poly_stride;           // words between consecutive input polynomials
@@ -112,7 +112,7 @@ template <int LOGN, int CLS, int K>
 __device__ __forceinline__ void inv_row_pass(u64 (&x)[16], u64 *sm, int tau, const RowMod &m) {
     constexpr int C = inv_c(LOGN, K), LB = inv_lb(LOGN, K);
     load_smem<LOGN, LB, C>(x, sm, tau);
-    if (CLS == kNarrow && K > 0 && inv_reduce_at(LOGN, K)) inv_reduce(x, m);
+    if (narrow_like(CLS) && K > 0 && inv_reduce_at(LOGN, K)) inv_reduce(x, m);
     inv_pass<LOGN, LB, C, CLS, inv_bound_in(LOGN, K)>(x, tau, m);
     store_smem<LOGN, LB, C>(x, sm, tau);
 }
@@ -192,10 +192,10 @@ __global__ void __launch_bounds__((1 << LOGN) / 16, (1024 / ((1 << LOGN) / 16)))
                 for (int b = 0; b < kBoxes; ++b) tma_prefetch_box(&map_in, (int)(nword >> 4) + b * kLinesPerBox);
             }
         }
-        const int cls = flags & 3;
+        const int cls = flags & 7;
         RowMod m;
         m.np = 0 - S.p;
-        m.kp = (cls == kWide || cls == kSmall) ? 2 * S.p : 4 * S.p;
+        m.kp = (cls == kWide || cls == kSmall) ? 2 * S.p : 4 * S.p;  // (NARROW / NARROW-H / MID: 4p)
         m.tw = nullptr;
         m.tw_s = smem_u32(tw_cache);
         m.slot = &S;
@@ -210,20 +210,22 @@ __global__ void __launch_bounds__((1 << LOGN) / 16, (1024 / ((1 << LOGN) / 16)))
         } else
 #ifndef HE_EXPERIMENT_ONLY_CLASS
         if (INVERSE) {
-            if (cls == kNarrow) inv_row<LOGN, kNarrow>(sm, tau, m);
+            if (cls == kNarrowH) inv_row<LOGN, kNarrowH>(sm, tau, m);
+            else if (cls == kNarrow) inv_row<LOGN, kNarrow>(sm, tau, m);
             else if (cls == kSmall) inv_row<LOGN, kSmall>(sm, tau, m);
             else if (cls == kMid) inv_row<LOGN, kMid>(sm, tau, m);
             else inv_row<LOGN, kWide>(sm, tau, m);
         } else {
-            const bool reduce_in = (flags & 4) != 0;
-            if (cls == kNarrow) fwd_row<LOGN, kNarrow>(sm, tau, m, reduce_in);
+            const bool reduce_in = (flags & 8) != 0;
+            if (cls == kNarrowH) fwd_row<LOGN, kNarrowH>(sm, tau, m, reduce_in);
+            else if (cls == kNarrow) fwd_row<LOGN, kNarrow>(sm, tau, m, reduce_in);
             else if (cls == kSmall) fwd_row<LOGN, kSmall>(sm, tau, m, reduce_in);
             else if (cls == kMid) fwd_row<LOGN, kMid>(sm, tau, m, reduce_in);
             else fwd_row<LOGN, kWide>(sm, tau, m, reduce_in);
         }
 #else  // register-pressure experiments: one class only
         if (INVERSE) inv_row<LOGN, HE_EXPERIMENT_ONLY_CLASS>(sm, tau, m);
-        else fwd_row<LOGN, HE_EXPERIMENT_ONLY_CLASS>(sm, tau, m, (flags & 4) != 0);
+        else fwd_row<LOGN, HE_EXPERIMENT_ONLY_CLASS>(sm, tau, m, (flags & 8) != 0);
 #endif
         // ---- TMA out: every thread makes its generic-proxy writes visible to the async proxy, then one thread copies
         fence_proxy_async_smem();
@@ -245,12 +247,12 @@ static void build_row_list(const Context &ctx, const NttRowMap &map, bool invers
     rl.count = 0;
     rl.src_poly_stride = map.src_mod ? map.src_poly_stride : (long long)map.rows_per_poly * ctx.n;
     // class-major order (the cheapest rows last, so the tail of the launch is made of short rows)
-    static const int order[4] = {kWide, kMid, kNarrow, kSmall};
-    for (int oi = 0; oi < 4; ++oi) {
+    static const int order[5] = {kWide, kMid, kNarrow, kNarrowH, kSmall};
+    for (int oi = 0; oi < 5; ++oi) {
         const int cls = order[oi];
         for (int r = 0; r < map.rows_per_poly; ++r) {
             const int slot = map.slot[r / map.group];
-            if (class_of_bits(ctx.slots[slot].dev.bits) != cls) continue;
+            if (class_of_modulus(ctx.slots[slot].dev.p, ctx.slots[slot].dev.bits) != cls) continue;
             const int i = rl.count++;
             rl.row[i] = (unsigned short)r;
             rl.slot[i] = (unsigned char)slot;
@@ -261,8 +263,8 @@ static void build_row_list(const Context &ctx, const NttRowMap &map, bool invers
                 // range of the butterflies (< 2p NARROW, < 8p MID, < 4p WIDE); otherwise re-reduce on load
                 // (Bfv+Keys.swift:168-172)
                 const u64 p = ctx.slots[slot].dev.p, src_p = ctx.slots[map.src_slot[r % map.src_mod]].dev.p;
-                const u64 room = cls == kNarrow ? 2u : cls == kMid ? 8u : cls == kSmall ? 1u : 4u;
-                if (src_p > p && (src_p - 1) / p >= room) flags |= 4;
+                const u64 room = narrow_like(cls) ? 2u : cls == kMid ? 8u : cls == kSmall ? 1u : 4u;
+                if (src_p > p && (src_p - 1) / p >= room) flags |= 8;
             }
             rl.flags[i] = (unsigned char)flags;
         }

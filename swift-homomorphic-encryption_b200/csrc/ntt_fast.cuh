@@ -39,6 +39,8 @@
 //   MID (p < 2^61): Harvey-style with doubled ranges, [0, 8p) forward (one conditional subtraction of 4p per
 //       butterfly), [0, 4p) inverse.
 //   WIDE (p < 2^62): exact quotient, [0, 4p) forward / [0, 2p) inverse (the reference's own ranges).
+//   NARROW-H (p = h 2^32 + 1 < 2^55): NARROW's ranges; the product q~ p needs one 32-bit multiply (q~0 h) instead of a
+//       wide one plus two: 4 IMAD.WIDE + 3 IMAD per butterfly.
 //   SMALL (p < 2^30, the moduli of the reference's Bfv<UInt32> and of the default PIR parameters): the butterflies
 //       run in 32-bit arithmetic -- one IMAD.HI and two IMAD per Shoup product instead of five IMAD.WIDE and four IMAD --
 //       on Harvey's ranges, with the 32-bit Shoup factor taken from the top half of the 64-bit one
@@ -54,10 +56,16 @@ constexpr int kMinLogN = 10, kMaxLogN = 14;
 constexpr int kNarrowBits = 55;  // reduction-free butterflies: lazy values < 512 p < 2^64
 constexpr int kMidBits = 61;     // 8 p < 2^64
 constexpr int kSmallBits = 30;   // Modulus<UInt32>.max = 2^30 - 1: the reference's 32-bit word size (Modulus.swift:177-180)
-enum { kNarrow = 0, kMid = 1, kWide = 2, kSmall = 3 };
+enum { kNarrow = 0, kMid = 1, kWide = 2, kSmall = 3, kNarrowH = 4 };
 HE_HD constexpr int class_of_bits(int bits) {
     return bits <= kSmallBits ? kSmall : bits <= kNarrowBits ? kNarrow : bits <= kMidBits ? kMid : kWide;
 }
+// NARROW primes of the form h 2^32 + 1 (the auxiliary primes context.cu picks for the multiply): the q p product of a
+// Shoup multiplication collapses to q + ((q0 h) << 32)
+HE_HD constexpr int class_of_modulus(u64 p, int bits) {
+    return (class_of_bits(bits) == kNarrow && (u32)p == 1u) ? kNarrowH : class_of_bits(bits);
+}
+HE_HD constexpr bool narrow_like(int cls) { return cls == kNarrow || cls == kNarrowH; }
 
 // ---- pass plans: stage counts of the forward passes, in execution order; the inverse runs the mirrored list
 HE_HD constexpr int plan_passes(int logn) { return logn <= 12 ? 3 : 4; }
@@ -299,6 +307,46 @@ HE_HD u64 shoup4(u64 y, u64 w, u64 wp, u64 np) {
     return y * w + q * np;
 #endif
 }
+// the same for p = h 2^32 + 1: q~ p = q~ + ((q~0 h) << 32) mod 2^64; nh = -h mod 2^32 (= high word of 2^64 - p, plus 1)
+HE_HD u64 shoup4h(u64 y, u64 w, u64 wp, u64 np) {
+#if defined(__CUDA_ARCH__)
+    u64 v;
+    asm volatile("{\n\t"
+        ".reg .u32 y0, y1, w0, w1, p0, p1, n0, n1, nh, a1, b1, q0, q1, v0, v1, z;\n\t"
+        ".reg .u64 A, B, Q, V;\n\t"
+        "mov.b64 {y0, y1}, %1;\n\t"
+        "mov.b64 {w0, w1}, %2;\n\t"
+        "mov.b64 {p0, p1}, %3;\n\t"
+        "mov.b64 {n0, n1}, %4;\n\t"
+        "add.u32 nh, n1, 1;\n\t"
+        "mul.hi.u32 a1, y1, p0;\n\t"
+        "mul.hi.u32 b1, y0, p1;\n\t"
+        "mov.u32 z, 0;\n\t"
+        "mov.b64 A, {a1, z};\n\t"
+        "mov.b64 B, {b1, z};\n\t"
+        "mad.wide.u32 Q, y1, p1, A;\n\t"
+        "add.u64 Q, Q, B;\n\t"
+        "mov.b64 {q0, q1}, Q;\n\t"
+        "mul.wide.u32 V, y0, w0;\n\t"
+        "mov.b64 {v0, v1}, V;\n\t"
+        "mad.lo.u32 v1, y1, w0, v1;\n\t"
+        "mad.lo.u32 v1, y0, w1, v1;\n\t"
+        "mad.lo.u32 v1, q0, nh, v1;\n\t"
+        "sub.cc.u32 v0, v0, q0;\n\t"
+        "subc.u32 v1, v1, q1;\n\t"
+        "mov.b64 %0, {v0, v1};\n\t}"
+        : "=l"(v)
+        : "l"(y), "l"(w), "l"(wp), "l"(np));
+    return v;
+#else
+    const u32 y0 = (u32)y, y1 = (u32)(y >> 32), wp0 = (u32)wp, wp1 = (u32)(wp >> 32);
+    const u64 q = (u64)y1 * wp1 + (((u64)y1 * wp0) >> 32) + (((u64)y0 * wp1) >> 32);
+    const u64 h = (0 - np) >> 32;
+    return y * w - q - ((u64)((u32)q * (u32)h) << 32);
+#endif
+}
+template <int CLS>
+HE_HD u64 shoup4c(u64 y, u64 w, u64 wp, u64 np) { return CLS == kNarrowH ? shoup4h(y, w, wp, np) : shoup4(y, w, wp, np); }
 // exact quotient: y w mod p in [0, 2p)
 HE_HD u64 shoup2(u64 y, u64 w, u64 wp, u64 np) { return y * w + mulhi64(y, wp) * np; }
 
@@ -338,8 +386,8 @@ HE_HD void ct_butterfly(u64 &x, u64 &y, const ulonglong2 w, const RowMod &m) {
         const u32 v = shoup32((u32)y, (u32)w.x, (u32)(w.y >> 32), p);
         x = xr + v;
         y = xr - v + p2;
-    } else if (CLS == kNarrow) {  // no reduction: x grows by < 4p per stage
-        const u64 v = shoup4(y, w.x, w.y, m.np);
+    } else if (narrow_like(CLS)) {  // no reduction: x grows by < 4p per stage
+        const u64 v = shoup4c<CLS>(y, w.x, w.y, m.np);
         const u64 xo = x + v;
         y = x - v + m.kp;
         x = xo;
@@ -398,9 +446,9 @@ HE_HD void gs_butterfly(u64 &x, u64 &y, const ulonglong2 w, const RowMod &m, u64
         const u32 s = csub32((u32)x + (u32)y, p2);
         y = shoup32((u32)x - (u32)y + p2, (u32)w.x, (u32)(w.y >> 32), p);
         x = s;
-    } else if (CLS == kNarrow) {  // inputs < kp (a multiple of p), outputs x < 2 kp, y < 4p
+    } else if (narrow_like(CLS)) {  // inputs < kp (a multiple of p), outputs x < 2 kp, y < 4p
         const u64 s = x + y;
-        y = shoup4(x - y + kp, w.x, w.y, m.np);
+        y = shoup4c<CLS>(x - y + kp, w.x, w.y, m.np);
         x = s;
     } else if (CLS == kMid) {  // inputs < 4p, outputs < 4p
         const u64 s = csub(x + y, kp);
@@ -421,7 +469,7 @@ HE_HD void inv_stage(u64 (&x)[16], const int tau, const RowMod &m) {
     constexpr bool kLast = (LB + J == LOGN - 1);
     constexpr int kGroups = 1 << (LOGN - 1 - LB - J);
     const int hi = tau >> (LB - E);
-    const u64 kp = CLS == kNarrow ? (0 - m.np) * (u64)inv_bound_after(BIN, J) : m.kp;  // inputs < kp
+    const u64 kp = narrow_like(CLS) ? (0 - m.np) * (u64)inv_bound_after(BIN, J) : m.kp;  // inputs < kp
     const ulonglong2 *tw_t = LB == 0 ? m.tw_t() + tau : nullptr;
 #pragma unroll
     for (int grp = 0; grp < (1 << (C - 1 - J)); ++grp) {

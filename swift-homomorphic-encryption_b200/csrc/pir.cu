@@ -16,6 +16,8 @@
 #include <algorithm>
 #include <cstring>
 
+#include <set>
+
 #include "capi_internal.hpp"
 
 using namespace hecuda;
@@ -202,8 +204,9 @@ struct StreamBuffers {  // stream-ordered temporaries, freed (stream-ordered) on
 };
 
 // PirUtil.expand on device buffers: d_in = ct_count canonical (Coeff) ciphertexts of L rows, d_out = output_count
+// d_steps_ready: the plan's steps already on the device (captured graphs upload them once, outside the capture)
 int32_t expand_device(const hecuda_context *h, const hecuda_evk *k, const u64 *d_in, int64_t ct_count, int64_t output_count,
-                      u64 *d_out, cudaStream_t s) {
+                      u64 *d_out, cudaStream_t s, const void *d_steps_ready = nullptr) {
     const Context &c = *h->ctx;
     const int l = c.L;
     const int64_t n = c.n;
@@ -222,9 +225,13 @@ int32_t expand_device(const hecuda_context *h, const hecuda_evk *k, const u64 *d
     CK(tmp.alloc(&c1_buf[0], ct_words * plan.max_nodes));
     CK(tmp.alloc(&c1_buf[1], ct_words * plan.max_nodes));
     CK(tmp.alloc(&scratch, galois_scratch_words(c, l) * (size_t)chunk));
-    CK(tmp.alloc_bytes((void **)&d_steps, plan.steps.size() * sizeof(ExpandStep)));
-    CK(cudaMemcpyAsync(d_steps, plan.steps.data(), plan.steps.size() * sizeof(ExpandStep), cudaMemcpyHostToDevice, s));
-    CK(wait_stream(s));  // plan.steps is a pageable temporary
+    if (d_steps_ready) {
+        d_steps = (ExpandStep *)d_steps_ready;
+    } else {
+        CK(tmp.alloc_bytes((void **)&d_steps, plan.steps.size() * sizeof(ExpandStep)));
+        CK(cudaMemcpyAsync(d_steps, plan.steps.data(), plan.steps.size() * sizeof(ExpandStep), cudaMemcpyHostToDevice, s));
+        CK(wait_stream(s));  // plan.steps is a pageable temporary
+    }
     const RowConsts rc = row_consts(c, l);
     const int threads = n >= 256 ? 256 : (n < 32 ? 32 : (int)n);
     const u64 *cur = d_in;  // the active roots are a prefix of the input (only the last one can be a single output)
@@ -286,7 +293,7 @@ struct ResponseShape {
 // indices_count x chunk_count ciphertexts of 2 x 1 x N (Coeff, one modulus)
 int32_t compute_response_device(const hecuda_context *h, const hecuda_evk *k, const hecuda_pir_database *const *dbs,
                                 int32_t db_count, const ResponseShape &shape, const u64 *d_query, int64_t query_ct_count,
-                                int64_t indices_count, u64 *d_out, cudaStream_t s) {
+                                int64_t indices_count, u64 *d_out, cudaStream_t s, const void *d_steps_ready = nullptr) {
     const Context &c = *h->ctx;
     const int L = c.L;
     const int64_t n = c.n;
@@ -297,7 +304,7 @@ int32_t compute_response_device(const hecuda_context *h, const hecuda_evk *k, co
     u64 *expanded = nullptr, *first_eval = nullptr, *results[2] = {nullptr, nullptr}, *lhs = nullptr, *ct3 = nullptr,
         *scratch = nullptr;
     CK(tmp.alloc(&expanded, ct_words * eqc * indices_count));
-    int32_t rc = expand_device(h, k, d_query, query_ct_count, eqc * indices_count, expanded, s);
+    int32_t rc = expand_device(h, k, d_query, query_ct_count, eqc * indices_count, expanded, s, d_steps_ready);
     if (rc) return rc;
     CK(tmp.alloc(&first_eval, ct_words * dim0));
     CK(tmp.alloc(&results[0], ct_words * rows));
@@ -396,6 +403,152 @@ int32_t check_response_args(const hecuda_context *h, const hecuda_evk *k, const 
     return check_expand_args(h, k, query, query_ct_count, shape.expanded_query_count * indices_count, out);
 }
 
+
+// ---------------------------------------------------------------- captured response pipelines
+// One query is ~100 small launches (level-by-level expansion, first-dimension scan, ct x ct folding, modulus switches);
+// at PIR sizes each kernel runs for a few microseconds, so the call is bound by launch latency.  The host entry point
+// therefore captures the pipeline of a (database, evaluation key, shape) triple into a CUDA graph the first time it
+// sees it and replays it afterwards: one graph launch per query.  An instance owns its query / reply buffers (the
+// addresses are baked into the graph) and serves one query at a time; concurrent callers get instances of their own.
+// HECUDA_PIR_GRAPH=0 disables this.
+}  // namespace
+namespace hecuda {
+namespace api {
+struct PirGraph {
+    const hecuda_evk *evk = nullptr;
+    unsigned long long evk_version = 0;
+    const hecuda_pir_database *db = nullptr;
+    std::vector<int64_t> dims;
+    int64_t chunk_count = 0, query_ct_count = 0;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    u64 *d_query = nullptr, *d_out = nullptr;
+    void *d_steps = nullptr;
+    unsigned long long launches = 0;  // kernels inside the graph (for hecuda_kernel_launch_count)
+    bool busy = false;
+    void release() {
+        if (exec) cudaGraphExecDestroy(exec);
+        if (graph) cudaGraphDestroy(graph);
+        if (d_query) cudaFree(d_query);
+        if (d_out) cudaFree(d_out);
+        if (d_steps) cudaFree(d_steps);
+    }
+};
+// Handles may outlive their context (a garbage-collected host destroys them in any order): only touch a live context.
+static std::mutex g_live_mu;
+static std::set<const hecuda_context *> g_live;
+void context_registered(const hecuda_context *h, bool alive) {
+    std::lock_guard<std::mutex> lock(g_live_mu);
+    if (alive) g_live.insert(h);
+    else g_live.erase(h);
+}
+void pir_graphs_purge(hecuda_context *h, const void *handle) {
+    if (!h) return;
+    std::vector<PirGraph *> dead;
+    {
+        std::lock_guard<std::mutex> live(g_live_mu);
+        if (!g_live.count(h)) return;
+        std::lock_guard<std::mutex> lock(h->mu);
+        auto &v = h->pir_graphs;
+        for (size_t i = 0; i < v.size();) {
+            if (!handle || v[i]->evk == handle || v[i]->db == handle) {
+                dead.push_back(v[i]);
+                v.erase(v.begin() + (long)i);
+            } else {
+                ++i;
+            }
+        }
+    }
+    if (!dead.empty()) cudaDeviceSynchronize();  // a purged instance may still be replaying on another thread's stream
+    for (PirGraph *g : dead) {
+        g->release();
+        delete g;
+    }
+}
+}  // namespace api
+}  // namespace hecuda
+namespace {
+
+bool pir_graphs_enabled() {
+    static const bool on = [] {
+        const char *env = std::getenv("HECUDA_PIR_GRAPH");
+        return !(env && env[0] == '0');
+    }();
+    return on;
+}
+
+// Finds an idle instance for this call or builds one; nullptr (with *rc == OK) when capture is not possible.
+PirGraph *acquire_graph(const hecuda_context *hc, const hecuda_evk *k, const hecuda_pir_database *db, const ResponseShape &shape,
+                        int64_t query_ct_count, cudaStream_t s, int32_t *rc) {
+    hecuda_context *h = const_cast<hecuda_context *>(hc);
+    *rc = HECUDA_OK;
+    {
+        std::lock_guard<std::mutex> lock(h->mu);
+        for (PirGraph *g : h->pir_graphs)
+            if (!g->busy && g->evk == k && g->evk_version == k->version && g->db == db && g->dims == shape.dims &&
+                g->chunk_count == shape.chunk_count && g->query_ct_count == query_ct_count) {
+                g->busy = true;
+                return g;
+            }
+    }
+    const Context &c = *h->ctx;
+    const size_t ct_words = (size_t)2 * c.L * c.n, out_words = (size_t)2 * c.n * shape.chunk_count;
+    PirGraph *g = new (std::nothrow) PirGraph();
+    if (!g) return nullptr;
+    g->evk = k;
+    g->evk_version = k->version;
+    g->db = db;
+    g->dims = shape.dims;
+    g->chunk_count = shape.chunk_count;
+    g->query_ct_count = query_ct_count;
+    const ExpandPlan plan = build_expand_plan(c.n, query_ct_count, shape.expanded_query_count);
+    cudaError_t e = cudaMalloc(&g->d_query, ct_words * query_ct_count * sizeof(u64));
+    if (e == cudaSuccess) e = cudaMalloc(&g->d_out, out_words * sizeof(u64));
+    if (e == cudaSuccess) e = cudaMalloc(&g->d_steps, std::max<size_t>(plan.steps.size(), 1) * sizeof(ExpandStep));
+    if (e == cudaSuccess && !plan.steps.empty()) e = upload(g->d_steps, plan.steps.data(), plan.steps.size() * sizeof(ExpandStep));
+    if (e != cudaSuccess) {
+        g->release();
+        delete g;
+        *rc = cuda_fail(e, "response graph buffers");
+        return nullptr;
+    }
+    e = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal);
+    int32_t body = HECUDA_OK;
+    if (e == cudaSuccess) {
+        const hecuda_pir_database *dbs[1] = {db};
+        body = compute_response_device(hc, k, dbs, 1, shape, g->d_query, query_ct_count, 1, g->d_out, s, g->d_steps);
+        e = cudaStreamEndCapture(s, &g->graph);
+    }
+    if (e == cudaSuccess && body == HECUDA_OK) e = cudaGraphInstantiate(&g->exec, g->graph, 0);
+    if (e == cudaSuccess && body == HECUDA_OK) {  // kernels per replay, for hecuda_kernel_launch_count
+        size_t count = 0;
+        if (cudaGraphGetNodes(g->graph, nullptr, &count) == cudaSuccess && count) {
+            std::vector<cudaGraphNode_t> nodes(count);
+            cudaGraphGetNodes(g->graph, nodes.data(), &count);
+            for (size_t i = 0; i < count; ++i) {
+                cudaGraphNodeType type;
+                if (cudaGraphNodeGetType(nodes[i], &type) == cudaSuccess && type == cudaGraphNodeTypeKernel) ++g->launches;
+            }
+        }
+    }
+    if (e != cudaSuccess || body != HECUDA_OK) {  // not capturable on this setup: the caller takes the direct path
+        cudaGetLastError();
+        g->release();
+        delete g;
+        if (body != HECUDA_OK) *rc = body;
+        return nullptr;
+    }
+    g->busy = true;
+    std::lock_guard<std::mutex> lock(h->mu);
+    h->pir_graphs.push_back(g);
+    return g;
+}
+void release_graph(const hecuda_context *hc, PirGraph *g) {
+    hecuda_context *h = const_cast<hecuda_context *>(hc);
+    std::lock_guard<std::mutex> lock(h->mu);
+    g->busy = false;
+}
+
 }  // namespace
 
 extern "C" {
@@ -443,6 +596,7 @@ int32_t hecuda_pir_database_create(const hecuda_context *h, const uint64_t *plai
 
 int32_t hecuda_pir_database_destroy(hecuda_pir_database *db) {
     if (!db) return HECUDA_OK;
+    if (db->owner) pir_graphs_purge(const_cast<hecuda_context *>(db->owner), db);
     if (db->d_plain) cudaFree(db->d_plain);
     if (db->d_present) cudaFree(db->d_present);
     delete db;
@@ -511,6 +665,20 @@ int32_t hecuda_mulpir_compute_response(const hecuda_context *h, const hecuda_evk
     const Context &c = *h->ctx;
     const size_t ct_words = (size_t)2 * c.L * c.n, out_words = (size_t)2 * c.n * chunk_count * indices_count;
     cudaStream_t s = g.w->stream;
+    if (indices_count == 1 && db_count == 1 && pir_graphs_enabled()) {
+        PirGraph *pg = acquire_graph(h, k, dbs[0], shape, query_ct_count, s, &rc);
+        if (rc) return rc;
+        if (pg) {
+            cudaError_t e = cudaMemcpyAsync(pg->d_query, query, ct_words * query_ct_count * sizeof(u64), cudaMemcpyHostToDevice, s);
+            if (e == cudaSuccess) e = cudaGraphLaunch(pg->exec, s);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(out, pg->d_out, out_words * sizeof(u64), cudaMemcpyDeviceToHost, s);
+            if (e == cudaSuccess) e = wait_stream(s);
+            g_kernel_launches += pg->launches;
+            release_graph(h, pg);
+            if (e != cudaSuccess) return cuda_fail(e, "response graph");
+            return HECUDA_OK;
+        }
+    }
     StreamBuffers tmp(s);
     u64 *d_query = nullptr, *d_out = nullptr;
     CK(tmp.alloc(&d_query, ct_words * query_ct_count));

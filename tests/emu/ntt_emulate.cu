@@ -44,7 +44,7 @@ static void inv_pass_k(std::vector<u64> &x, std::vector<u64> &sm, const RowMod &
     }
     for (int tau = 0; tau < T; ++tau) {
         u64(&xr)[16] = *reinterpret_cast<u64(*)[16]>(&x[tau * 16]);
-        if (CLS == kNarrow && K > 0 && inv_reduce_at(LOGN, K)) inv_reduce(xr, m);
+        if (narrow_like(CLS) && K > 0 && inv_reduce_at(LOGN, K)) inv_reduce(xr, m);
         inv_pass<LOGN, LB, C, CLS, inv_bound_in(LOGN, K)>(xr, tau, m);
     }
     for (int tau = 0; tau < T; ++tau) {
@@ -118,7 +118,7 @@ int main(int argc, char **argv) {
     const u64 n_inv_w = host::mulmod(n_inv, itw[1].x, p);
     slot.inv_scale[0].c0 = n_inv; slot.inv_scale[0].c0p = host::shoup_factor(n_inv, p);
     slot.inv_scale[0].c1 = n_inv_w; slot.inv_scale[0].c1p = host::shoup_factor(n_inv_w, p);
-    const int cls = class_of_bits(slot.bits);
+    const int cls = class_of_modulus(p, slot.bits);
     RowMod m;
     m.np = 0 - p;
     m.kp = (cls == kWide || cls == kSmall) ? 2 * p : 4 * p;
@@ -127,7 +127,7 @@ int main(int argc, char **argv) {
     slot.itw_t = itr.data();
     m.slot = &slot;
     m.scale_mode = inverse ? 0 : -1;
-#define RUN(L) case L: if (cls == kNarrow) run<L, kNarrow>(inverse, in.data(), out.data(), m); else if (cls == kSmall) run<L, kSmall>(inverse, in.data(), out.data(), m); else if (cls == kMid) run<L, kMid>(inverse, in.data(), out.data(), m); else run<L, kWide>(inverse, in.data(), out.data(), m); break;
+#define RUN(L) case L: if (cls == kNarrowH) run<L, kNarrowH>(inverse, in.data(), out.data(), m); else if (cls == kNarrow) run<L, kNarrow>(inverse, in.data(), out.data(), m); else if (cls == kSmall) run<L, kSmall>(inverse, in.data(), out.data(), m); else if (cls == kMid) run<L, kMid>(inverse, in.data(), out.data(), m); else run<L, kWide>(inverse, in.data(), out.data(), m); break;
     switch (logn) { RUN(10) RUN(11) RUN(12) RUN(13) RUN(14) default: return 4; }
     for (int i = 0; i < n; ++i) printf("%llu\n", out[i]);
     return 0;

@@ -97,3 +97,21 @@ def test_plans_cover_all_elements_and_are_conflict_free(logn, inverse):
                     slots.append((phys // 2) % 8 if vec else phys % 16)
                 assert max(Counter(slots).values()) == 1, (logn, inverse, LB, C, r, w0)
         assert seen == set(range(n))
+
+
+@pytest.mark.parametrize("logn", [10, 12, 13, 14])
+def test_emulated_narrow_h_class(emu, logn):
+    """Primes h 2^32 + 1 below 2^55 (the auxiliary primes of the multiply) take the NARROW-H butterfly."""
+    n = 1 << logn
+    p = (1 << 54) + 1
+    while not orc.is_prime(p):
+        p += 1 << 32
+    assert p < 1 << 55 and p % (1 << 32) == 1
+    x = orc.fill_uniform(logn, [p], n, 1)[0]
+    x[:3] = [0, p - 1, 1]
+    fwd = run_emu(emu, logn, p, "fwd", 0, x)
+    assert np.array_equal(fwd, orc.ntt_forward(n, [p], [x])[0])
+    assert np.array_equal(run_emu(emu, logn, p, "inv", 0, fwd), x)
+    worst = np.full(n, p - 1, dtype=np.uint64)
+    assert np.array_equal(run_emu(emu, logn, p, "fwd", 0, worst), orc.ntt_forward(n, [p], [worst])[0])
+    assert np.array_equal(run_emu(emu, logn, p, "inv", 0, worst), orc.ntt_inverse(n, [p], [worst])[0])
