@@ -121,7 +121,13 @@ int32_t hecuda_ntt_inverse_rows(const hecuda_context *ctx, uint64_t modulus, uin
 
 /* Bfv.mulAssign(_:_:) -- Bfv/Bfv+Multiply.swift:18-21 (multiplyWithoutScaling :63-85 + dropExtendedBase :31-48).
  * lhs, rhs: batch x 2 x L x N (Coeff, top level, correction factor 1); out: batch x 3 x L x N (Coeff).
- * Ciphertexts below the top level are refused (HECUDA_ERR_UNSUPPORTED; DESIGN.md "levels"). */
+ * TOP LEVEL ONLY, by construction: the entry point has no moduli_count argument and always reads L rows per polynomial,
+ * so a caller holding ciphertexts below the top level (after modSwitchDown) must not pass them here -- the Swift overlay
+ * checks `ciphertext.moduli.count == context.ciphertextContext.moduli.count` and throws
+ * HeError.unsupportedHeOperation otherwise.  Reason: below the top level the reference derives its
+ * [Bsk, m~] base by dropping m~ from the top-level one (RnsTool.swift:185-186 with PolyContext.swift:131-141) while
+ * smallMontgomeryReduce still assumes it (:340-360); no reference test pins what that computes, so it is not
+ * reproduced (DESIGN.md "levels").  MulPir and PNNS multiply at the top level only. */
 int32_t hecuda_bfv_multiply(const hecuda_context *ctx, const uint64_t *lhs, const uint64_t *rhs, uint64_t *out,
                             int64_t batch);
 int32_t hecuda_bfv_multiply_device(const hecuda_context *ctx, const uint64_t *lhs, const uint64_t *rhs, uint64_t *out,

@@ -97,6 +97,7 @@ bool make_map(const Context &c, int32_t base, int32_t rows, NttRowMap &map, std:
             map = c.map_qaux();
             return true;
         case HECUDA_BASE_KEYSWITCH:
+            if (!c.has_ks) { err = "invalidPolyContext: these parameters have no key-switching modulus"; return false; }
             if (rows < 2 || rows > c.L + 1) { err = "invalidPolyContext: BASE_KEYSWITCH needs 2..L+1 rows"; return false; }
             map = c.map_ks(rows - 1);
             return true;
@@ -624,6 +625,8 @@ int32_t hecuda_evk_create_empty(const hecuda_context *h, hecuda_evk **out) {
     if (rc) return rc;
     if (!out) return fail(HECUDA_ERR_INVALID_ARGUMENT, "null argument");
     const Context &c = *h->ctx;
+    if (!c.has_ks)  // Context.supportsEvaluationKey == false with a single coefficient modulus (Context.swift:102-107)
+        return fail(HECUDA_ERR_UNSUPPORTED, "unsupportedHeOperation: a single coefficient modulus leaves no key-switching modulus");
     hecuda_evk *k = new (std::nothrow) hecuda_evk();
     if (!k) return fail(HECUDA_ERR_CUDA, "out of host memory");
     k->owner = h;

@@ -101,8 +101,10 @@ Context *Context::create(int64_t n, const u64 *coeff_moduli, int nmod, u64 t, st
         if (coeff_moduli[i] >> (word_bits - 2)) { err = "invalidModulus: " + std::to_string(coeff_moduli[i]) + " exceeds the maximum of this word size"; return nullptr; }
     if (n < 2 || (n & (n - 1)) || n > (1 << 17)) { err = "invalidDegree: N must be a power of two in [2, 2^17]"; return nullptr; }
     // the NTT kernels keep a whole row in one CTA's shared memory: N <= 2^14 (a 2^15 row is 256 KB)
-    if (n > (1 << fast::kMaxLogN)) { err = "unsupportedHeOperation: polynomial degrees above 2^" + std::to_string(fast::kMaxLogN) + " are not supported by the NTT kernels"; return nullptr; }
-    if (nmod < 2) { err = "invalidEncryptionParameters: need >= 1 ciphertext modulus plus the key-switching modulus"; return nullptr; }
+    // 2^15 (the reference's largest predefined degree, EncryptionParameters.swift:199-206) runs as one cross-half stage
+    // plus two 2^14 transforms (ntt_fast.cu)
+    if (n > (1 << fast::kSplitLogN)) { err = "unsupportedHeOperation: polynomial degrees above 2^" + std::to_string(fast::kSplitLogN) + " are not supported by the NTT kernels"; return nullptr; }
+    if (nmod < 1) { err = "invalidEncryptionParameters: need at least one coefficient modulus"; return nullptr; }
     if (nmod - 1 > kMaxL) { err = "unsupportedHeOperation: more than " + std::to_string(kMaxL) + " ciphertext moduli"; return nullptr; }
     if (t < 2) { err = "invalidEncryptionParameters: plaintext modulus"; return nullptr; }
     for (int i = 0; i < nmod; ++i)
@@ -112,7 +114,9 @@ Context *Context::create(int64_t n, const u64 *coeff_moduli, int nmod, u64 t, st
     Context *c = new Context();
     c->n = n;
     c->logn = bit_length((u64)n) - 1;
-    c->L = nmod - 1;
+    // one coefficient modulus: it is the ciphertext modulus and there is no key-switching modulus (Context.swift:102-107)
+    c->has_ks = nmod >= 2;
+    c->L = c->has_ks ? nmod - 1 : 1;
     c->t = t;
     c->word_bits = word_bits;
     c->mtilde = word_bits == 64 ? (1ull << 32) : (1ull << 16);                       // Scalar.swift:509-511, 522-524
@@ -123,7 +127,7 @@ Context *Context::create(int64_t n, const u64 *coeff_moduli, int nmod, u64 t, st
     cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device);
     const int L = c->L;
     c->q.assign(coeff_moduli, coeff_moduli + L);
-    c->q_ks = coeff_moduli[L];
+    c->q_ks = c->has_ks ? coeff_moduli[L] : 0;
     for (u64 qi : c->q)
         if (t >= qi) { err = "invalidEncryptionParameters: plaintext modulus must be below every coefficient modulus"; delete c; return nullptr; }
     // BEHZ auxiliary base: the L+1 smallest (bitWidth - 3)-bit NTT primes (RnsTool.swift:30-33)
@@ -183,13 +187,24 @@ Context *Context::create(int64_t n, const u64 *coeff_moduli, int nmod, u64 t, st
         for (int j = 0; j <= L; ++j) slot_mod[c->slot_aux(j)] = c->aux[j];
     const size_t table_bytes = sizeof(ulonglong2) * (size_t)n;
     const bool fast = c->logn >= fast::kMinLogN && c->logn <= fast::kMaxLogN;
-    const int threads = (int)(n / 16);
-    const size_t tr_bytes = fast ? sizeof(ulonglong2) * (size_t)15 * threads : 0;  // transposed line-owning-pass tables
-    const size_t slot_bytes = 2 * (table_bytes + tr_bytes);
+    const bool split = c->logn == fast::kSplitLogN;  // two half-size transforms per row, each with its own twiddle view
+    const int half_logn = c->logn - 1;
+    const int64_t half_n = n / 2;
+    const int threads = (int)((split ? half_n : n) / 16);
+    const size_t tr_bytes = (fast || split) ? sizeof(ulonglong2) * (size_t)15 * threads : 0;  // transposed line-owning-pass tables
+    const size_t half_bytes = sizeof(ulonglong2) * (size_t)half_n;
+    // per slot: [tw][itw] then, unsplit: [tw_t][itw_t]; split: per half [tw_h][itw_h][tw_t_h][itw_t_h]
+    const size_t slot_bytes = 2 * table_bytes + (split ? 2 * (2 * half_bytes + 2 * tr_bytes) : 2 * tr_bytes);
     if (cudaMalloc(&c->d_pool, slot_bytes * nslots) != cudaSuccess) { err = "cudaMalloc failed for twiddle tables"; delete c; return nullptr; }
-    std::vector<ulonglong2> tw, itw, tr(15 * (size_t)threads), itr(15 * (size_t)threads);
-    std::vector<ModSlot> dev_slots(nslots);
+    std::vector<ulonglong2> tw, itw, tr(15 * (size_t)threads), itr(15 * (size_t)threads), twh, itwh;
+    std::vector<ModSlot> dev_slots(split ? 3 * nslots : nslots);
+    c->split_slot_base = split ? nslots : 0;
     for (int s = 0; s < nslots; ++s) {
+        if (s == c->slot_ks() && !c->has_ks) {  // no key-switching modulus: the slot stays empty
+            std::memset(&c->slots[s].dev, 0, sizeof(ModSlot));
+            dev_slots[s] = c->slots[s].dev;
+            continue;
+        }
         if (!build_slot(c->slots[s], slot_mod[s], n, c->logn, t, tw, itw, err)) { delete c; return nullptr; }
         char *base = (char *)c->d_pool + slot_bytes * s;
         cudaMemcpy(base, tw.data(), table_bytes, cudaMemcpyHostToDevice);
@@ -208,9 +223,40 @@ Context *Context::create(int64_t n, const u64 *coeff_moduli, int nmod, u64 t, st
             c->slots[s].dev.itw_t = (const ulonglong2 *)(base + 2 * table_bytes + tr_bytes);
         }
         dev_slots[s] = c->slots[s].dev;
+        if (split) {
+            // After the cross-half stage, half h of a row is a 2^14-point transform whose stage s' (2^s' groups) uses the
+            // full table's entries (2 + h) 2^s' + group: lay those out like a table of a 2^14 transform, so the 2^14
+            // kernels run on the halves unchanged (virtual slot nslots + 2 s + h).
+            for (int hh = 0; hh < 2; ++hh) {
+                twh.assign(half_n, tw[0]);
+                itwh.assign(half_n, itw[0]);
+                for (int64_t i = 1; i < half_n; ++i) {
+                    const int sp = bit_length((u64)i) - 1;
+                    const int64_t src = ((int64_t)(2 + hh) << sp) + (i - ((int64_t)1 << sp));
+                    twh[i] = tw[src];
+                    itwh[i] = itw[src];
+                }
+                for (int k = 0; k < 15; ++k)
+                    for (int tau = 0; tau < threads; ++tau) {
+                        tr[(size_t)k * threads + tau] = twh[fast::fwd_last_source(half_logn, k, tau)];
+                        itr[(size_t)k * threads + tau] = itwh[fast::inv_first_source(half_logn, k, tau)];
+                    }
+                char *hb = base + 2 * table_bytes + hh * (2 * half_bytes + 2 * tr_bytes);
+                cudaMemcpy(hb, twh.data(), half_bytes, cudaMemcpyHostToDevice);
+                cudaMemcpy(hb + half_bytes, itwh.data(), half_bytes, cudaMemcpyHostToDevice);
+                cudaMemcpy(hb + 2 * half_bytes, tr.data(), tr_bytes, cudaMemcpyHostToDevice);
+                cudaMemcpy(hb + 2 * half_bytes + tr_bytes, itr.data(), tr_bytes, cudaMemcpyHostToDevice);
+                ModSlot v = c->slots[s].dev;
+                v.tw = (const ulonglong2 *)hb;
+                v.itw = (const ulonglong2 *)(hb + half_bytes);
+                v.tw_t = (const ulonglong2 *)(hb + 2 * half_bytes);
+                v.itw_t = (const ulonglong2 *)(hb + 2 * half_bytes + tr_bytes);
+                dev_slots[nslots + 2 * s + hh] = v;
+            }
+        }
     }
-    if (cudaMalloc(&c->d_slots, sizeof(ModSlot) * nslots) != cudaSuccess) { err = "cudaMalloc failed"; delete c; return nullptr; }
-    cudaMemcpy(c->d_slots, dev_slots.data(), sizeof(ModSlot) * nslots, cudaMemcpyHostToDevice);
+    if (cudaMalloc(&c->d_slots, sizeof(ModSlot) * dev_slots.size()) != cudaSuccess) { err = "cudaMalloc failed"; delete c; return nullptr; }
+    cudaMemcpy(c->d_slots, dev_slots.data(), sizeof(ModSlot) * dev_slots.size(), cudaMemcpyHostToDevice);
 
     // ---- BEHZ constants (top level)
     const u64 *Q = c->q.data();
@@ -315,6 +361,7 @@ Context *Context::create(int64_t n, const u64 *coeff_moduli, int nmod, u64 t, st
     for (int l = 1; l <= L; ++l) {
         std::vector<u64> base(c->q.begin(), c->q.begin() + l);
         if (l >= 2) c->ms_divround[l] = build_divround(base);
+        if (!c->has_ks) continue;
         base.push_back(c->q_ks);
         c->ks_divround[l] = build_divround(base);
     }

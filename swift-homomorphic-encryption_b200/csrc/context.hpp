@@ -127,12 +127,14 @@ class Context {
     int device;
     int sm_count;
     std::vector<u64> q;    // q_0..q_{L-1}
-    u64 q_ks;
+    u64 q_ks;              // 0 when the parameters have a single coefficient modulus: no key-switching modulus, no
+    bool has_ks = true;    // evaluation keys (Context.swift:102-107, supportsEvaluationKey == false)
     std::vector<u64> bsk;  // L+1 primes: the reference's BEHZ base (RnsTool.swift:30-33)
     std::vector<u64> aux;  // L+1 primes: the base ct x ct multiply actually computes in (context.cu); == bsk when
     bool aux_is_reference = true;  // the conditions for the faster base do not hold (or HECUDA_AUX_BASE=reference)
     std::vector<HostSlot> slots;  // L q's, L+1 bsk, 1 q_ks, then L+1 aux (when different from bsk)
-    ModSlot *d_slots = nullptr;   // device array [2L+2]
+    ModSlot *d_slots = nullptr;   // device array: the slots, then (N = 2^15 only) 2 virtual half-transform slots per slot
+    int split_slot_base = 0;      // index of the first virtual slot (slot s, half h -> split_slot_base + 2 s + h)
     LiftConsts lift;        // over [Q, Bsk]: stage-level entry points
     FloorConsts floor;
     LiftConsts lift_mul;    // over [Q, aux]: Bfv.mulAssign / innerProduct

@@ -24,15 +24,16 @@
 namespace hecuda {
 using namespace fast;
 
-constexpr int kMaxRowList = (kMaxL + 1) * kMaxL;  // key-switch digit rows: (l + 1) * l
+constexpr int kMaxRowList = 2 * (kMaxL + 1) * kMaxL;  // key-switch digit rows: (l + 1) * l, twice that as half rows of N = 2^15
 struct RowList {          // rows (within a polynomial) that one launch handles
     int rows_per_poly;
     int count;
     unsigned short row[kMaxRowList];
     unsigned char slot[kMaxRowList];
-    // 3 bits class | bit 3: re-reduce the gathered input into this row's modulus (forward only)
+    // 3 bits class | bit 3: re-reduce the gathered input into this row's modulus (forward only) | bit 4: half of a
+    // 2^15 row (inverse only: no N^-1 scaling)
     unsigned char flags[kMaxRowList];
-    unsigned char src_row[kMaxRowList];  // input side (forward only): source row
+    unsigned short src_row[kMaxRowList];  // input side (forward only): source row
     long long src_poly_stride;           // words between consecutive input polynomials
 };
 
@@ -114,6 +115,14 @@ __device__ __forceinline__ void inv_row_pass(u64 (&x)[16], u64 *sm, int tau, con
     load_smem<LOGN, LB, C>(x, sm, tau);
     if (narrow_like(CLS) && K > 0 && inv_reduce_at(LOGN, K)) inv_reduce(x, m);
     inv_pass<LOGN, LB, C, CLS, inv_bound_in(LOGN, K)>(x, tau, m);
+    if (K == plan_passes(LOGN) - 1 && m.partial) {  // half of a 2^15 row: hand canonical residues to the merge kernel
+        if (CLS == kSmall) {
+#pragma unroll
+            for (int r = 0; r < 16; ++r) x[r] = csub32((u32)x[r], (u32)(0 - m.np));
+        } else {
+            reduce_small16(x, m);  // NARROW < 512 p, MID < 4p, WIDE < 2p
+        }
+    }
     store_smem<LOGN, LB, C>(x, sm, tau);
 }
 template <int LOGN, int CLS>
@@ -200,6 +209,7 @@ __global__ void __launch_bounds__((1 << LOGN) / 16, (1024 / ((1 << LOGN) / 16)))
         m.tw_s = smem_u32(tw_cache);
         m.slot = &S;
         m.scale_mode = INVERSE ? scale_mode : -1;
+        m.partial = INVERSE && (flags & 16) != 0;
         if (new_slot) {
             mbar_wait(bar_tw, phase_tw);
             phase_tw ^= 1;
@@ -256,7 +266,7 @@ static void build_row_list(const Context &ctx, const NttRowMap &map, bool invers
             const int i = rl.count++;
             rl.row[i] = (unsigned short)r;
             rl.slot[i] = (unsigned char)slot;
-            rl.src_row[i] = (unsigned char)(map.src_mod && !inverse ? r % map.src_mod : r);
+            rl.src_row[i] = (unsigned short)(map.src_mod && !inverse ? r % map.src_mod : r);
             int flags = cls;
             if (map.src_mod && !inverse) {
                 // inputs are residues mod the source modulus: fine as they are while they stay inside the lazy input
@@ -340,7 +350,127 @@ static cudaError_t launch_logn(const Context &ctx, const NttRowMap &map, const u
     return cudaGetLastError();
 }
 
-bool ntt_fast_supported(const Context &ctx) { return ctx.logn >= kMinLogN && ctx.logn <= kMaxLogN; }
+// ---------------------------------------------------------------------------------------------- N = 2^15
+// A 2^15 row (256 KB) does not fit one CTA's shared memory.  Its first forward stage (pairs i, i + N/2, one twiddle) and
+// last inverse stage are elementwise over the two halves; in between each half is an independent 2^14-point transform
+// that uses the entries (2 + h) 2^s + g of the twiddle table, which context.cu lays out as a table of its own ("virtual
+// slot").  So: forward = split kernel (global memory, also performs the key-switch gather) + the 2^14 kernel over twice
+// as many rows; inverse = the 2^14 kernel with the `partial` flag + merge kernel (N^-1 scaling).
+struct SplitRows {
+    int rows_per_poly, count;
+    unsigned short row[kMaxRowList];
+    unsigned short src_row[kMaxRowList];
+    unsigned char slot[kMaxRowList], reduce_in[kMaxRowList];
+    long long src_poly_stride;
+};
+__global__ void __launch_bounds__(256) ntt_split_forward_kernel(const u64 *__restrict__ in, u64 *__restrict__ out,
+                                                               const ModSlot *__restrict__ slots,
+                                                               const __grid_constant__ SplitRows sr, int polys, int logn) {
+    const int64_t n = (int64_t)1 << logn, half = n >> 1;
+    const int which = blockIdx.y;
+    const int64_t poly = blockIdx.z;
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;  // two adjacent coefficients per thread
+    if (i >= half) return;
+    const ModSlot &S = slots[sr.slot[which]];
+    const u64 p = S.p;
+    const ulonglong2 w = S.tw[1];
+    const u64 *src = in + poly * sr.src_poly_stride + ((int64_t)sr.src_row[which] << logn) + i;
+    u64 *dst = out + (((poly * sr.rows_per_poly) + sr.row[which]) << logn) + i;
+    ulonglong2 x = *reinterpret_cast<const ulonglong2 *>(src), y = *reinterpret_cast<const ulonglong2 *>(src + half);
+    if (sr.reduce_in[which]) {  // gathered key-switch digit: residues of another modulus (Bfv+Keys.swift:168-172)
+        x.x = barrett64(x.x, p, S.mu1), x.y = barrett64(x.y, p, S.mu1);
+        y.x = barrett64(y.x, p, S.mu1), y.y = barrett64(y.y, p, S.mu1);
+    }
+    const u64 v0 = shoup_mul(y.x, w.x, w.y, p), v1 = shoup_mul(y.y, w.x, w.y, p);
+    *reinterpret_cast<ulonglong2 *>(dst) = make_ulonglong2(add_mod(x.x, v0, p), add_mod(x.y, v1, p));
+    *reinterpret_cast<ulonglong2 *>(dst + half) = make_ulonglong2(sub_mod(x.x, v0, p), sub_mod(x.y, v1, p));
+}
+__global__ void __launch_bounds__(256) ntt_merge_inverse_kernel(u64 *__restrict__ data, const ModSlot *__restrict__ slots,
+                                                               const __grid_constant__ SplitRows sr, int polys, int logn,
+                                                               int scale_mode) {
+    const int64_t n = (int64_t)1 << logn, half = n >> 1;
+    const int which = blockIdx.y;
+    const int64_t poly = blockIdx.z;
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+    if (i >= half) return;
+    const ModSlot &S = slots[sr.slot[which]];
+    const u64 p = S.p;
+    const ModSlot::InvScale sc = S.inv_scale[scale_mode];
+    u64 *row = data + (((poly * sr.rows_per_poly) + sr.row[which]) << logn) + i;
+    const ulonglong2 x = *reinterpret_cast<const ulonglong2 *>(row), y = *reinterpret_cast<const ulonglong2 *>(row + half);
+    // (x + y) N^-1 and (x - y) N^-1 psi^-(N/2), each times the scaling of scale_mode (PolyRq+Ntt.swift:416-419)
+    *reinterpret_cast<ulonglong2 *>(row) =
+        make_ulonglong2(shoup_mul(x.x + y.x, sc.c0, sc.c0p, p), shoup_mul(x.y + y.y, sc.c0, sc.c0p, p));
+    *reinterpret_cast<ulonglong2 *>(row + half) =
+        make_ulonglong2(shoup_mul(x.x - y.x + p, sc.c1, sc.c1p, p), shoup_mul(x.y - y.y + p, sc.c1, sc.c1p, p));
+}
+
+template <bool INVERSE>
+static cudaError_t launch_split(const Context &ctx, const NttRowMap &map, const u64 *in, u64 *out, int64_t rows, int scale_mode,
+                                cudaStream_t stream) {
+    constexpr int LOGN = kMaxLogN;  // the half transforms
+    if (rows % map.rows_per_poly) return cudaErrorInvalidValue;
+    if (rows == 0) return cudaSuccess;
+    if (rows * 2 > 0x7fffffffLL || 2 * map.rows_per_poly > kMaxRowList) return cudaErrorInvalidValue;
+    const int polys = (int)(rows / map.rows_per_poly);
+    RowList full;
+    build_row_list(ctx, map, INVERSE, full);
+    SplitRows sr;
+    sr.rows_per_poly = full.rows_per_poly;
+    sr.count = full.count;
+    sr.src_poly_stride = full.src_poly_stride;
+    RowList rl;  // the half rows: row 2r + h of a polynomial with twice as many rows, on the virtual slot of (slot, h)
+    rl.rows_per_poly = 2 * full.rows_per_poly;
+    rl.count = 2 * full.count;
+    rl.src_poly_stride = (long long)rl.rows_per_poly << LOGN;
+    for (int i = 0; i < full.count; ++i) {
+        sr.row[i] = full.row[i];
+        sr.slot[i] = full.slot[i];
+        sr.src_row[i] = full.src_row[i];
+        // any gathered row is re-reduced here (cheap next to the two transforms), so the halves see canonical residues
+        sr.reduce_in[i] = (unsigned char)((map.src_mod && !INVERSE) ? 1 : 0);
+        for (int hh = 0; hh < 2; ++hh) {
+            const int j = 2 * i + hh;
+            rl.row[j] = (unsigned short)(2 * full.row[i] + hh);
+            rl.src_row[j] = rl.row[j];  // the half transforms run in place: source row = the row itself
+            rl.slot[j] = (unsigned char)(ctx.split_slot_base + 2 * full.slot[i] + hh);
+            rl.flags[j] = (unsigned char)((full.flags[i] & 7) | (INVERSE ? 16 : 0));
+        }
+    }
+    const dim3 egrid((unsigned)((ctx.n / 4 + 255) / 256), (unsigned)full.count, (unsigned)polys);
+    if (!INVERSE) {
+        ++g_kernel_launches;
+        ntt_split_forward_kernel<<<egrid, 256, 0, stream>>>(in, out, ctx.d_slots, sr, polys, ctx.logn);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        in = out;
+    }
+    // the 2^14 kernel, in place over `out` (forward) / from `in` to `out` (inverse); rows addressed like inverse rows
+    CUtensorMap map_in, map_out;
+    if (!make_line_map(&map_in, in, LOGN) || !make_line_map(&map_out, out, LOGN)) return cudaErrorInvalidValue;
+    {
+        constexpr int threads = (1 << LOGN) / 16;
+        constexpr size_t smem = ntt_smem_bytes<LOGN>();
+        auto k = ntt_rows_kernel<LOGN, INVERSE>;
+        cudaError_t e;
+        if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        int per_sm = 0;
+        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, threads, smem)) != cudaSuccess) return e;
+        if (per_sm < 1) return cudaErrorInvalidConfiguration;
+        const int64_t grid = std::min<int64_t>(2 * rows, (int64_t)ctx.sm_count * per_sm);
+        ++g_kernel_launches;
+        k<<<(unsigned)grid, threads, smem, stream>>>(map_in, map_out, ctx.d_slots, rl, polys, scale_mode, 0);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    }
+    if (INVERSE) {
+        ++g_kernel_launches;
+        ntt_merge_inverse_kernel<<<egrid, 256, 0, stream>>>(out, ctx.d_slots, sr, polys, ctx.logn, scale_mode);
+        return cudaGetLastError();
+    }
+    return cudaSuccess;
+}
+
+bool ntt_fast_supported(const Context &ctx) { return ctx.logn >= kMinLogN && ctx.logn <= kSplitLogN; }
 
 template <bool INVERSE>
 static cudaError_t launch_fast(const Context &ctx, const NttRowMap &map, const u64 *in, u64 *out, int64_t rows,
@@ -351,6 +481,7 @@ static cudaError_t launch_fast(const Context &ctx, const NttRowMap &map, const u
         case 12: return launch_logn<12, INVERSE>(ctx, map, in, out, rows, scale_mode, stream);
         case 13: return launch_logn<13, INVERSE>(ctx, map, in, out, rows, scale_mode, stream);
         case 14: return launch_logn<14, INVERSE>(ctx, map, in, out, rows, scale_mode, stream);
+        case 15: return launch_split<INVERSE>(ctx, map, in, out, rows, scale_mode, stream);
         default: return cudaErrorInvalidValue;
     }
 }

@@ -53,6 +53,7 @@ namespace hecuda {
 namespace fast {
 
 constexpr int kMinLogN = 10, kMaxLogN = 14;
+constexpr int kSplitLogN = 15;  // one cross-half stage in global memory + two kMaxLogN transforms (ntt_fast.cu)
 constexpr int kNarrowBits = 55;  // reduction-free butterflies: lazy values < 512 p < 2^64
 constexpr int kMidBits = 61;     // 8 p < 2^64
 constexpr int kSmallBits = 30;   // Modulus<UInt32>.max = 2^30 - 1: the reference's 32-bit word size (Modulus.swift:177-180)
@@ -199,6 +200,8 @@ struct RowMod {
     unsigned tw_s;           // device: shared-memory address of the CTA's copy of tw[0 .. N/16) (the LB > 0 passes)
     const ModSlot *slot;     // p, mu1, red_shift, red_recip, inv_scale[scale_mode], tw_t / itw_t
     int scale_mode;          // < 0: forward transform
+    bool partial;            // inverse only: this row is one half of a 2^15 transform -- its last stage is an ordinary
+                             // butterfly (twiddle entry 1 of its table) and the N^-1 scaling happens in the merge kernel
     // transposed copy of the twiddles for the LB == 0 pass: entry k of thread tau at [k * T + tau]
     HE_HD const ulonglong2 *tw_t() const { return scale_mode < 0 ? slot->tw_t : slot->itw_t; }
 };
@@ -473,7 +476,7 @@ HE_HD void inv_stage(u64 (&x)[16], const int tau, const RowMod &m) {
     const ulonglong2 *tw_t = LB == 0 ? m.tw_t() + tau : nullptr;
 #pragma unroll
     for (int grp = 0; grp < (1 << (C - 1 - J)); ++grp) {
-        if (!kLast) {
+        if (!kLast || m.partial) {
             // LB == 0: entry index inside the thread's 15 = (groups of the earlier stages) + grp
             const ulonglong2 w = LB == 0 ? ld_tw(tw_t + (16 - (16 >> J) + grp) * T)
                                          : ld_tw_cached(m, kGroups + (hi << (C - 1 - J)) + grp);

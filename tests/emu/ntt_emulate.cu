@@ -127,6 +127,7 @@ int main(int argc, char **argv) {
     slot.itw_t = itr.data();
     m.slot = &slot;
     m.scale_mode = inverse ? 0 : -1;
+    m.partial = false;
 #define RUN(L) case L: if (cls == kNarrowH) run<L, kNarrowH>(inverse, in.data(), out.data(), m); else if (cls == kNarrow) run<L, kNarrow>(inverse, in.data(), out.data(), m); else if (cls == kSmall) run<L, kSmall>(inverse, in.data(), out.data(), m); else if (cls == kMid) run<L, kMid>(inverse, in.data(), out.data(), m); else run<L, kWide>(inverse, in.data(), out.data(), m); break;
     switch (logn) { RUN(10) RUN(11) RUN(12) RUN(13) RUN(14) default: return 4; }
     for (int i = 0; i < n; ++i) printf("%llu\n", out[i]);
