@@ -19,7 +19,7 @@ typedef unsigned __int128 u128;
 typedef uint64_t u64;
 typedef int64_t i64;
 
-#define ORC_MAX_MODULI 40
+#define ORC_MAX_MODULI 80 /* 32 coefficient moduli (EncryptionParameters.swift:148) + Bsk + m~ */
 
 /* =====================================================================================
  * Scalar arithmetic -- Sources/ModularArithmetic/Scalar.swift, Modulus.swift

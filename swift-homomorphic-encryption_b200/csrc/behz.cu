@@ -250,6 +250,72 @@ __global__ void __launch_bounds__(kThreads) floor_kernel(const u64 *__restrict__
     for (int i = 0; i < L; ++i) stc<COLS>(dst + (int64_t)i * n, outv[i]);
 }
 
+// ---- more than 16 ciphertext moduli (the reference allows 32 coefficient moduli, EncryptionParameters.swift:148): the
+// same arithmetic with run-time loop bounds, one column per thread, the per-modulus temporaries in local memory.  Such
+// parameter sets are rare and slow on every platform; this keeps them correct rather than fast.
+__global__ void __launch_bounds__(kThreads) lift_generic_kernel(const u64 *__restrict__ in, int polys_in, u64 *__restrict__ ext,
+                                                               int ext_polys, int out_poly_offset,
+                                                               const __grid_constant__ LiftConsts c, int n) {
+    const int L = c.L, R = 2 * L + 1;
+    const int coeff = blockIdx.x * kThreads + threadIdx.x;
+    if (coeff >= n) return;
+    const int64_t poly = (int64_t)blockIdx.z * gridDim.y + blockIdx.y;
+    const int64_t item = poly / polys_in;
+    const int pin = (int)(poly - item * polys_in);
+    const u64 *src = in + poly * L * n + coeff;
+    u64 *dst = ext + ((item * ext_polys + out_poly_offset + pin) * R) * n + coeff;
+    u64 z[kMaxL];
+    u32 acc_mt = 0;
+    for (int i = 0; i < L; ++i) {
+        const u64 x = src[(int64_t)i * n];
+        dst[(int64_t)i * n] = x;
+        z[i] = shoup_mul(x, c.in_w[i], c.in_wp[i], c.q[i]);
+        acc_mt += (u32)z[i] * c.punct_mt[i];
+    }
+    const u32 r = (acc_mt * c.neg_inv_q_mt) & c.mt_mask;
+    const bool neg = r >= c.mt_half;
+    for (int j = 0; j <= L; ++j) {
+        const u64 rc = neg ? (u64)r + c.neg_off[j] : (u64)r;
+        u128 acc = (u128)rc * c.qr[j];
+        for (int i = 0; i < L; ++i) mac128(acc, z[i], c.mat[j][i]);
+        const u64 red = mont_reduce(acc, c.b[j], c.b_ninv[j]);
+        dst[(int64_t)(L + j) * n] = c.wide_sums ? barrett64(red, c.b[j], c.b_mu1[j]) : csub(red, c.b[j]);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) floor_generic_kernel(const u64 *__restrict__ in, u64 *__restrict__ out,
+                                                                const __grid_constant__ FloorConsts c, int n) {
+    const int L = c.L, R = 2 * L + 1;
+    const int coeff = blockIdx.x * kThreads + threadIdx.x;
+    if (coeff >= n) return;
+    const int64_t poly = (int64_t)blockIdx.z * gridDim.y + blockIdx.y;
+    const u64 *src = in + poly * R * n + coeff;
+    u64 *dst = out + poly * L * n + coeff;
+    u64 y[kMaxL], f[kMaxL + 1], w[kMaxL];
+    for (int i = 0; i < L; ++i) y[i] = shoup_mul(src[(int64_t)i * n], c.inq_w[i], c.inq_wp[i], c.q[i]);
+    for (int j = 0; j <= L; ++j) {
+        u128 acc = (u128)src[(int64_t)(L + j) * n] * c.fq[j];
+        for (int i = 0; i < L; ++i) mac128(acc, y[i], c.fmat[j][i]);
+        f[j] = mont_reduce(acc, c.b[j], c.b_ninv[j]);
+    }
+    const u64 msk = c.b[L];
+    u128 acc = (u128)f[L] * c.a_msk;
+    for (int i = 0; i < L; ++i) {
+        w[i] = shoup_mul(f[i], c.inb_w[i], c.inb_wp[i], c.b[i]);
+        mac128(acc, w[i], c.amat[i]);
+    }
+    u64 alpha = mont_reduce(acc, msk, c.b_ninv[L]);
+    alpha = c.wide_sums ? barrett64(alpha, msk, c.msk_mu1) : csub(csub(csub(alpha, 4 * msk), 2 * msk), msk);
+    const bool exceeds = alpha > (msk >> 1);
+    const u64 alpha_c = exceeds ? msk - alpha : alpha;
+    for (int i = 0; i < L; ++i) {
+        u128 o = (u128)alpha_c * (exceeds ? c.b_mod_q[i] : c.neg_b_mod_q[i]);
+        for (int kk = 0; kk < L; ++kk) mac128(o, w[kk], c.omat[i][kk]);
+        // (L + 1) b q / 2^64 may exceed 3q with this many moduli: finish with a Barrett reduction
+        dst[(int64_t)i * n] = barrett64(mont_reduce(o, c.q[i], c.q_ninv[i]), c.q[i], c.q_mu1[i]);
+    }
+}
+
 #define HE_DISPATCH_L(L_, CALL)                                                                                       \
     switch (L_) {                                                                                                     \
         case 1: { constexpr int LL = 1; CALL; } break;                                                                \
@@ -287,10 +353,12 @@ cudaError_t launch_lift(const Context &ctx, const u64 *in, int polys_in, u64 *ex
     // the z dimension must divide exactly: launch in slabs of y = 32768 polys, then the remainder
     while (polys > 0) {
         int64_t slab = polys >= 32768 ? (polys / 32768) * 32768 : polys;
-        const int cols = ctx.n >= 2 ? cols_per_thread() : 1;
+        const int cols = ctx.L > 16 ? 1 : (ctx.n >= 2 ? cols_per_thread() : 1);
         const dim3 grid = poly_grid(ctx.n, slab, cols);
         ++g_kernel_launches;
-        if (cols == 2) {
+        if (ctx.L > 16) {
+            lift_generic_kernel<<<grid, kThreads, 0, stream>>>(in, polys_in, ext, ext_polys, out_poly_offset, consts, (int)ctx.n);
+        } else if (cols == 2) {
             HE_DISPATCH_L(ctx.L, (lift_kernel<LL, 2><<<grid, kThreads, 0, stream>>>(in, polys_in, ext, ext_polys,
                                                                                  out_poly_offset, consts, (int)ctx.n)));
         } else {
@@ -372,10 +440,12 @@ cudaError_t launch_floor(const Context &ctx, const u64 *in, u64 *out, int64_t po
     const int R = 2 * ctx.L + 1;
     while (polys > 0) {
         int64_t slab = polys >= 32768 ? (polys / 32768) * 32768 : polys;
-        const int cols = ctx.n >= 2 ? cols_per_thread() : 1;
+        const int cols = ctx.L > 16 ? 1 : (ctx.n >= 2 ? cols_per_thread() : 1);
         const dim3 grid = poly_grid(ctx.n, slab, cols);
         ++g_kernel_launches;
-        if (cols == 2) {
+        if (ctx.L > 16) {
+            floor_generic_kernel<<<grid, kThreads, 0, stream>>>(in, out, consts, (int)ctx.n);
+        } else if (cols == 2) {
             HE_DISPATCH_L(ctx.L, (floor_kernel<LL, 2><<<grid, kThreads, 0, stream>>>(in, out, consts, (int)ctx.n)));
         } else {
             HE_DISPATCH_L(ctx.L, (floor_kernel<LL, 1><<<grid, kThreads, 0, stream>>>(in, out, consts, (int)ctx.n)));

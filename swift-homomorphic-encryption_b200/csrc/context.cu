@@ -105,7 +105,7 @@ Context *Context::create(int64_t n, const u64 *coeff_moduli, int nmod, u64 t, st
     // plus two 2^14 transforms (ntt_fast.cu)
     if (n > (1 << fast::kSplitLogN)) { err = "unsupportedHeOperation: polynomial degrees above 2^" + std::to_string(fast::kSplitLogN) + " are not supported by the NTT kernels"; return nullptr; }
     if (nmod < 1) { err = "invalidEncryptionParameters: need at least one coefficient modulus"; return nullptr; }
-    if (nmod - 1 > kMaxL) { err = "unsupportedHeOperation: more than " + std::to_string(kMaxL) + " ciphertext moduli"; return nullptr; }
+    if (nmod > kMaxL) { err = "invalidEncryptionParameters: more than " + std::to_string(kMaxL) + " coefficient moduli (EncryptionParameters.swift:148)"; return nullptr; }
     if (t < 2) { err = "invalidEncryptionParameters: plaintext modulus"; return nullptr; }
     for (int i = 0; i < nmod; ++i)
         for (int j = 0; j < i; ++j)
@@ -300,6 +300,7 @@ Context *Context::create(int64_t n, const u64 *coeff_moduli, int nmod, u64 t, st
         const u64 qi = Q[i];
         fl.q[i] = qi;
         fl.q_ninv[i] = c->slots[c->slot_q(i)].dev.ninv;
+        fl.q_mu1[i] = c->slots[c->slot_q(i)].dev.mu1;
         const u64 r64 = c->slots[c->slot_q(i)].dev.r64;
         fl.inq_w[i] = invmod(punctured_mod(Q, L, i, qi), qi);
         fl.inq_wp[i] = shoup_factor(fl.inq_w[i], qi);
@@ -353,6 +354,16 @@ Context *Context::create(int64_t n, const u64 *coeff_moduli, int nmod, u64 t, st
         err = "unsupportedHeOperation: " + std::to_string(L) + " ciphertext moduli of this size overflow the 128-bit lazy sums";
         delete c;
         return nullptr;
+    }
+
+    {   // key switching accumulates l products of two residues in 128 bits (keyswitch.cu)
+        u64 mmax = c->q_ks;
+        for (u64 v : c->q) mmax = v > mmax ? v : mmax;
+        if (std::log2((double)L) + 2 * std::log2((double)mmax) >= 128.0) {
+            err = "unsupportedHeOperation: " + std::to_string(L) + " moduli of this size overflow the key-switching accumulator";
+            delete c;
+            return nullptr;
+        }
     }
 
     // ---- divide-and-round constants

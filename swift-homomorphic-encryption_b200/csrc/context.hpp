@@ -14,7 +14,7 @@
 
 namespace hecuda {
 
-constexpr int kMaxL = 16;               // ciphertext moduli supported by the kernels
+constexpr int kMaxL = 32;               // coefficient moduli: the reference allows 32 (EncryptionParameters.swift:148)
 constexpr int kMaxSlots = 3 * kMaxL + 3;  // q_0..q_{L-1} | bsk_0..bsk_L | q_ks | aux_0..aux_L
 constexpr int kMaxRows = 2 * kMaxL + 1;
 
@@ -85,7 +85,7 @@ struct FloorConsts {
     int L;
     int wide_sums;                     // alpha may exceed 8 m_sk: finish with a Barrett reduction
     u64 msk_mu1;                       // floor(2^64 / m_sk)
-    u64 q[kMaxL], q_ninv[kMaxL];
+    u64 q[kMaxL], q_ninv[kMaxL], q_mu1[kMaxL];
     u64 inq_w[kMaxL], inq_wp[kMaxL];   // (Q/q_i)^-1 mod q_i
     u64 b[kMaxL + 1], b_ninv[kMaxL + 1];
     u64 fq[kMaxL + 1];                 // Q^-1 2^64 mod b_j

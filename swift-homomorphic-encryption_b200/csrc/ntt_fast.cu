@@ -29,7 +29,7 @@ struct RowList {          // rows (within a polynomial) that one launch handles
     int rows_per_poly;
     int count;
     unsigned short row[kMaxRowList];
-    unsigned char slot[kMaxRowList];
+    unsigned short slot[kMaxRowList];  // (virtual slots of N = 2^15 exceed a byte at 32 moduli)
     // 3 bits class | bit 3: re-reduce the gathered input into this row's modulus (forward only) | bit 4: half of a
     // 2^15 row (inverse only: no N^-1 scaling)
     unsigned char flags[kMaxRowList];
@@ -265,7 +265,7 @@ static void build_row_list(const Context &ctx, const NttRowMap &map, bool invers
             if (class_of_modulus(ctx.slots[slot].dev.p, ctx.slots[slot].dev.bits) != cls) continue;
             const int i = rl.count++;
             rl.row[i] = (unsigned short)r;
-            rl.slot[i] = (unsigned char)slot;
+            rl.slot[i] = (unsigned short)slot;
             rl.src_row[i] = (unsigned short)(map.src_mod && !inverse ? r % map.src_mod : r);
             int flags = cls;
             if (map.src_mod && !inverse) {
@@ -359,8 +359,8 @@ static cudaError_t launch_logn(const Context &ctx, const NttRowMap &map, const u
 struct SplitRows {
     int rows_per_poly, count;
     unsigned short row[kMaxRowList];
-    unsigned short src_row[kMaxRowList];
-    unsigned char slot[kMaxRowList], reduce_in[kMaxRowList];
+    unsigned short src_row[kMaxRowList], slot[kMaxRowList];
+    unsigned char reduce_in[kMaxRowList];
     long long src_poly_stride;
 };
 __global__ void __launch_bounds__(256) ntt_split_forward_kernel(const u64 *__restrict__ in, u64 *__restrict__ out,
@@ -433,7 +433,7 @@ static cudaError_t launch_split(const Context &ctx, const NttRowMap &map, const 
             const int j = 2 * i + hh;
             rl.row[j] = (unsigned short)(2 * full.row[i] + hh);
             rl.src_row[j] = rl.row[j];  // the half transforms run in place: source row = the row itself
-            rl.slot[j] = (unsigned char)(ctx.split_slot_base + 2 * full.slot[i] + hh);
+            rl.slot[j] = (unsigned short)(ctx.split_slot_base + 2 * full.slot[i] + hh);
             rl.flags[j] = (unsigned char)((full.flags[i] & 7) | (INVERSE ? 16 : 0));
         }
     }
