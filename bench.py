@@ -484,8 +484,10 @@ def run_mul(h, name):
     peak, _ = hbm_peak()
     R = 2 * L + 1
     # the dominant kernel: forward NTT over the extended base the multiply computes in (28 of its 49 NTTs), timed
-    # alone at the launch shape of one pipeline stage of the host path
-    roofline = ntt_roofline(h, ctx, hecuda.BASE_Q_AUX, R, min(batch, 64) * 4, n,
+    # alone at the launch shape it has inside the timed step (the device path works in chunks of ~2 GB of scratch:
+    # capi.cu, hecuda_context_create)
+    device_chunk = max(1, min(4096, (2048 * 1024 * 1024) // (7 * R * n * 8)))
+    roofline = ntt_roofline(h, ctx, hecuda.BASE_Q_AUX, R, min(batch, device_chunk) * 4, n,
                             f"ntt_rows_kernel<{n.bit_length() - 1}, forward> over [Q, aux] ({R} "
                             f"{'SMALL (32-bit butterfly)' if word32 else 'NARROW'} rows per polynomial)",
                             None if word32 else "ntt_forward_dram_bytes_per_row_narrow")

@@ -155,9 +155,11 @@ Context *Context::create(int64_t n, const u64 *coeff_moduli, int nmod, u64 t, st
         for (u64 v : c->q) log_q += std::log2((double)v);
         const double log_n = (double)c->logn, log_t = std::log2((double)t);
         for (int wi = 0; wi < 2 && want_fast && c->aux == c->bsk && word_bits == 64; ++wi) {
-            // 55-bit width: primes h 2^32 + 1 just above 2^54 (1 mod 2N for every supported N; the NTT's NARROW-H class)
-            std::vector<u64> cand = widths[wi] == 55 ? smallest_ntt_primes(55, L + 1 + nmod, 1ull << 31)
-                                                     : smallest_ntt_primes(widths[wi], L + 1 + nmod, (u64)n);
+            // (primes h 2^32 + 1 -- the NTT's NARROW-H class, -DHE_NTT_NARROW_H -- were measured here too: a wash, see
+            //  ntt_fast.cuh; the plain smallest primes stay)
+            const bool h_primes = fast::kNarrowHEnabled && std::getenv("HECUDA_AUX_H_PRIMES") != nullptr;
+            std::vector<u64> cand = (widths[wi] == 55 && h_primes) ? smallest_ntt_primes(55, L + 1 + nmod, 1ull << 31)
+                                                                   : smallest_ntt_primes(widths[wi], L + 1 + nmod, (u64)n);
             std::vector<u64> pick;
             for (u64 v : cand) {
                 bool used = false;

@@ -220,14 +220,14 @@ __global__ void __launch_bounds__((1 << LOGN) / 16, (1024 / ((1 << LOGN) / 16)))
         } else
 #ifndef HE_EXPERIMENT_ONLY_CLASS
         if (INVERSE) {
-            if (cls == kNarrowH) inv_row<LOGN, kNarrowH>(sm, tau, m);
+            if (kNarrowHEnabled && cls == kNarrowH) inv_row<LOGN, kNarrowHEnabled ? kNarrowH : kNarrow>(sm, tau, m);
             else if (cls == kNarrow) inv_row<LOGN, kNarrow>(sm, tau, m);
             else if (cls == kSmall) inv_row<LOGN, kSmall>(sm, tau, m);
             else if (cls == kMid) inv_row<LOGN, kMid>(sm, tau, m);
             else inv_row<LOGN, kWide>(sm, tau, m);
         } else {
             const bool reduce_in = (flags & 8) != 0;
-            if (cls == kNarrowH) fwd_row<LOGN, kNarrowH>(sm, tau, m, reduce_in);
+            if (kNarrowHEnabled && cls == kNarrowH) fwd_row<LOGN, kNarrowHEnabled ? kNarrowH : kNarrow>(sm, tau, m, reduce_in);
             else if (cls == kNarrow) fwd_row<LOGN, kNarrow>(sm, tau, m, reduce_in);
             else if (cls == kSmall) fwd_row<LOGN, kSmall>(sm, tau, m, reduce_in);
             else if (cls == kMid) fwd_row<LOGN, kMid>(sm, tau, m, reduce_in);

@@ -63,8 +63,15 @@ HE_HD constexpr int class_of_bits(int bits) {
 }
 // NARROW primes of the form h 2^32 + 1 (the auxiliary primes context.cu picks for the multiply): the q p product of a
 // Shoup multiplication collapses to q + ((q0 h) << 32)
+// Compiled in only with -DHE_NTT_NARROW_H: a fifth instruction stream in the kernel cost the NARROW rows 3.5 %
+// (measured), which is what the NARROW-H rows of the multiply's auxiliary base gained.
+#if defined(HE_NTT_NARROW_H)
+constexpr bool kNarrowHEnabled = true;
+#else
+constexpr bool kNarrowHEnabled = false;
+#endif
 HE_HD constexpr int class_of_modulus(u64 p, int bits) {
-    return (class_of_bits(bits) == kNarrow && (u32)p == 1u) ? kNarrowH : class_of_bits(bits);
+    return (kNarrowHEnabled && class_of_bits(bits) == kNarrow && (u32)p == 1u) ? kNarrowH : class_of_bits(bits);
 }
 HE_HD constexpr bool narrow_like(int cls) { return cls == kNarrow || cls == kNarrowH; }
 
