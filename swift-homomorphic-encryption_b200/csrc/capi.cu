@@ -780,8 +780,8 @@ int32_t hecuda_evk_set_galois_key(hecuda_evk *k, uint32_t element, const uint64_
         it->second = d;
     } else {
         k->galois[element] = d;
-        ++k->version;
     }
+    ++k->version;  // captured pipelines (pir.cu) bake the key pointers in: they are rebuilt on the next call
     return HECUDA_OK;
 }
 

@@ -222,3 +222,71 @@ def test_wire_level_response_matches_oracle_and_decrypts(n, bits, t, entries, en
     assert opir.decrypt_response(o, oparam, [recovered], [index], sk) == [database[index]]
     key.close()
     g.close()
+
+
+def test_captured_response_graph_follows_key_changes_and_concurrent_callers():
+    """The host entry point replays the response pipeline of a (database, key, shape) triple as a CUDA graph
+    (csrc/pir.cu).  Replacing a Galois key must invalidate the capture (its device pointers are baked into the graph);
+    concurrent callers must each get a private instance; results stay bit-exact with the oracle throughout."""
+    import threading
+
+    g, o = contexts(64, [55, 55, 55], 65537)
+    rng = random.Random(9)
+    config = pir.IndexPirConfig(200, 24, 2, 1, True, "hybridCompression", False)
+    param = pir.MulPir.generateParameter(config, g)
+    oparam = opir.generate_parameter(opir.IndexPirConfig(200, 24, 2, 1, True, "hybridCompression", False), o.n, o.t)
+    database = [bytes(rng.randrange(256) for _ in range(24)) for _ in range(200)]
+    server = pir.MulPirServer(param, g, [pir.MulPirServer.process(database, g, param)])
+    odb = opir.process_database(o, oparam, database)
+    elements = param.evaluationKeyConfig.galoisElements
+
+    def check(sk, relin, key, okeys, index, seed):
+        query = opir.generate_query(o, oparam, [index], sk, seed)
+        expected = opir.compute_response(o, query, 1, okeys, relin, [odb], oparam)
+        got = server.computeResponse(np.stack(query), key, indicesCount=1)
+        for chunk in range(server.chunkCount):
+            assert np.array_equal(got[0, chunk], expected[0][chunk])
+        reply = [[got[0, c] for c in range(server.chunkCount)]]
+        assert opir.decrypt_response(o, oparam, reply, [index], sk) == [database[index]]
+
+    sk, relin = o.keygen(41)
+    key, okeys = load_keys(g, o, sk, relin, elements, seed=700)
+    for trial in range(3):  # first call captures, the next ones replay
+        check(sk, relin, key, okeys, rng.randrange(200), 900 + trial)
+    # a second client's secret key: new relinearization key object, and the FIRST key's Galois keys replaced in place
+    sk2, relin2 = o.keygen(43)
+    key2, okeys2 = load_keys(g, o, sk2, relin2, elements, seed=800)
+    check(sk2, relin2, key2, okeys2, 17, 950)
+    for e in elements:  # replace key material on the original handle: the capture made for it is stale now
+        okeys[e] = o.galois_keygen(990 + e, sk, e)
+        key.setGaloisKey(e, okeys[e])
+    check(sk, relin, key, okeys, 23, 960)
+    # concurrent callers on the same (database, key, shape); the oracle side is computed up front (single-threaded)
+    jobs = []
+    for tid in range(4):
+        for k in range(3):
+            index = (31 * tid + k) % 200
+            query = opir.generate_query(o, oparam, [index], sk2, 1000 + 10 * tid + k)
+            jobs.append((tid, np.stack(query), opir.compute_response(o, query, 1, okeys2, relin2, [odb], oparam)))
+    errors = []
+
+    def worker(tid):
+        try:
+            for t, query, expected in jobs:
+                if t != tid:
+                    continue
+                got = server.computeResponse(query, key2, indicesCount=1)
+                for chunk in range(server.chunkCount):
+                    assert np.array_equal(got[0, chunk], expected[0][chunk])
+        except Exception as exc:  # noqa: BLE001
+            errors.append(exc)
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(4)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors
+    key.close()
+    key2.close()
+    g.close()
