@@ -554,6 +554,24 @@ def run_mul(h, name):
             host_mul()
         torch.cuda.synchronize()
         dt = h.max_over_ranks(time.perf_counter() - t0)
+        if not word32 and "error" not in extra and h.world == 1:
+            # the fused call a server would make: multiply + relinearize + modSwitchDown, only 2 x (L-1) rows come back
+            try:
+                kh = h.uniform((L, 2, L + 1, n), moduli).cpu().numpy().view(np.uint64)
+                evk2 = hecuda.EvaluationKey(ctx, kh)
+                hf = hecuda.PinnedBuffer((batch, 2, L - 1, n))
+                hecuda.Bfv.mulRelinearize(ctx, hl.array, hr.array, evk2, modSwitchDown=True, out=hf.array)
+                f0 = time.perf_counter()
+                for _ in range(steps):
+                    hecuda.Bfv.mulRelinearize(ctx, hl.array, hr.array, evk2, modSwitchDown=True, out=hf.array)
+                fdt = time.perf_counter() - f0
+                extra["e2e_multiply_relinearize_modswitch"] = {
+                    "value": batch * steps / fdt, "unit": "ciphertexts/s", "h2d_bytes_per_step": int(hl.array.nbytes + hr.array.nbytes),
+                    "d2h_bytes_per_step": int(hf.array.nbytes), "call": "hecuda_bfv_multiply_relinearize(mod_switch = 1)"}
+                hf.free()
+                evk2.close()
+            except Exception as exc:  # noqa: BLE001
+                extra["e2e_multiply_relinearize_modswitch"] = {"error": repr(exc)}
         e2e = {"value": h.world * batch * steps / dt, "unit": "mult/s",
                "h2d_bytes_per_step": int(hl.array.nbytes + hr.array.nbytes), "d2h_bytes_per_step": int(ho.array.nbytes),
                "steps": steps, "timer": "host wall clock around blocking C-ABI calls, max over ranks",

@@ -163,6 +163,16 @@ int32_t hecuda_bfv_relinearize(const hecuda_context *ctx, const hecuda_evk *evk,
 int32_t hecuda_bfv_relinearize_device(const hecuda_context *ctx, const hecuda_evk *evk, const uint64_t *ct3,
                                       int32_t moduli_count, uint64_t *out, int64_t batch, void *stream);
 
+/* Bfv.mulAssign, Bfv.relinearize and (mod_switch != 0) Bfv.modSwitchDown in one pass over a batch -- the sequence the
+ * reference's callers run back to back (RlweBenchmark.swift:387-493; PirUtil.swift:447-480).  The three-polynomial
+ * product never leaves the device: lhs, rhs: batch x 2 x L x N (Coeff, top level); out: batch x 2 x L x N, or
+ * batch x 2 x (L-1) x N with the modulus switch.  Same residues as the three separate calls. */
+int32_t hecuda_bfv_multiply_relinearize(const hecuda_context *ctx, const hecuda_evk *evk, const uint64_t *lhs,
+                                        const uint64_t *rhs, int32_t mod_switch, uint64_t *out, int64_t batch);
+int32_t hecuda_bfv_multiply_relinearize_device(const hecuda_context *ctx, const hecuda_evk *evk, const uint64_t *lhs,
+                                               const uint64_t *rhs, int32_t mod_switch, uint64_t *out, int64_t batch,
+                                               void *stream);
+
 /* Bfv.modSwitchDown(_:) -- Bfv/Bfv.swift:163-171 (PolyRq.divideAndRoundQLast, PolyRq.swift:365-393).
  * ct: batch x poly_count x l x N (Coeff), l = moduli_count in [2, L]; out: batch x poly_count x (l-1) x N. */
 int32_t hecuda_bfv_mod_switch_down(const hecuda_context *ctx, const uint64_t *ct, int32_t poly_count,

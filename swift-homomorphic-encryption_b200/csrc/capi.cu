@@ -753,6 +753,74 @@ int32_t hecuda_bfv_mod_switch_down(const hecuda_context *h, const uint64_t *ct, 
 }
 
 
+// ---------------------------------------------------------------- multiply -> relinearize (-> modSwitchDown), fused
+// The sequence every caller of ct x ct multiply runs (RlweBenchmark.swift:387-493; PirUtil.swift:447-480):
+// Bfv.mulAssign, Bfv.relinearize, optionally Bfv.modSwitchDown, on a batch, in one pass: the three-polynomial product
+// and the relinearized ciphertext stay in HBM and only 2 x L (or 2 x (L-1)) rows per ciphertext come back.
+static size_t mul_relin_scratch_words(const Context &c) {
+    // multiply scratch | 3-poly product | relinearize scratch | relinearized ciphertext (only with the modulus switch)
+    return multiply_scratch_words(c) + (size_t)3 * c.L * c.n + relinearize_scratch_words(c, c.L) + (size_t)2 * c.L * c.n;
+}
+static cudaError_t mul_relin_chunk(const Context &c, u64 *scratch, const u64 *key, const u64 *lhs, const u64 *rhs, bool mod_switch,
+                                   u64 *out, int64_t items, cudaStream_t s) {
+    u64 *mul_scratch = scratch;
+    u64 *prod = mul_scratch + multiply_scratch_words(c) * (size_t)items;
+    u64 *ks_scratch = prod + (size_t)3 * c.L * c.n * items;
+    u64 *relin = ks_scratch + relinearize_scratch_words(c, c.L) * (size_t)items;
+    cudaError_t e;
+    if ((e = multiply_chunk(c, mul_scratch, lhs, rhs, prod, items, s)) != cudaSuccess) return e;
+    if ((e = relinearize_chunk(c, ks_scratch, key, prod, c.L, mod_switch ? relin : out, items, s)) != cudaSuccess) return e;
+    if (mod_switch) return launch_mod_switch(c, relin, c.L, out, items * 2, s);
+    return cudaSuccess;
+}
+static int32_t check_mul_relin(const hecuda_context *h, const hecuda_evk *k, const void *lhs, const void *rhs, const void *out,
+                               int32_t mod_switch, int64_t batch) {
+    int32_t rc = check_ctx(h);
+    if (rc) return rc;
+    if (!k || !k->loaded) return fail(HECUDA_ERR_MISSING_KEY, "missingRelinearizationKey");
+    if (k->owner != h) return fail(HECUDA_ERR_INVALID_ARGUMENT, "invalidContext: evaluation key belongs to another context");
+    if (mod_switch && h->ctx->L < 2)
+        return fail(HECUDA_ERR_INVALID_ARGUMENT, "invalidPolyContext: modSwitchDown needs a next context (L >= 2)");
+    if (batch < 0 || (batch && (!lhs || !rhs || !out))) return fail(HECUDA_ERR_INVALID_ARGUMENT, "invalidCiphertext: null buffer");
+    return HECUDA_OK;
+}
+int32_t hecuda_bfv_multiply_relinearize_device(const hecuda_context *h, const hecuda_evk *k, const uint64_t *lhs,
+                                               const uint64_t *rhs, int32_t mod_switch, uint64_t *out, int64_t batch,
+                                               void *stream) {
+    int32_t rc = check_mul_relin(h, k, lhs, rhs, out, mod_switch, batch);
+    if (rc || batch == 0) return rc;
+    const Context &c = *h->ctx;
+    const size_t in_words = (size_t)2 * c.L * c.n, out_words = (size_t)2 * (c.L - (mod_switch ? 1 : 0)) * c.n;
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(h->chunk / 2, batch));
+    cudaStream_t s = (cudaStream_t)stream;
+    u64 *scratch = nullptr;
+    CK(cudaMallocAsync(&scratch, mul_relin_scratch_words(c) * (size_t)chunk * sizeof(u64), s));
+    for (int64_t done = 0; done < batch; done += chunk) {
+        const int64_t items = std::min<int64_t>(chunk, batch - done);
+        cudaError_t e = mul_relin_chunk(c, scratch, k->d_relin, (const u64 *)lhs + in_words * done, (const u64 *)rhs + in_words * done,
+                                        mod_switch != 0, (u64 *)out + out_words * done, items, s);
+        if (e != cudaSuccess) {
+            cudaFreeAsync(scratch, s);
+            return cuda_fail(e, "multiply_relinearize");
+        }
+    }
+    CK(cudaFreeAsync(scratch, s));
+    return HECUDA_OK;
+}
+int32_t hecuda_bfv_multiply_relinearize(const hecuda_context *h, const hecuda_evk *k, const uint64_t *lhs, const uint64_t *rhs,
+                                        int32_t mod_switch, uint64_t *out, int64_t batch) {
+    int32_t rc = check_mul_relin(h, k, lhs, rhs, out, mod_switch, batch);
+    if (rc) return rc;
+    const Context &c = *h->ctx;
+    const size_t in_words = (size_t)2 * c.L * c.n, out_words = (size_t)2 * (c.L - (mod_switch ? 1 : 0)) * c.n;
+    std::vector<HostIo> in = {{(const u64 *)lhs, in_words}, {(const u64 *)rhs, in_words}};
+    return host_pipeline(h, batch, std::max<int64_t>(1, h->chunk / 2), mul_relin_scratch_words(c), in, (u64 *)out, out_words,
+                         [&](Workspace &w, const std::vector<const u64 *> &d_in, u64 *d_out, int64_t items) {
+                             return mul_relin_chunk(c, w.buf[0], k->d_relin, d_in[0], d_in[1], mod_switch != 0, d_out, items,
+                                                    w.stream);
+                         });
+}
+
 // ---------------------------------------------------------------- Galois
 
 static bool valid_galois_element(int64_t element, int64_t n) {  // isValidGaloisElement, Galois.swift:100-105

@@ -51,6 +51,8 @@ SYMBOLS = {
     "hecuda_u32_bfv_mod_switch_down": (C.c_int32, [_VP, _VP, C.c_int32, C.c_int32, _VP, C.c_int64]),
     "hecuda_u32_rnstool_lift_q_to_qbsk": (C.c_int32, [_VP, _VP, _VP, C.c_int64]),
     "hecuda_u32_rnstool_floor_qbsk_to_q": (C.c_int32, [_VP, _VP, _VP, C.c_int64]),
+    "hecuda_bfv_multiply_relinearize": (C.c_int32, [_VP, _VP, _VP, _VP, C.c_int32, _VP, C.c_int64]),
+    "hecuda_bfv_multiply_relinearize_device": (C.c_int32, [_VP, _VP, _VP, _VP, C.c_int32, _VP, C.c_int64, _VP]),
     "hecuda_comm_unique_id": (C.c_int32, [_VP]),
     "hecuda_comm_create": (C.c_int32, [_VP, C.c_int32, C.c_int32, C.POINTER(_VP)]),
     "hecuda_comm_destroy": (C.c_int32, [_VP]),
@@ -369,6 +371,23 @@ class Bfv:
         if out is None:
             out = np.empty(a.shape[:-3] + (3, context.L, context.degree), dtype=np.uint64)
         _check(load_library().hecuda_bfv_multiply(context._h, _ptr(a), _ptr(b), _ptr(out), batch))
+        return out
+
+    @staticmethod
+    def mulRelinearize(context: Context, lhs, rhs, key: EvaluationKey, modSwitchDown: bool = False, out=None):
+        """mulAssign + relinearize (+ modSwitchDown) in one pass (hecuda_bfv_multiply_relinearize): (batch, 2, L, N) x2 ->
+        (batch, 2, L, N) or (batch, 2, L-1, N).  Same residues as the separate calls."""
+        a, b = _host(lhs), _host(rhs)
+        L, n = context.L, context.degree
+        if a.shape != b.shape or a.shape[-3:] != (2, L, n):
+            raise HeError(-1, "invalidCiphertext: multiply takes top-level two-polynomial ciphertexts")
+        if key is None:
+            raise HeError(-5, "missingRelinearizationKey")
+        rows = L - 1 if modSwitchDown else L
+        if out is None:
+            out = np.empty(a.shape[:-3] + (2, rows, n), dtype=np.uint64)
+        _check(load_library().hecuda_bfv_multiply_relinearize(context._h, key._h, _ptr(a), _ptr(b), 1 if modSwitchDown else 0,
+                                                              _ptr(out), a.size // (2 * L * n)))
         return out
 
     @staticmethod
