@@ -140,6 +140,104 @@ cudaError_t launch_inner_product_plain(const Context &ctx, const u64 *cts, int n
     return cudaGetLastError();
 }
 
+// ---- the same scan for moduli below 2^31 (the reference's default PIR parameters, 27 / 28 / 28 bits): the database
+// rows are kept as uint32 (half the bytes to stream), a product of two residues fits 62 bits, so one IMAD.WIDE with a
+// 64-bit accumulator replaces the 128-bit multiply-accumulate, reduced (single-word Barrett) every max_terms terms.
+struct IpSmallConsts {
+    int l;
+    int max_terms;
+    u64 p[kMaxL], mu1[kMaxL];
+};
+template <int NPOLY>
+__global__ void __launch_bounds__(128) inner_product_plain_small_kernel(const u64 *__restrict__ cts, const u32 *__restrict__ pts,
+                                                                       const unsigned char *__restrict__ present,
+                                                                       u64 *__restrict__ out,
+                                                                       const __grid_constant__ IpSmallConsts c, int n,
+                                                                       long long terms, long long out_count) {
+    const int coeff = (blockIdx.x * 128 + threadIdx.x) * 4;  // four adjacent coefficients: 16-byte loads of the uint32 rows
+    if (coeff >= n) return;
+    const int r = blockIdx.y, l = c.l;
+    const long long o = blockIdx.z;
+    const u64 p = c.p[r], mu1 = c.mu1[r];
+    u64 acc[NPOLY][4];
+#pragma unroll
+    for (int q = 0; q < NPOLY; ++q) acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0;
+    const long long pt_stride = (long long)l * n, ct_stride = (long long)NPOLY * l * n;
+    const u64 *ct = cts + (long long)r * n + coeff;
+    const u32 *pt = pts + ((o * terms) * l + r) * (long long)n + coeff;
+    const unsigned char *pres = present ? present + o * terms : nullptr;
+    int since_reduce = 0;
+#pragma unroll 2
+    for (long long k = 0; k < terms; ++k) {
+        if (pres && !pres[k]) continue;  // nil plaintext (Bfv.swift:493), uniform across the block
+        const uint4 pv = __ldcs(reinterpret_cast<const uint4 *>(pt + k * pt_stride));
+#pragma unroll
+        for (int q = 0; q < NPOLY; ++q) {
+            const u64 *cq = ct + k * ct_stride + (long long)q * pt_stride;
+            const ulonglong2 c01 = __ldg(reinterpret_cast<const ulonglong2 *>(cq));
+            const ulonglong2 c23 = __ldg(reinterpret_cast<const ulonglong2 *>(cq + 2));
+            acc[q][0] += (u64)(u32)c01.x * pv.x;
+            acc[q][1] += (u64)(u32)c01.y * pv.y;
+            acc[q][2] += (u64)(u32)c23.x * pv.z;
+            acc[q][3] += (u64)(u32)c23.y * pv.w;
+        }
+        if (++since_reduce >= c.max_terms) {  // reduceInPlace, Bfv.swift:365-377
+            since_reduce = 0;
+#pragma unroll
+            for (int q = 0; q < NPOLY; ++q)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[q][j] = barrett64(acc[q][j], p, mu1);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < NPOLY; ++q) {  // reduceToCiphertext, Bfv.swift:380-394
+        u64 *dst = out + (((o * NPOLY + q) * l + r) * (long long)n) + coeff;
+        reinterpret_cast<ulonglong2 *>(dst)[0] = make_ulonglong2(barrett64(acc[q][0], p, mu1), barrett64(acc[q][1], p, mu1));
+        reinterpret_cast<ulonglong2 *>(dst)[1] = make_ulonglong2(barrett64(acc[q][2], p, mu1), barrett64(acc[q][3], p, mu1));
+    }
+}
+
+bool inner_product_plain_small_supported(const Context &ctx, int l) {
+    if (ctx.n < 4) return false;
+    for (int r = 0; r < l; ++r)
+        if (ctx.slots[ctx.slot_q(r)].dev.bits > 31) return false;
+    return true;
+}
+
+cudaError_t launch_inner_product_plain_small(const Context &ctx, const u64 *cts, int npoly, int l, int64_t terms, const u32 *pts,
+                                             const unsigned char *present, u64 *out, int64_t out_count, cudaStream_t stream) {
+    if (out_count == 0) return cudaSuccess;
+    if (npoly < 1 || npoly > 3 || l < 1 || l > ctx.L || !inner_product_plain_small_supported(ctx, l)) return cudaErrorInvalidValue;
+    IpSmallConsts c;
+    c.l = l;
+    u64 qmax = 0;
+    for (int r = 0; r < l; ++r) {
+        const ModSlot &S = ctx.slots[ctx.slot_q(r)].dev;
+        c.p[r] = S.p;
+        c.mu1[r] = S.mu1;
+        qmax = S.p > qmax ? S.p : qmax;
+    }
+    // a reduced accumulator (< p) plus max_terms products (< (p-1)^2 each) must stay below 2^64
+    const u128 room = (~(u128)0 >> 64) - qmax;
+    const u128 max_count = room / ((u128)(qmax - 1) * (qmax - 1));
+    c.max_terms = max_count > 0x7fffffff ? 0x7fffffff : (int)max_count;
+    if (c.max_terms < 1) return cudaErrorInvalidValue;
+    const unsigned gx = (unsigned)((ctx.n / 4 + 127) / 128);
+    for (int64_t done = 0; done < out_count;) {
+        const int64_t chunk = (out_count - done) > 65535 ? 65535 : (out_count - done);
+        dim3 grid(gx ? gx : 1, (unsigned)l, (unsigned)chunk);
+        const u32 *pt = pts + done * terms * l * ctx.n;
+        const unsigned char *pr = present ? present + done * terms : nullptr;
+        u64 *o = out + done * npoly * l * ctx.n;
+        ++g_kernel_launches;
+        if (npoly == 1) inner_product_plain_small_kernel<1><<<grid, 128, 0, stream>>>(cts, pt, pr, o, c, (int)ctx.n, terms, chunk);
+        else if (npoly == 2) inner_product_plain_small_kernel<2><<<grid, 128, 0, stream>>>(cts, pt, pr, o, c, (int)ctx.n, terms, chunk);
+        else inner_product_plain_small_kernel<3><<<grid, 128, 0, stream>>>(cts, pt, pr, o, c, (int)ctx.n, terms, chunk);
+        done += chunk;
+    }
+    return cudaGetLastError();
+}
+
 // Plaintext.convertToEvalFormat, Plaintext.swift:149-171: centered lift mod each q_r (the forward NTT follows)
 __global__ void __launch_bounds__(256) plaintext_lift_kernel(const u64 *__restrict__ plain, u64 *__restrict__ out,
                                                             const __grid_constant__ IpConsts c, u64 t, int n) {

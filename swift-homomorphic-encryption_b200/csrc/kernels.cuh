@@ -66,6 +66,10 @@ cudaError_t launch_galois_eval(const Context &ctx, int rows, unsigned element, c
 // ---- lazy ct x pt inner product and plaintext Eval conversion (innerprod.cu): Bfv.swift:476-505, Plaintext.swift:149-171
 cudaError_t launch_inner_product_plain(const Context &ctx, const u64 *cts, int npoly, int l, int64_t terms, const u64 *pts,
                                        const unsigned char *present, u64 *out, int64_t out_count, cudaStream_t stream);
+// the same scan for moduli below 2^31 with the plaintext rows stored as uint32 (innerprod.cu)
+bool inner_product_plain_small_supported(const Context &ctx, int l);
+cudaError_t launch_inner_product_plain_small(const Context &ctx, const u64 *cts, int npoly, int l, int64_t terms, const u32 *pts,
+                                             const unsigned char *present, u64 *out, int64_t out_count, cudaStream_t stream);
 cudaError_t launch_plaintext_to_eval(const Context &ctx, const u64 *plain, int l, u64 *out, int64_t count,
                                      cudaStream_t stream);
 

@@ -14,6 +14,7 @@
 // Everything is enqueued on one stream; concurrent queries (different clients, different keys) run on different
 // streams from different host threads.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include <set>
@@ -26,6 +27,7 @@ using namespace hecuda::api;
 struct hecuda_pir_database {
     const hecuda_context *owner = nullptr;
     u64 *d_plain = nullptr;              // count x L x N, Eval format; all-zero rows where present == 0
+    u32 *d_plain32 = nullptr;            // the same rows as uint32 instead, when every ciphertext modulus is below 2^31
     unsigned char *d_present = nullptr;  // count
     int64_t count = 0;
 };
@@ -332,8 +334,9 @@ int32_t compute_response_device(const hecuda_context *h, const hecuda_evk *k, co
         // firstDimensionQueries: convertToEvalFormat (:523-532)
         if ((e = launch_ntt_forward(c, map, cts, first_eval, dim0 * 2 * L, s)) != cudaSuccess) return cuda_fail(e, "ntt");
         // every column of every chunk: Scheme.innerProduct(ciphertexts:plaintexts:) then convertToCanonicalFormat (:427-435)
-        if ((e = launch_inner_product_plain(c, first_eval, 2, L, dim0, db->d_plain, db->d_present, results[0], rows, s)) !=
-            cudaSuccess)
+        e = db->d_plain32 ? launch_inner_product_plain_small(c, first_eval, 2, L, dim0, db->d_plain32, db->d_present, results[0], rows, s)
+                          : launch_inner_product_plain(c, first_eval, 2, L, dim0, db->d_plain, db->d_present, results[0], rows, s);
+        if (e != cudaSuccess)
             return cuda_fail(e, "innerProduct(ciphertexts:plaintexts:)");
         if ((e = launch_ntt_inverse(c, map, results[0], results[0], rows * 2 * L, kScalePlain, s)) != cudaSuccess)
             return cuda_fail(e, "ntt");
@@ -586,6 +589,20 @@ int32_t hecuda_pir_database_create(const hecuda_context *h, const uint64_t *plai
             cudaFree(d_coeff);
         }
     }
+    static const bool compact_ok = [] {
+        const char *env = std::getenv("HECUDA_PIR_COMPACT");
+        return !(env && env[0] == '0');
+    }();
+    if (e == cudaSuccess && compact_ok && inner_product_plain_small_supported(c, c.L)) {
+        // small moduli (the default PIR parameters): keep the rows as uint32 -- half the bytes per scan, half the HBM
+        e = cudaMalloc(&db->d_plain32, row_words * count * sizeof(u32));
+        if (e == cudaSuccess) e = launch_narrow(db->d_plain, db->d_plain32, (int64_t)(row_words * count), nullptr);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(nullptr);
+        if (e == cudaSuccess) {
+            cudaFree(db->d_plain);
+            db->d_plain = nullptr;
+        }
+    }
     if (e != cudaSuccess) {
         hecuda_pir_database_destroy(db);
         return cuda_fail(e, "pir database upload");
@@ -598,6 +615,7 @@ int32_t hecuda_pir_database_destroy(hecuda_pir_database *db) {
     if (!db) return HECUDA_OK;
     if (db->owner) pir_graphs_purge(const_cast<hecuda_context *>(db->owner), db);
     if (db->d_plain) cudaFree(db->d_plain);
+    if (db->d_plain32) cudaFree(db->d_plain32);
     if (db->d_present) cudaFree(db->d_present);
     delete db;
     return HECUDA_OK;
@@ -605,8 +623,9 @@ int32_t hecuda_pir_database_destroy(hecuda_pir_database *db) {
 
 int32_t hecuda_pir_database_device_buffer(hecuda_pir_database *db, void **device_ptr, uint64_t *bytes) {
     if (!db || !device_ptr || !bytes) return fail(HECUDA_ERR_INVALID_ARGUMENT, "null argument");
-    *device_ptr = db->d_plain;
-    *bytes = (uint64_t)db->count * db->owner->ctx->L * db->owner->ctx->n * sizeof(u64);
+    // (uint32 rows when every ciphertext modulus is below 2^31: the bytes say which)
+    *device_ptr = db->d_plain32 ? (void *)db->d_plain32 : (void *)db->d_plain;
+    *bytes = (uint64_t)db->count * db->owner->ctx->L * db->owner->ctx->n * (db->d_plain32 ? sizeof(u32) : sizeof(u64));
     return HECUDA_OK;
 }
 

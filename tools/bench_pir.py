@@ -120,7 +120,10 @@ def run(entries=1 << 20, entry_size=64, threads=8, per_thread=30, cpu=True):
         dist.destroy_process_group()
         return None
 
-    db_bytes = count * L * n * 8
+    import ctypes as C
+    ptr, nbytes = C.c_void_p(), C.c_uint64(0)
+    hecuda.load_library().hecuda_pir_database_device_buffer(db._h, C.byref(ptr), C.byref(nbytes))
+    db_bytes = int(nbytes.value) or count * L * n * 8  # uint32 rows for the small default moduli
     out = {
         "metric": "MulPir computeResponse queries/s (index PIR, database resident in HBM)",
         "config": {"workload": f"N={n}, q=27/28/28 bit, t={t}, entries={entries} x {entry_size} B, dims={param.dimensions}, "
