@@ -131,9 +131,8 @@ struct WsGuard {
 
 int32_t check_ctx(const hecuda_context *h);
 
-// Wait for a stream from a host thread.  With many host threads serving queries concurrently, spinning in
-// cudaStreamSynchronize burns a core per waiting thread; HECUDA_BLOCKING_SYNC=1 makes the wait yield the CPU instead
-// (an event created with cudaEventBlockingSync, one per thread).
+// Wait for a stream from a host thread: yields the CPU (an event created with cudaEventBlockingSync, one per thread)
+// unless HECUDA_BLOCKING_SYNC=0 asks for the spinning cudaStreamSynchronize.
 cudaError_t wait_stream(cudaStream_t s);
 bool make_map(const Context &c, int32_t base, int32_t rows, NttRowMap &map, std::string &err);
 
