@@ -163,6 +163,11 @@ int32_t hecuda_bfv_relinearize(const hecuda_context *ctx, const hecuda_evk *evk,
 int32_t hecuda_bfv_relinearize_device(const hecuda_context *ctx, const hecuda_evk *evk, const uint64_t *ct3,
                                       int32_t moduli_count, uint64_t *out, int64_t batch, void *stream);
 
+/* Bfv.relinearize followed by Bfv.modSwitchDown in one pass (host pointers): ct3: batch x 3 x l x N -> out: batch x 2 x
+ * (l-1) x N; the relinearized ciphertext stays on the device.  Same residues as the two separate calls. */
+int32_t hecuda_bfv_relinearize_mod_switch_down(const hecuda_context *ctx, const hecuda_evk *evk, const uint64_t *ct3,
+                                               int32_t moduli_count, uint64_t *out, int64_t batch);
+
 /* Bfv.mulAssign, Bfv.relinearize and (mod_switch != 0) Bfv.modSwitchDown in one pass over a batch -- the sequence the
  * reference's callers run back to back (RlweBenchmark.swift:387-493; PirUtil.swift:447-480).  The three-polynomial
  * product never leaves the device: lhs, rhs: batch x 2 x L x N (Coeff, top level); out: batch x 2 x L x N, or

@@ -757,6 +757,26 @@ int32_t hecuda_bfv_mod_switch_down(const hecuda_context *h, const uint64_t *ct, 
 }
 
 
+// ---------------------------------------------------------------- relinearize -> modSwitchDown, fused
+// Bfv.relinearize then Bfv.modSwitchDown on a batch in one pass (BASELINE config 3): the relinearized ciphertext stays
+// in HBM, 2 x (l-1) rows per ciphertext come back.
+int32_t hecuda_bfv_relinearize_mod_switch_down(const hecuda_context *h, const hecuda_evk *k, const uint64_t *ct3, int32_t l,
+                                               uint64_t *out, int64_t batch) {
+    int32_t rc = check_relin(h, k, ct3, l, out, batch);
+    if (rc) return rc;
+    if (l < 2) return fail(HECUDA_ERR_INVALID_ARGUMENT, "invalidPolyContext: modSwitchDown needs a next context (moduli_count >= 2)");
+    const Context &c = *h->ctx;
+    const size_t relin_words = (size_t)2 * l * c.n;
+    std::vector<HostIo> in = {{(const u64 *)ct3, (size_t)3 * l * c.n}};
+    return host_pipeline(h, batch, h->chunk, relinearize_scratch_words(c, l) + relin_words, in, (u64 *)out, (size_t)2 * (l - 1) * c.n,
+                         [&](Workspace &w, const std::vector<const u64 *> &d_in, u64 *d_out, int64_t items) {
+                             u64 *relin = w.buf[0] + relinearize_scratch_words(c, l) * (size_t)items;
+                             cudaError_t e = relinearize_chunk(c, w.buf[0], k->d_relin, d_in[0], l, relin, items, w.stream);
+                             if (e != cudaSuccess) return e;
+                             return launch_mod_switch(c, relin, l, d_out, items * 2, w.stream);
+                         });
+}
+
 // ---------------------------------------------------------------- multiply -> relinearize (-> modSwitchDown), fused
 // The sequence every caller of ct x ct multiply runs (RlweBenchmark.swift:387-493; PirUtil.swift:447-480):
 // Bfv.mulAssign, Bfv.relinearize, optionally Bfv.modSwitchDown, on a batch, in one pass: the three-polynomial product

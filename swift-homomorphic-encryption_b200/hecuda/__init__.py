@@ -51,6 +51,7 @@ SYMBOLS = {
     "hecuda_u32_bfv_mod_switch_down": (C.c_int32, [_VP, _VP, C.c_int32, C.c_int32, _VP, C.c_int64]),
     "hecuda_u32_rnstool_lift_q_to_qbsk": (C.c_int32, [_VP, _VP, _VP, C.c_int64]),
     "hecuda_u32_rnstool_floor_qbsk_to_q": (C.c_int32, [_VP, _VP, _VP, C.c_int64]),
+    "hecuda_bfv_relinearize_mod_switch_down": (C.c_int32, [_VP, _VP, _VP, C.c_int32, _VP, C.c_int64]),
     "hecuda_bfv_multiply_relinearize": (C.c_int32, [_VP, _VP, _VP, _VP, C.c_int32, _VP, C.c_int64]),
     "hecuda_bfv_multiply_relinearize_device": (C.c_int32, [_VP, _VP, _VP, _VP, C.c_int32, _VP, C.c_int64, _VP]),
     "hecuda_comm_unique_id": (C.c_int32, [_VP]),
@@ -371,6 +372,21 @@ class Bfv:
         if out is None:
             out = np.empty(a.shape[:-3] + (3, context.L, context.degree), dtype=np.uint64)
         _check(load_library().hecuda_bfv_multiply(context._h, _ptr(a), _ptr(b), _ptr(out), batch))
+        return out
+
+    @staticmethod
+    def relinearizeModSwitchDown(context: Context, ciphertext, key: EvaluationKey, out=None):
+        """relinearize + modSwitchDown in one pass (hecuda_bfv_relinearize_mod_switch_down): (batch, 3, l, N) -> (batch, 2, l-1, N)."""
+        c = _host(ciphertext)
+        if c.ndim < 3 or c.shape[-3] != 3 or c.shape[-1] != context.degree:
+            raise HeError(-1, "invalidCiphertext: ciphertext must have three polys when relinearizing")
+        if key is None:
+            raise HeError(-5, "missingRelinearizationKey")
+        l = c.shape[-2]
+        batch = int(np.prod(c.shape[:-3], dtype=np.int64))
+        if out is None:
+            out = np.empty(c.shape[:-3] + (2, l - 1, context.degree), dtype=np.uint64)
+        _check(load_library().hecuda_bfv_relinearize_mod_switch_down(context._h, key._h, _ptr(c), l, _ptr(out), batch))
         return out
 
     @staticmethod
