@@ -542,8 +542,26 @@ PirGraph *acquire_graph(const hecuda_context *hc, const hecuda_evk *k, const hec
         return nullptr;
     }
     g->busy = true;
-    std::lock_guard<std::mutex> lock(h->mu);
-    h->pir_graphs.push_back(g);
+    // bounded cache: every instance pins its scratch (tens of MB); beyond the cap the oldest idle one makes room
+    const char *cap_env = std::getenv("HECUDA_PIR_GRAPH_CACHE");  // (read per build: building a graph is the slow path)
+    const long cap_v = cap_env ? std::atol(cap_env) : 32;
+    const size_t cap = (size_t)(cap_v < 1 ? 1 : cap_v);
+    PirGraph *evicted = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(h->mu);
+        if (h->pir_graphs.size() >= cap)
+            for (size_t i = 0; i < h->pir_graphs.size(); ++i)
+                if (!h->pir_graphs[i]->busy) {
+                    evicted = h->pir_graphs[i];
+                    h->pir_graphs.erase(h->pir_graphs.begin() + (long)i);
+                    break;
+                }
+        h->pir_graphs.push_back(g);
+    }
+    if (evicted) {  // idle: its last replay was waited for by its caller
+        evicted->release();
+        delete evicted;
+    }
     return g;
 }
 void release_graph(const hecuda_context *hc, PirGraph *g) {

@@ -224,6 +224,35 @@ def test_wire_level_response_matches_oracle_and_decrypts(n, bits, t, entries, en
     g.close()
 
 
+def test_captured_response_graph_cache_is_bounded(monkeypatch):
+    """More (database, key) pairs than HECUDA_PIR_GRAPH_CACHE: old idle captures are evicted, answers stay right."""
+    monkeypatch.setenv("HECUDA_PIR_GRAPH_CACHE", "2")
+    g, o = contexts(64, [55, 55, 55], 65537)
+    rng = random.Random(11)
+    config = pir.IndexPirConfig(100, 8, 2, 1, False, "noCompression", False)
+    param = pir.MulPir.generateParameter(config, g)
+    oparam = opir.generate_parameter(opir.IndexPirConfig(100, 8, 2, 1, False, "noCompression", False), o.n, o.t)
+    database = [bytes(rng.randrange(256) for _ in range(8)) for _ in range(100)]
+    server = pir.MulPirServer(param, g, [pir.MulPirServer.process(database, g, param)])
+    odb = opir.process_database(o, oparam, database)
+    clients = []
+    for c in range(4):
+        sk, relin = o.keygen(60 + c)
+        key, okeys = load_keys(g, o, sk, relin, param.evaluationKeyConfig.galoisElements, seed=300 + 10 * c)
+        clients.append((sk, relin, key, okeys))
+    for round_ in range(2):
+        for c, (sk, relin, key, okeys) in enumerate(clients):
+            index = (7 * c + round_) % 100
+            query = opir.generate_query(o, oparam, [index], sk, 400 + 10 * c + round_)
+            expected = opir.compute_response(o, query, 1, okeys, relin, [odb], oparam)
+            got = server.computeResponse(np.stack(query), key, indicesCount=1)
+            for chunk in range(server.chunkCount):
+                assert np.array_equal(got[0, chunk], expected[0][chunk])
+    for _, _, key, _ in clients:
+        key.close()
+    g.close()
+
+
 def test_captured_response_graph_follows_key_changes_and_concurrent_callers():
     """The host entry point replays the response pipeline of a (database, key, shape) triple as a CUDA graph
     (csrc/pir.cu).  Replacing a Galois key must invalidate the capture (its device pointers are baked into the graph);
