@@ -28,7 +28,7 @@ struct hecuda_pir_database {
     const hecuda_context *owner = nullptr;
     u64 *d_plain = nullptr;              // count x L x N, Eval format; all-zero rows where present == 0
     u32 *d_plain32 = nullptr;            // the same rows as uint32 instead, when every ciphertext modulus is below 2^31
-    unsigned char *d_present = nullptr;  // count
+    unsigned char *d_present = nullptr;  // count; null = all present
     int64_t count = 0;
 };
 
@@ -587,10 +587,10 @@ int32_t hecuda_pir_database_create(const hecuda_context *h, const uint64_t *plai
     db->owner = h;
     db->count = count;
     cudaError_t e = cudaMalloc(&db->d_plain, row_words * count * sizeof(u64));
-    if (e == cudaSuccess) e = cudaMalloc(&db->d_present, (size_t)count);
-    if (e == cudaSuccess)
-        e = present ? upload(db->d_present, present, (size_t)count)
-                    : fill(db->d_present, 1, (size_t)count);
+    if (e == cudaSuccess && present) {  // no flags at all = every plaintext present: the scan then runs without the test
+        e = cudaMalloc(&db->d_present, (size_t)count);
+        if (e == cudaSuccess) e = upload(db->d_present, present, (size_t)count);
+    }
     if (e == cudaSuccess) {
         if (eval_format) {
             e = upload(db->d_plain, plaintexts, row_words * count * sizeof(u64));
