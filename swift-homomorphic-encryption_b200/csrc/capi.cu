@@ -341,7 +341,8 @@ int32_t hecuda_bind_host_to_device(int32_t device, int32_t *numa_node, int32_t *
     CPU_ZERO(&want);
     if (sched_getaffinity(0, sizeof(current), &current) != 0) return HECUDA_OK;  // nothing to intersect with: leave as is
     int picked = 0;
-    for (char *tok = std::strtok(list, ",\n"); tok; tok = std::strtok(nullptr, ",\n")) {
+    char *save = nullptr;
+    for (char *tok = strtok_r(list, ",\n", &save); tok; tok = strtok_r(nullptr, ",\n", &save)) {
         int lo = 0, hi = 0;
         const int fields = std::sscanf(tok, "%d-%d", &lo, &hi);
         if (fields < 1) continue;
