@@ -85,7 +85,7 @@ int32_t hecuda_context_create(int64_t poly_degree, const uint64_t *coefficient_m
  * moduli below 2^30, m~ = 2^16, rnsCorrectionFactor 2^30 - 20405, 29-bit Bsk primes.  Buffers of the hecuda_u32_* entry
  * points are uint32_t in the same layouts as their uint64_t counterparts; residues cross PCIe as 4 bytes and the NTT
  * butterflies run in 32-bit arithmetic.  The uint64_t entry points also accept such a context (64-bit storage of the
- * same residues); the application drivers (MulPir / PNNS / codec / decrypt) are uint64_t-only. */
+ * same residues); the application drivers (MulPir / PNNS), the codec and decryption are uint64_t-only. */
 int32_t hecuda_context_create_u32(int64_t poly_degree, const uint32_t *coefficient_moduli, int32_t moduli_count,
                                   uint32_t plaintext_modulus, hecuda_context **out);
 int32_t hecuda_context_word_bits(const hecuda_context *ctx, int32_t *bits); /* 64 or 32 */
@@ -413,6 +413,15 @@ int32_t hecuda_u32_bfv_relinearize(const hecuda_context *ctx, const hecuda_evk *
                                    uint32_t *out, int64_t batch);
 int32_t hecuda_u32_bfv_mod_switch_down(const hecuda_context *ctx, const uint32_t *ct, int32_t poly_count, int32_t moduli_count,
                                        uint32_t *out, int64_t batch);
+int32_t hecuda_u32_bfv_multiply_relinearize(const hecuda_context *ctx, const hecuda_evk *evk, const uint32_t *lhs,
+                                            const uint32_t *rhs, int32_t mod_switch, uint32_t *out, int64_t batch);
+int32_t hecuda_u32_bfv_relinearize_mod_switch_down(const hecuda_context *ctx, const hecuda_evk *evk, const uint32_t *ct3,
+                                                   int32_t moduli_count, uint32_t *out, int64_t batch);
+int32_t hecuda_u32_evk_set_galois_key(hecuda_evk *evk, uint32_t element, const uint32_t *key);
+int32_t hecuda_u32_bfv_apply_galois(const hecuda_context *ctx, const hecuda_evk *evk, const uint32_t *ct, int32_t moduli_count,
+                                    uint32_t element, uint32_t *out, int64_t batch);
+int32_t hecuda_u32_bfv_inner_product(const hecuda_context *ctx, const uint32_t *lhs, const uint32_t *rhs, uint32_t *out,
+                                     int64_t pair_count, int64_t group_count);
 int32_t hecuda_u32_rnstool_lift_q_to_qbsk(const hecuda_context *ctx, const uint32_t *polys, uint32_t *out, int64_t poly_count);
 int32_t hecuda_u32_rnstool_floor_qbsk_to_q(const hecuda_context *ctx, const uint32_t *polys, uint32_t *out, int64_t poly_count);
 

@@ -1182,6 +1182,44 @@ int32_t hecuda_u32_bfv_mod_switch_down(const hecuda_context *h, const uint32_t *
     Io32Scope scope;
     return hecuda_bfv_mod_switch_down(h, reinterpret_cast<const uint64_t *>(ct), polys, l, reinterpret_cast<uint64_t *>(out), batch);
 }
+int32_t hecuda_u32_bfv_multiply_relinearize(const hecuda_context *h, const hecuda_evk *evk, const uint32_t *lhs, const uint32_t *rhs,
+                                            int32_t mod_switch, uint32_t *out, int64_t batch) {
+    int32_t rc = need_word32(h);
+    if (rc) return rc;
+    Io32Scope scope;
+    return hecuda_bfv_multiply_relinearize(h, evk, reinterpret_cast<const uint64_t *>(lhs), reinterpret_cast<const uint64_t *>(rhs),
+                                           mod_switch, reinterpret_cast<uint64_t *>(out), batch);
+}
+int32_t hecuda_u32_bfv_relinearize_mod_switch_down(const hecuda_context *h, const hecuda_evk *evk, const uint32_t *ct3, int32_t l,
+                                                   uint32_t *out, int64_t batch) {
+    int32_t rc = need_word32(h);
+    if (rc) return rc;
+    Io32Scope scope;
+    return hecuda_bfv_relinearize_mod_switch_down(h, evk, reinterpret_cast<const uint64_t *>(ct3), l,
+                                                  reinterpret_cast<uint64_t *>(out), batch);
+}
+int32_t hecuda_u32_evk_set_galois_key(hecuda_evk *evk, uint32_t element, const uint32_t *key) {
+    if (!evk || !key) return fail(HECUDA_ERR_INVALID_ARGUMENT, "null argument");
+    int32_t rc = need_word32(evk->owner);
+    if (rc) return rc;
+    std::vector<uint64_t> wide(key, key + evk->words);  // setup-time: widened on the host
+    return hecuda_evk_set_galois_key(evk, element, wide.data());
+}
+int32_t hecuda_u32_bfv_apply_galois(const hecuda_context *h, const hecuda_evk *evk, const uint32_t *ct, int32_t l, uint32_t element,
+                                    uint32_t *out, int64_t batch) {
+    int32_t rc = need_word32(h);
+    if (rc) return rc;
+    Io32Scope scope;
+    return hecuda_bfv_apply_galois(h, evk, reinterpret_cast<const uint64_t *>(ct), l, element, reinterpret_cast<uint64_t *>(out), batch);
+}
+int32_t hecuda_u32_bfv_inner_product(const hecuda_context *h, const uint32_t *lhs, const uint32_t *rhs, uint32_t *out, int64_t pairs,
+                                     int64_t groups) {
+    int32_t rc = need_word32(h);
+    if (rc) return rc;
+    Io32Scope scope;
+    return hecuda_bfv_inner_product(h, reinterpret_cast<const uint64_t *>(lhs), reinterpret_cast<const uint64_t *>(rhs),
+                                    reinterpret_cast<uint64_t *>(out), pairs, groups);
+}
 int32_t hecuda_u32_rnstool_lift_q_to_qbsk(const hecuda_context *h, const uint32_t *polys, uint32_t *out, int64_t count) {
     int32_t rc = need_word32(h);
     if (rc) return rc;

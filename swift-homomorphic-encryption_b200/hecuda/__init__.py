@@ -49,6 +49,11 @@ SYMBOLS = {
     "hecuda_u32_evk_create": (C.c_int32, [_VP, _VP, C.POINTER(_VP)]),
     "hecuda_u32_bfv_relinearize": (C.c_int32, [_VP, _VP, _VP, C.c_int32, _VP, C.c_int64]),
     "hecuda_u32_bfv_mod_switch_down": (C.c_int32, [_VP, _VP, C.c_int32, C.c_int32, _VP, C.c_int64]),
+    "hecuda_u32_bfv_multiply_relinearize": (C.c_int32, [_VP, _VP, _VP, _VP, C.c_int32, _VP, C.c_int64]),
+    "hecuda_u32_bfv_relinearize_mod_switch_down": (C.c_int32, [_VP, _VP, _VP, C.c_int32, _VP, C.c_int64]),
+    "hecuda_u32_evk_set_galois_key": (C.c_int32, [_VP, C.c_uint32, _VP]),
+    "hecuda_u32_bfv_apply_galois": (C.c_int32, [_VP, _VP, _VP, C.c_int32, C.c_uint32, _VP, C.c_int64]),
+    "hecuda_u32_bfv_inner_product": (C.c_int32, [_VP, _VP, _VP, _VP, C.c_int64, C.c_int64]),
     "hecuda_u32_rnstool_lift_q_to_qbsk": (C.c_int32, [_VP, _VP, _VP, C.c_int64]),
     "hecuda_u32_rnstool_floor_qbsk_to_q": (C.c_int32, [_VP, _VP, _VP, C.c_int64]),
     "hecuda_bfv_relinearize_mod_switch_down": (C.c_int32, [_VP, _VP, _VP, C.c_int32, _VP, C.c_int64]),
@@ -672,6 +677,10 @@ def _host32(a) -> np.ndarray:
 class EvaluationKey32:
     """EvaluationKey<Bfv<UInt32>>: relinearization key as uint32 (L x 2 x K x N, Eval)."""
 
+    def setGaloisKey(self, element: int, key):
+        k = _host32(key)
+        _check(load_library().hecuda_u32_evk_set_galois_key(self._h, int(element), _ptr(k)))
+
     def __init__(self, context: Context, relin_key):
         h = C.c_void_p()
         k = _host32(relin_key)
@@ -692,6 +701,39 @@ class EvaluationKey32:
 
 class Bfv32:
     """The Bfv<UInt32> data path (uint32 arrays, Context(..., scalar=np.uint32)): same shapes as the Bfv methods."""
+
+    @staticmethod
+    def mulRelinearize(context: Context, lhs, rhs, key: "EvaluationKey32", modSwitchDown: bool = False):
+        a, b = _host32(lhs), _host32(rhs)
+        L, n = context.L, context.degree
+        out = np.empty(a.shape[:-3] + (2, L - 1 if modSwitchDown else L, n), dtype=np.uint32)
+        _check(load_library().hecuda_u32_bfv_multiply_relinearize(context._h, key._h, _ptr(a), _ptr(b), 1 if modSwitchDown else 0,
+                                                                  _ptr(out), a.size // (2 * L * n)))
+        return out
+
+    @staticmethod
+    def relinearizeModSwitchDown(context: Context, ciphertext, key: "EvaluationKey32"):
+        c = _host32(ciphertext)
+        l, n = c.shape[-2], context.degree
+        out = np.empty(c.shape[:-3] + (2, l - 1, n), dtype=np.uint32)
+        _check(load_library().hecuda_u32_bfv_relinearize_mod_switch_down(context._h, key._h, _ptr(c), l, _ptr(out), c.size // (3 * l * n)))
+        return out
+
+    @staticmethod
+    def applyGalois(context: Context, ciphertext, element: int, key: "EvaluationKey32"):
+        c = _host32(ciphertext)
+        l, n = c.shape[-2], context.degree
+        out = np.empty_like(c)
+        _check(load_library().hecuda_u32_bfv_apply_galois(context._h, key._h, _ptr(c), l, int(element), _ptr(out), c.size // (2 * l * n)))
+        return out
+
+    @staticmethod
+    def innerProductCiphertexts(context: Context, lhs, rhs):
+        a, b = _host32(lhs), _host32(rhs)  # (groups, pairs, 2, L, N)
+        L, n = context.L, context.degree
+        out = np.empty((a.shape[0], 3, L, n), dtype=np.uint32)
+        _check(load_library().hecuda_u32_bfv_inner_product(context._h, _ptr(a), _ptr(b), _ptr(out), a.shape[1], a.shape[0]))
+        return out
 
     @staticmethod
     def forwardNtt(context: Context, polys, base: int = BASE_Q):

@@ -102,3 +102,31 @@ def test_u64_entry_points_refuse_nothing_but_u32_entry_points_need_a_32_bit_cont
     x = np.zeros((1, 2, n), dtype=np.uint32)
     with pytest.raises(hecuda.HeError):
         hecuda.Bfv32.forwardNtt(g64, x)
+
+
+def test_fused_calls_galois_and_inner_product_u32():
+    """The remaining uint32 entry points: multiply+relinearize(+modSwitchDown), relinearize+modSwitchDown, applyGalois and
+    the ct x ct inner product, against the 32-bit oracle."""
+    n, t = 4096, 17
+    moduli, g, o = setup(n, PIR_MODULI, t)
+    L = len(moduli) - 1
+    a = orc.fill_uniform(21, moduli[:L], n, 4 * 2 * L).reshape(4, 2, L, n)
+    b = orc.fill_uniform(22, moduli[:L], n, 4 * 2 * L).reshape(4, 2, L, n)
+    sk, rk = o.keygen(5)
+    key = hecuda.EvaluationKey32(g, rk.astype(np.uint32))
+    prod = o.mul(a, b)
+    relin = o.relinearize(prod, rk)
+    a32, b32 = a.astype(np.uint32), b.astype(np.uint32)
+    assert np.array_equal(hecuda.Bfv32.mulRelinearize(g, a32, b32, key).astype(np.uint64), relin)
+    assert np.array_equal(hecuda.Bfv32.mulRelinearize(g, a32, b32, key, modSwitchDown=True).astype(np.uint64), o.mod_switch_down(relin))
+    assert np.array_equal(hecuda.Bfv32.relinearizeModSwitchDown(g, prod.astype(np.uint32), key).astype(np.uint64),
+                          o.mod_switch_down(relin))
+    element = 3
+    gk = o.galois_keygen(77, sk, element)
+    key.setGaloisKey(element, gk.astype(np.uint32))
+    want = o.apply_galois(a[:2], element, gk)
+    assert np.array_equal(hecuda.Bfv32.applyGalois(g, a32[:2], element, key).astype(np.uint64), want)
+    lhs, rhs = a.reshape(2, 2, 2, L, n), b.reshape(2, 2, 2, L, n)
+    assert np.array_equal(hecuda.Bfv32.innerProductCiphertexts(g, lhs.astype(np.uint32), rhs.astype(np.uint32)).astype(np.uint64),
+                          o.inner_product(lhs, rhs))
+    key.close()
