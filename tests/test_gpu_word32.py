@@ -130,3 +130,38 @@ def test_fused_calls_galois_and_inner_product_u32():
     assert np.array_equal(hecuda.Bfv32.innerProductCiphertexts(g, lhs.astype(np.uint32), rhs.astype(np.uint32)).astype(np.uint64),
                           o.inner_product(lhs, rhs))
     key.close()
+
+
+def test_mulpir_on_a_32_bit_context():
+    """MulPir computeResponse at the reference's default PIR parameters (n_4096_logq_27_28_28, t = 17) with Bfv<UInt32>'s
+    constants: the application driver runs on the 32-bit context through the uint64 entry points (64-bit storage of the
+    same residues); reply bit-exact with the 32-bit oracle and decrypting to the database entry."""
+    import random
+
+    from hecuda import pir
+    from oracle import pir_oracle as opir
+
+    n, t = 4096, 17
+    moduli, g, o = setup(n, PIR_MODULI, t)
+    entries, entry_size = 30000, 1
+    rng = random.Random(entries)
+    config = pir.IndexPirConfig(entries, entry_size, 2, 1, True, "hybridCompression", False)
+    param = pir.MulPir.generateParameter(config, g)
+    oparam = opir.generate_parameter(opir.IndexPirConfig(entries, entry_size, 2, 1, True, "hybridCompression", False), n, t)
+    database = [bytes(rng.randrange(256) for _ in range(entry_size)) for _ in range(entries)]
+    sk, relin = o.keygen(13)
+    key = hecuda.EvaluationKey(g, relin)
+    okeys = {}
+    for i, e in enumerate(param.evaluationKeyConfig.galoisElements):
+        okeys[e] = o.galois_keygen(100 + i, sk, e)
+        key.setGaloisKey(e, okeys[e])
+    server = pir.MulPirServer(param, g, [pir.MulPirServer.process(database, g, param)])
+    index = rng.randrange(entries)
+    query = opir.generate_query(o, oparam, [index], sk, 900)
+    got = server.computeResponse(np.stack(query), key)
+    reply = [[got[0, c] for c in range(server.chunkCount)]]
+    assert opir.decrypt_response(o, oparam, reply, [index], sk) == [database[index]]
+    expected = opir.compute_response(o, query, 1, okeys, relin, [opir.process_database(o, oparam, database)], oparam)
+    for c in range(server.chunkCount):
+        assert np.array_equal(got[0, c], expected[0][c])
+    key.close()
