@@ -188,6 +188,46 @@ struct Bfv {
         ct = std::move(out);
     }
 
+    // mulAssign + relinearize (+ modSwitchDown when modSwitch) for a whole batch in one device pass -- the sequence
+    // the reference's callers run back to back (RlweBenchmark.swift:387-493, PirUtil.swift:447-480).  The 3-poly
+    // product stays on the device; results equal the three separate calls.
+    static void mulRelinearizeAssign(std::vector<Ciphertext> &lhs, const std::vector<Ciphertext> &rhs, const EvaluationKey &key,
+                                     bool modSwitch = false) {
+        if (lhs.size() != rhs.size()) throw HeError(HeError::incompatibleCiphertexts, "batch sizes differ");
+        if (lhs.empty()) return;
+        for (size_t i = 0; i < lhs.size(); ++i) validateMultiply(lhs[i], rhs[i]);
+        const auto ctx = lhs[0].context;
+        if (!(*ctx == *key.context)) throw HeError(HeError::invalidContext, "key belongs to another context");
+        const int rows = lhs[0].moduliCount;
+        if (modSwitch && rows < 2) throw HeError(HeError::invalidPolyContext, "no next context");
+        const int outRows = modSwitch ? rows - 1 : rows;
+        const size_t n = lhs[0].polyWords() / (size_t)rows;
+        const size_t in_words = 2 * lhs[0].polyWords(), out_words = 2 * (size_t)outRows * n;
+        std::vector<uint64_t> a(in_words * lhs.size()), b(in_words * lhs.size()), o(out_words * lhs.size());
+        for (size_t i = 0; i < lhs.size(); ++i) {
+            std::copy(lhs[i].data.begin(), lhs[i].data.end(), a.begin() + i * in_words);
+            std::copy(rhs[i].data.begin(), rhs[i].data.end(), b.begin() + i * in_words);
+        }
+        check(hecuda_bfv_multiply_relinearize(ctx->handle(), key.handle(), a.data(), b.data(), modSwitch ? 1 : 0, o.data(),
+                                              (int64_t)lhs.size()));
+        for (size_t i = 0; i < lhs.size(); ++i) {
+            lhs[i].moduliCount = outRows;
+            lhs[i].data.assign(o.begin() + i * out_words, o.begin() + (i + 1) * out_words);
+        }
+    }
+
+    // relinearize + modSwitchDown in one device pass (3 polys at `moduliCount` rows -> 2 polys at one row fewer)
+    static void relinearizeModSwitchDown(Ciphertext &ct, const EvaluationKey &key) {
+        if (ct.correctionFactor != 1) throw HeError(HeError::invalidCiphertext, "correction factor must be 1");
+        if (ct.polyCount != 3) throw HeError(HeError::invalidCiphertext, "ciphertext must have three polys when relinearizing");
+        if (!(*ct.context == *key.context)) throw HeError(HeError::invalidContext, "key belongs to another context");
+        if (ct.moduliCount < 2) throw HeError(HeError::invalidPolyContext, "no next context");
+        Ciphertext out(ct.context, 2, ct.moduliCount - 1);
+        check(hecuda_bfv_relinearize_mod_switch_down(ct.context->handle(), key.handle(), ct.data.data(), ct.moduliCount,
+                                                     out.data.data(), 1));
+        ct = std::move(out);
+    }
+
     // Bfv.modSwitchDownToSingle (HeScheme.swift:1481-1485)
     static void modSwitchDownToSingle(Ciphertext &ct) {
         while (ct.moduliCount > 1) modSwitchDown(ct);

@@ -38,6 +38,24 @@ int main(int argc, char **argv) {
         lhs.push_back(x);
         rhs.push_back(y);
     }
+    // fused paths: multiply+relinearize(+modSwitchDown) over the batch, relinearize+modSwitchDown on a product
+    {
+        auto l1 = lhs, l2 = lhs;
+        he::Bfv::mulRelinearizeAssign(l1, rhs, evk, false);
+        he::Bfv::mulRelinearizeAssign(l2, rhs, evk, true);
+        for (int i = 0; i < batch; ++i) {
+            failures += l1[i].polyCount != 2 || l1[i].moduliCount != L || l1[i].data.size() != 2 * pw ||
+                        std::memcmp(l1[i].data.data(), relin.data() + i * 2 * pw, 2 * pw * 8) != 0;
+            failures += l2[i].moduliCount != L - 1 || l2[i].data.size() != 2 * (pw - n) ||
+                        std::memcmp(l2[i].data.data(), switched.data() + i * 2 * (pw - n), 2 * (pw - n) * 8) != 0;
+        }
+        he::Ciphertext prod(ctx, 3, L);
+        std::copy(product.begin(), product.begin() + 3 * pw, prod.data.begin());
+        he::Bfv::relinearizeModSwitchDown(prod, evk);
+        failures += prod.polyCount != 2 || prod.moduliCount != L - 1 ||
+                    std::memcmp(prod.data.data(), switched.data(), 2 * (pw - n) * 8) != 0;
+        try { he::Ciphertext two(ctx, 2, L); he::Bfv::relinearizeModSwitchDown(two, evk); ++failures; } catch (const he::HeError &e) { failures += e.kind != he::HeError::invalidCiphertext; }
+    }
     // single-ciphertext path
     he::Ciphertext one = lhs[0];
     he::Bfv::mulAssign(one, rhs[0]);
